@@ -1,0 +1,208 @@
+/*
+ * tzddpc.h -- C ABI of libtzddpc.so: the B200 (sm_100a) hot path of TZDDPC.
+ *
+ * The reference (rssalessio/TZDDPC) is pure Python; its hot path calls into the
+ * third-party packages pyzonotope / pydatadrivenreachability / cvxpy.  Each entry
+ * point below replaces one of those call sites (cited as file:line relative to the
+ * reference root) and is what a ctypes / torch-custom-op binding on the reference
+ * side would bind.
+ *
+ * Conventions
+ *   - return 0 on success, a negative TZ_E* code otherwise; nothing throws across the ABI;
+ *     tz_last_error() returns a thread-local message for the last failing call;
+ *   - every `double*` / `int32_t*` is CALLER-OWNED DEVICE memory unless the name ends in
+ *     `_host`; the library allocates nothing on the device except inside
+ *     tz_program_create (freed by tz_program_destroy);
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*), no implicit sync;
+ *   - thread-safe: no mutable globals; per-scenario failures go to `status[S]`
+ *     (TZ_STATUS_*), never to the return code;
+ *   - arithmetic is IEEE fp64 throughout.
+ *
+ * Layouts
+ *   SoA ("scenario-fastest"), used by the fused closed-loop path: a batch of S vectors of
+ *       length d is a d x S row-major array, element (i, s) at [i*S + s].
+ *   AoS ("one zonotope per block"), used by the stand-alone zonotope ops: a batch of S
+ *       zonotopes is S x n x (1+g) row-major, Z[s] = [c, G] with column 0 the centre.
+ */
+#ifndef TZDDPC_H
+#define TZDDPC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TZ_OK 0
+#define TZ_EINVAL (-22)    /* bad argument / shape                                  */
+#define TZ_ENOMEM (-12)    /* allocation failed                                     */
+#define TZ_ERANGE (-34)    /* program larger than every compiled kernel bucket      */
+#define TZ_ECUDA (-5)      /* CUDA runtime error (message in tz_last_error)         */
+
+/* per-scenario status written by the solve kernels */
+#define TZ_STATUS_OK 0
+#define TZ_STATUS_MAXITER 1     /* ADMM hit max_iter before eps                     */
+#define TZ_STATUS_INFEASIBLE 2  /* reference: raises 'Problem is unbounded', tzddpc/tzddpc.py:374-375 */
+#define TZ_STATUS_NONFINITE 3
+
+const char* tz_version(void);
+/* copies the calling thread's last error message, returns its length */
+size_t tz_last_error(char* buf, size_t cap);
+/* compute capability (major*10+minor) of the current device, or a negative error */
+int tz_device_cc(void);
+
+/* ------------------------------------------------------------------------------------
+ * Parametric per-step program (the canonicalised form of tzddpc/tzddpc.py:132-241).
+ *
+ *   minimise   0.5 z'Pz + (q0 + Qp p)'z + sum_i wabs_i |(Az)_i - kink0_i - r_i(p)| + c0(p)
+ *   subject to l0 + r(p) <= A z <= u0 + r(p),      r(p) = R [1; p; alpha(p)],
+ *              alpha_j(p) = |Bt_j p + gam_j|,       p = [xbar0; e0]  (tzddpc/tzddpc.py:155-157)
+ *   feasible (parameter-only rows, e.g. xbar0 + e0 in X) iff  Rchk [1; p; alpha] <= 0
+ *   c0(p) = cc [1; p; alpha] + p' CC2 p
+ *
+ * All arrays are HOST pointers, row-major, unscaled; D, E, c are the Ruiz scalings
+ * (z = D zbar, Abar = E A D, Pbar = c D P D).  Rows with wabs > 0 must come first.
+ * ------------------------------------------------------------------------------------ */
+typedef struct TzProgramDesc {
+  int32_t n, m, horizon;      /* dim_x, dim_u, N                                          */
+  int32_t nv, nz, nc;         /* N*m decision inputs, nv + epigraph variables, rows       */
+  int32_t npar, na, nchk;     /* 2n, #alpha atoms, #parameter-only check rows             */
+  int32_t nkink;              /* rows [0, nkink) carry an |.| cost                         */
+  int32_t g1;                 /* generators of Ze[1] (tzddpc/tzddpc.py:205-207,377)       */
+  int32_t nterms;             /* nnz of the Ze[1] term table                              */
+  const double *P, *q0, *Qp;  /* nz*nz, nz, nz*npar                                       */
+  const double *A;            /* nc*nz                                                    */
+  const double *l0, *u0, *kink0, *wabs;   /* nc each (+-inf allowed in l0/u0)             */
+  const double *R;            /* nc*(1+npar+na)                                           */
+  const double *Bt, *gam;     /* na*npar, na                                              */
+  const double *Rchk;         /* nchk*(1+npar+na)                                         */
+  const double *cc, *CC2;     /* 1+npar+na, npar*npar                                     */
+  const double *XB;           /* (N+1)n * (1+nv+npar): xbar_0..xbar_N = XB [1; v; p]      */
+  const int32_t *ze1_ptr;     /* n(1+g1)+1 : CSR over the entries of Ze[1].Z, row-major   */
+  const int32_t *ze1_idx;     /* nterms: index into w = [1; v; p]                         */
+  const double *ze1_val;      /* nterms                                                   */
+  const double *D, *E;        /* nz, nc                                                   */
+  double c;                   /* cost scaling                                             */
+  const double *K;            /* m*n feedback gain theta.K (examples/2.pulley_sim.py:91)  */
+} TzProgramDesc;
+
+typedef struct TzProgram TzProgram;   /* opaque */
+
+int tz_program_create(const TzProgramDesc* desc, TzProgram** out);
+void tz_program_destroy(TzProgram* prog);
+/* which compiled kernel bucket serves this program: writes "NZxNCx..." into buf */
+int tz_program_bucket(const TzProgram* prog, char* buf, size_t cap);
+
+typedef struct TzSolverOpts {
+  double rho;        /* base ADMM penalty (scaled problem)         default 0.1  */
+  double rho_active; /* multiplier for rows detected active        default 100  */
+  double rho_inactive;/* multiplier for rows detected inactive     default 0.1  */
+  double sigma;      /* proximal weight                            default 1e-6 */
+  double alpha;      /* over-relaxation                            default 1.6  */
+  double eps_abs, eps_rel;   /*                                     default 1e-6 */
+  int32_t max_iter;  /*                                            default 4000 */
+  int32_t check_every;/* residual check period                     default 4    */
+  int32_t polish;    /* masked augmented-Lagrangian polish on/off  default 1    */
+  int32_t warm_start;/* reuse (z, y) from the `warm` buffer        default 0    */
+} TzSolverOpts;
+
+void tz_solver_opts_default(TzSolverOpts* o);
+
+/* ------------------------------------------------------------------------------------
+ * tz_solve: batched replacement of TZDDPC.solve(xbar0, e0), tzddpc/tzddpc.py:357-377.
+ *   in : xbar0, e0           n x S   (SoA)
+ *   out: cost                S
+ *        v                   (N*m) x S
+ *        xbar_traj           ((N+1)*n) x S
+ *        ze1                 (n*(1+g1)) x S   Ze[1].Z, entry (r, j) at row r*(1+g1)+j
+ *        status, iters       S   (int32)
+ *   warm: (nz + nc) x S scratch carrying (zbar, ybar) between calls, or NULL
+ *   any of cost / v / xbar_traj / ze1 / iters may be NULL (not written).
+ * ------------------------------------------------------------------------------------ */
+int tz_solve(const TzProgram* prog, const TzSolverOpts* opts, int64_t S,
+             const double* xbar0, const double* e0,
+             double* cost, double* v, double* xbar_traj, double* ze1,
+             int32_t* status, int32_t* iters, double* warm, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * tz_closed_loop_step: one fused closed-loop step for S scenarios
+ * (examples/2.pulley_sim.py:81-96 ; examples/3.5dimsystem_sim.py:73-89):
+ *     (cost, v, xbar_traj, Ze1) = solve(xbar, e)
+ *     u = K e + v[0];  x+ = A_true x + B_true u + w;  xbar+ = xbar_traj[1];  e+ = x+ - xbar+
+ *   x, xbar, e    n x S, updated IN PLACE
+ *   noise         n x S   the realisation w_t (an input: W.sample(), :92)
+ *   A_true,B_true device n*n, n*m row-major (the simulated plant)
+ *   u_out         m x S or NULL
+ *   stats         TZ_NSTATS doubles accumulated with atomics, or NULL:
+ *                 [sum |x+|_2, sum |x+|_2^2, sum cost, #infeasible, #maxiter, sum iters, #X-violations, S]
+ *   scenarios whose status is INFEASIBLE/NONFINITE keep their state unchanged.
+ * ------------------------------------------------------------------------------------ */
+#define TZ_NSTATS 8
+int tz_closed_loop_step(const TzProgram* prog, const TzSolverOpts* opts, int64_t S,
+                        double* x, double* xbar, double* e, const double* noise,
+                        const double* A_true, const double* B_true,
+                        double* cost, double* v, double* xbar_traj, double* ze1, double* u_out,
+                        int32_t* status, int32_t* iters, double* warm, double* stats, void* stream);
+
+/* Same step with HOST buffers (pinned or pageable): H2D of (x, xbar, e, noise), the fused
+ * kernel, D2H of every non-NULL output, chunked over `nchunks` internal streams so that
+ * copies overlap compute; synchronises before returning.  `dev_scratch` is caller-owned
+ * device memory of at least tz_closed_loop_step_host_scratch_bytes(prog, S). */
+size_t tz_closed_loop_step_host_scratch_bytes(const TzProgram* prog, int64_t S);
+int tz_closed_loop_step_host(const TzProgram* prog, const TzSolverOpts* opts, int64_t S,
+                             double* x_host, double* xbar_host, double* e_host, const double* noise_host,
+                             const double* A_true_host, const double* B_true_host,
+                             double* cost_host, double* v_host, double* xbar_traj_host, double* ze1_host,
+                             int32_t* status_host, void* dev_scratch, int32_t nchunks);
+
+/* ------------------------------------------------------------------------------------
+ * Stand-alone zonotope ops (AoS batches).
+ * ------------------------------------------------------------------------------------ */
+
+/* Interval hull  c -+ sum_j |G[:, j]|   (Zonotope.interval, tzddpc/tzddpc.py:191-197).
+ * Z: S x n x (1+g);  lo, hi: S x n. */
+int tz_interval_hull(int64_t S, int32_t n, int32_t g, const double* Z, double* lo, double* hi, void* stream);
+
+/* MatrixZonotope x Zonotope (+ Zonotope)  (tzddpc/tzddpc.py:175-176,181,185,205):
+ *   Zout[s] = [C Z_s, G_1 Z_s, ..., G_N Z_s]  (+) W      with Z_s = [c, G]  (p x (1+g))
+ * C: n x p, Gm: N x n x p (shared by all scenarios when model_stride == 0, else per scenario
+ * with C at C + s*n*p and Gm at Gm + s*N*n*p).  W: n x (1+gW) or NULL (gW = 0).
+ * Zout: S x n x ((N+1)(1+g) + gW). */
+int tz_reach_step(int64_t S, int32_t n, int32_t p, int32_t N, int32_t g, int32_t gW,
+                  const double* C, const double* Gm, int32_t per_scenario_model,
+                  const double* Z, const double* W, double* Zout, void* stream);
+
+/* Girard order reduction (Zonotope.reduce / MatrixZonotope.reduce, tzddpc/tzddpc.py:126-128,
+ * examples/1.double_integrator_sim.py:170):
+ *   drop all-zero generators; if g' <= order*n keep; else box the g' - floor(n(order-1))
+ *   generators of smallest metric (ties: lowest index) into diag(sum|.|), kept ones first
+ *   in original order.  metric: 0 = l1 - linf, 1 = l1, 2 = l2.
+ * Z: S x n x (1+g) -> Zout: S x n x (1+gout_cap), gout[s] = generators written (<= gout_cap,
+ * columns beyond are zero).  gout_cap >= max(n*order rounded up, g when no reduction). */
+int tz_girard_reduce(int64_t S, int32_t n, int32_t g, double order, int32_t metric,
+                     const double* Z, int32_t gout_cap, double* Zout, int32_t* gout, void* stream);
+
+/* Data-driven model  M_Sigma = (X1 - M_w) pinv([X0; U0])  (tzddpc/tzddpc.py:81-83) followed by
+ * tzddpc/tzddpc.py:119-128 (MdataK = Mdata [I;K], Mdelta, order-1 reduction), batched over S datasets:
+ *   X: S x T x n, U: S x T x m (as Data.x / Data.u), WZ: n x (1+gW) shared, K: S x m x n or NULL
+ *   AB    S x n x (n+m)      centre of Mdata
+ *   dAB   S x n x (n+m)      box of Mdata/Mdelta after reduce(1):  sum_i |G_i|
+ *   dK    S x n x n          box of MdataK after reduce(1) (needs K)
+ *   Pinv  S x (T-1) x (n+m)  pinv([X0;U0]) (optional, NULL to skip)
+ * status[s] = NONFINITE when the Gram matrix is not positive definite. */
+int tz_identify(int64_t S, int32_t T, int32_t n, int32_t m, int32_t gW,
+                const double* X, const double* U, const double* WZ, const double* K,
+                double* AB, double* dAB, double* dK, double* Pinv, int32_t* status, void* stream);
+
+/* Generic batched ADMM QP on an explicit instance batch (the solver stage alone):
+ *   minimise 0.5 z'Pz + q_s'z  s.t. l_s <= A z <= u_s   with (P, A) from `prog`
+ *   q: nz x S, l,u: nc x S (SoA, unscaled);  z: nz x S, y: nc x S. */
+int tz_qp_solve(const TzProgram* prog, const TzSolverOpts* opts, int64_t S,
+                const double* q, const double* l, const double* u,
+                double* z, double* y, int32_t* status, int32_t* iters, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TZDDPC_H */

@@ -1,0 +1,140 @@
+"""ctypes binding of libtzddpc.so (include/tzddpc.h).  No fallback: if the library is
+missing the import of the hot path fails loudly."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+LIB_PATH = Path(__file__).resolve().parent / "lib" / "libtzddpc.so"
+
+TZ_OK = 0
+TZ_STATUS_OK, TZ_STATUS_MAXITER, TZ_STATUS_INFEASIBLE, TZ_STATUS_NONFINITE = 0, 1, 2, 3
+TZ_NSTATS = 8
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+
+class TzProgramDesc(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ("n", "m", "horizon", "nv", "nz", "nc", "npar", "na", "nchk", "nkink", "g1", "nterms")] + \
+               [(k, C.c_void_p) for k in ("P", "q0", "Qp", "A", "l0", "u0", "kink0", "wabs", "R", "Bt", "gam", "Rchk", "cc",
+                                          "CC2", "XB", "ze1_ptr", "ze1_idx", "ze1_val", "D", "E")] + \
+               [("c", C.c_double), ("K", C.c_void_p)]
+
+
+class TzSolverOpts(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("rho", "rho_active", "rho_inactive", "sigma", "alpha", "eps_abs", "eps_rel")] + \
+               [(k, C.c_int32) for k in ("max_iter", "check_every", "polish", "warm_start")]
+
+
+class TzddpcLibraryMissing(RuntimeError):
+    pass
+
+
+_lib = None
+
+# every symbol include/tzddpc.h declares (tests/test_abi.py checks the library exports all of them)
+EXPORTS = ["tz_version", "tz_last_error", "tz_device_cc", "tz_program_create", "tz_program_destroy", "tz_program_bucket",
+           "tz_solver_opts_default", "tz_solve", "tz_closed_loop_step", "tz_closed_loop_step_host_scratch_bytes",
+           "tz_closed_loop_step_host", "tz_interval_hull", "tz_reach_step", "tz_girard_reduce", "tz_identify",
+           "tz_qp_solve"]
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise TzddpcLibraryMissing(
+            f"{LIB_PATH} not found: the TZDDPC hot path has no CPU fallback. Build it with "
+            f"`python -m tzddpc_b200.build` (needs nvcc; cross-compiles for sm_100a without a GPU).")
+    L = C.CDLL(str(LIB_PATH))
+    vp, i64, i32, dbl = C.c_void_p, C.c_int64, C.c_int32, C.c_double
+    L.tz_version.restype = C.c_char_p
+    L.tz_last_error.restype = C.c_size_t
+    L.tz_last_error.argtypes = [C.c_char_p, C.c_size_t]
+    L.tz_device_cc.restype = C.c_int
+    L.tz_program_create.restype = C.c_int
+    L.tz_program_create.argtypes = [C.POINTER(TzProgramDesc), C.POINTER(vp)]
+    L.tz_program_destroy.restype = None
+    L.tz_program_destroy.argtypes = [vp]
+    L.tz_program_bucket.restype = C.c_int
+    L.tz_program_bucket.argtypes = [vp, C.c_char_p, C.c_size_t]
+    L.tz_solver_opts_default.restype = None
+    L.tz_solver_opts_default.argtypes = [C.POINTER(TzSolverOpts)]
+    L.tz_solve.restype = C.c_int
+    L.tz_solve.argtypes = [vp, C.POINTER(TzSolverOpts), i64] + [vp] * 10
+    L.tz_closed_loop_step.restype = C.c_int
+    L.tz_closed_loop_step.argtypes = [vp, C.POINTER(TzSolverOpts), i64] + [vp] * 16
+    L.tz_closed_loop_step_host_scratch_bytes.restype = C.c_size_t
+    L.tz_closed_loop_step_host_scratch_bytes.argtypes = [vp, i64]
+    L.tz_closed_loop_step_host.restype = C.c_int
+    L.tz_closed_loop_step_host.argtypes = [vp, C.POINTER(TzSolverOpts), i64] + [vp] * 12 + [i32]
+    L.tz_interval_hull.restype = C.c_int
+    L.tz_interval_hull.argtypes = [i64, i32, i32, vp, vp, vp, vp]
+    L.tz_reach_step.restype = C.c_int
+    L.tz_reach_step.argtypes = [i64, i32, i32, i32, i32, i32, vp, vp, i32, vp, vp, vp, vp]
+    L.tz_girard_reduce.restype = C.c_int
+    L.tz_girard_reduce.argtypes = [i64, i32, i32, dbl, i32, vp, i32, vp, vp, vp]
+    L.tz_identify.restype = C.c_int
+    L.tz_identify.argtypes = [i64, i32, i32, i32, i32] + [vp] * 10
+    L.tz_qp_solve.restype = C.c_int
+    L.tz_qp_solve.argtypes = [vp, C.POINTER(TzSolverOpts), i64] + [vp] * 8
+    _lib = L
+    return L
+
+
+def last_error() -> str:
+    buf = C.create_string_buffer(512)
+    lib().tz_last_error(buf, 512)
+    return buf.value.decode(errors="replace")
+
+
+def check(rc: int, what: str) -> None:
+    if rc != TZ_OK:
+        raise RuntimeError(f"{what} failed (code {rc}): {last_error()}")
+
+
+def _host(a, dtype) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=dtype))
+
+
+class Program:
+    """Owner of a TzProgram handle built from a tzddpc_b200.program.CompiledProgram."""
+
+    def __init__(self, prog, K: np.ndarray):
+        L = lib()
+        order = np.argsort(-(prog.wabs > 0).astype(np.int64), kind="stable")       # |.|-cost rows first
+        keep = {}
+        f64 = lambda a: _host(a, np.float64)                                        # noqa: E731
+        A, l0, u0 = f64(prog.A[order]), f64(prog.l0[order]), f64(prog.u0[order])
+        kink0, wabs, R, E = f64(prog.kink0[order]), f64(prog.wabs[order]), f64(prog.R[order]), f64(prog.E[order])
+        arrs = dict(P=f64(prog.P), q0=f64(prog.q0), Qp=f64(prog.Qp), A=A, l0=l0, u0=u0, kink0=kink0, wabs=wabs, R=R,
+                    Bt=f64(prog.Bt), gam=f64(prog.gam), Rchk=f64(prog.Rchk), cc=f64(prog.cc), CC2=f64(prog.CC2),
+                    XB=f64(prog.XB), ze1_ptr=_host(prog.ze1_ptr, np.int32), ze1_idx=_host(prog.ze1_idx, np.int32),
+                    ze1_val=f64(prog.ze1_val), D=f64(prog.D), E=E, K=f64(K))
+        d = TzProgramDesc()
+        d.n, d.m, d.horizon, d.nv, d.nz, d.nc = prog.n, prog.m, prog.N, prog.nv, prog.nz, prog.nc
+        d.npar, d.na, d.nchk, d.nkink = prog.npar, prog.na, prog.Rchk.shape[0], int((prog.wabs > 0).sum())
+        d.g1, d.nterms, d.c = prog.g1, len(prog.ze1_idx), float(prog.c)
+        for k, a in arrs.items():
+            setattr(d, k, a.ctypes.data if a.size else None)
+        keep["arrs"] = arrs
+        h = C.c_void_p()
+        check(L.tz_program_create(C.byref(d), C.byref(h)), "tz_program_create")
+        self.handle = h
+        self.row_order = order
+        self.compiled = prog
+        buf = C.create_string_buffer(64)
+        L.tz_program_bucket(h, buf, 64)
+        self.bucket = buf.value.decode()
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                lib().tz_program_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass

@@ -1,0 +1,475 @@
+// Stand-alone batched zonotope kernels (AoS: one zonotope = one contiguous n x (1+g) block).
+//   tz_interval_hull   Zonotope.interval                      tzddpc/tzddpc.py:191-197
+//   tz_reach_step      MatrixZonotope * Zonotope (+ Zonotope)  tzddpc/tzddpc.py:175-176,181,185,205
+//   tz_girard_reduce   Zonotope.reduce / MatrixZonotope.reduce tzddpc/tzddpc.py:126-128,
+//                                                              examples/1.double_integrator_sim.py:170
+// All three are HBM-bound (1-2 flop per byte): a warp / CTA owns one zonotope, rows are
+// contiguous so every global access is a full-line coalesced access, the generator block is
+// staged once in shared memory and never re-read from HBM.
+#include "tz_common.cuh"
+
+namespace tz {
+
+// ---------------------------------------------------------------------------------------
+// interval hull: one warp per zonotope; lanes stride the columns of a row, shuffle-reduce.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) hull_kernel(int64_t S, int n, int g, const double* __restrict__ Z,
+                                                   double* __restrict__ lo, double* __restrict__ hi) {
+  const int lane = threadIdx.x & 31;
+  const int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (s >= S) return;
+  const int ld = 1 + g;
+  const double* Zs = Z + s * (int64_t)n * ld;
+  for (int r = 0; r < n; ++r) {
+    const double* row = Zs + (int64_t)r * ld;
+    double acc = 0.0;
+    for (int j = 1 + lane; j < ld; j += 32) acc += fabs(__ldcs(row + j));
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      const double c = row[0];
+      lo[s * n + r] = c - acc;
+      hi[s * n + r] = c + acc;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// MatrixZonotope x Zonotope (+ W): one CTA per scenario.
+//   out[r][b*(1+g) + j] = sum_k M_b[r][k] Z[k][j],  M_0 = C, M_b = G_b     (b = 0..N)
+//   out[:,0] += W[:,0];  out[:, (N+1)(1+g) + t] = W[:, 1+t]
+// The (N+1) small matrices are staged in shared memory; Z columns are read coalesced and
+// each thread produces the n rows of one output column (n independent FMA chains).
+// ---------------------------------------------------------------------------------------
+template <int NMAX>
+__global__ void __launch_bounds__(256) reach_kernel(int n, int p, int N, int g, int gW, const double* __restrict__ C,
+                                                    const double* __restrict__ Gm, int per_scenario,
+                                                    const double* __restrict__ Z, const double* __restrict__ W,
+                                                    double* __restrict__ Zout) {
+  extern __shared__ double sm[];                  // (N+1) * n * p
+  const int64_t s = blockIdx.x;
+  const int np_ = n * p;
+  const double* Cs = C + (per_scenario ? s * (int64_t)np_ : 0);
+  const double* Gs = Gm + (per_scenario ? s * (int64_t)N * np_ : 0);
+  for (int i = threadIdx.x; i < np_; i += blockDim.x) sm[i] = Cs[i];
+  for (int i = threadIdx.x; i < N * np_; i += blockDim.x) sm[np_ + i] = Gs[i];
+  __syncthreads();
+  const int ldz = 1 + g;
+  const int ldo = (N + 1) * ldz + gW;
+  const double* Zs = Z + s * (int64_t)p * ldz;
+  double* Os = Zout + s * (int64_t)n * ldo;
+  const int total = (N + 1) * ldz;
+  for (int col = threadIdx.x; col < total; col += blockDim.x) {
+    const int b = col / ldz, j = col - b * ldz;
+    const double* M = sm + (size_t)b * np_;
+    double acc[NMAX];
+#pragma unroll
+    for (int r = 0; r < NMAX; ++r) acc[r] = 0.0;
+    for (int k = 0; k < p; ++k) {
+      const double zk = Zs[(int64_t)k * ldz + j];
+#pragma unroll
+      for (int r = 0; r < NMAX; ++r)
+        if (r < n) acc[r] = fma(M[r * p + k], zk, acc[r]);
+    }
+    if (col == 0 && W != nullptr) {
+#pragma unroll
+      for (int r = 0; r < NMAX; ++r)
+        if (r < n) acc[r] += W[(int64_t)r * (1 + gW)];
+    }
+#pragma unroll
+    for (int r = 0; r < NMAX; ++r)
+      if (r < n) __stcs(Os + (int64_t)r * ldo + col, acc[r]);
+  }
+  for (int t = threadIdx.x; t < gW * n; t += blockDim.x) {
+    const int r = t / gW, c = t - r * gW;
+    Os[(int64_t)r * ldo + total + c] = W[(int64_t)r * (1 + gW) + 1 + c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Girard reduction: one CTA per zonotope, generator block in shared memory.
+//   metric per column -> 64-bit radix select of the nReduced smallest (ties: lowest index)
+//   -> box of the selected columns -> stable compaction of the kept columns + diag(d).
+// ---------------------------------------------------------------------------------------
+constexpr int kGirardThreads = 256;
+constexpr int kGirardMaxDim = 128;    // vectorised matrix zonotopes reach n*(n+m) = 96
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* warp_tot, int& total) {
+  // blockDim.x == kGirardThreads; returns the exclusive prefix of v, total = block sum
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_tot[wid] = inc;
+  __syncthreads();
+  int base = 0, tot = 0;
+  for (int w = 0; w < kGirardThreads / 32; ++w) {
+    const int t = warp_tot[w];
+    if (w < wid) base += t;
+    tot += t;
+  }
+  __syncthreads();
+  total = tot;
+  return base + inc - v;
+}
+
+__global__ void __launch_bounds__(kGirardThreads) girard_kernel(int n, int g, double order, int metric,
+                                                                const double* __restrict__ Z, int gout_cap,
+                                                                double* __restrict__ Zout, int32_t* __restrict__ gout) {
+  extern __shared__ unsigned char smraw[];
+  double* G = reinterpret_cast<double*>(smraw);                              // n x g
+  unsigned long long* key = reinterpret_cast<unsigned long long*>(G + (size_t)n * g);   // g
+  unsigned char* flag = reinterpret_cast<unsigned char*>(key + g);           // g: 0 zero, 1 keep, 2 reduce
+  __shared__ int hist[256];
+  __shared__ int warp_tot[kGirardThreads / 32];
+  __shared__ unsigned long long sel_prefix;
+  __shared__ int sel_remaining;
+  __shared__ double dbox[kGirardMaxDim];
+  __shared__ double red[kGirardThreads / 32];
+
+  const int64_t s = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int ldz = 1 + g, ldo = 1 + gout_cap;
+  const double* Zs = Z + s * (int64_t)n * ldz;
+  double* Os = Zout + s * (int64_t)n * ldo;
+
+  for (int i = tid; i < n * g; i += kGirardThreads) {
+    const int r = i / g, j = i - r * g;
+    G[i] = __ldcs(Zs + (int64_t)r * ldz + 1 + j);
+  }
+  __syncthreads();
+  // metric (rows accumulated r = 0..n-1, exactly as oracle/zono.py:_girard_metric) and zero filter
+  int nnz_local = 0;
+  for (int j = tid; j < g; j += kGirardThreads) {
+    double sum = 0.0, mx = 0.0;
+    bool nzc = false;
+    for (int r = 0; r < n; ++r) {
+      const double a = fabs(G[(size_t)r * g + j]);
+      nzc = nzc || (a != 0.0);
+      if (metric == 2) sum = __dadd_rn(sum, __dmul_rn(a, a));      // no FMA contraction: selection must match the oracle bit for bit
+      else sum += a;
+      mx = fmax(mx, a);
+    }
+    const double h = (metric == 0) ? (sum - mx) : sum;
+    key[j] = (unsigned long long)__double_as_longlong(h);      // h >= 0: bit pattern is order-preserving
+    flag[j] = nzc ? 1 : 0;
+    nnz_local += nzc ? 1 : 0;
+  }
+  int gnz;
+  (void)block_exclusive_scan(nnz_local, warp_tot, gnz);
+  const bool do_reduce = (double)gnz > order * (double)n;
+  int n_unred = gnz, n_red = 0;
+  if (do_reduce) {
+    n_unred = (int)floor((double)n * (order - 1.0));
+    if (n_unred < 0) n_unred = 0;
+    n_red = gnz - n_unred;
+    // ---- radix select (MSB first, 8 bits per pass) of the n_red-th smallest key among non-zero columns
+    if (tid == 0) { sel_prefix = 0ull; sel_remaining = n_red; }
+    __syncthreads();
+    for (int pass = 7; pass >= 0; --pass) {
+      for (int i = tid; i < 256; i += kGirardThreads) hist[i] = 0;
+      __syncthreads();
+      const unsigned long long prefix = sel_prefix;
+      const unsigned long long himask = (pass == 7) ? 0ull : (~0ull << ((pass + 1) * 8));
+      for (int j = tid; j < g; j += kGirardThreads)
+        if (flag[j] && ((key[j] & himask) == prefix)) atomicAdd(&hist[(int)((key[j] >> (pass * 8)) & 0xffull)], 1);
+      __syncthreads();
+      if (tid == 0) {
+        int rem = sel_remaining, d = 0;
+        for (; d < 256; ++d) {
+          if (hist[d] >= rem) break;
+          rem -= hist[d];
+        }
+        sel_prefix = prefix | ((unsigned long long)d << (pass * 8));
+        sel_remaining = rem;
+      }
+      __syncthreads();
+    }
+    // keys < thr are reduced; among keys == thr the first `sel_remaining` (lowest index) are reduced
+    const unsigned long long thr = sel_prefix;
+    const int ties_needed = sel_remaining;
+    // stable rank among the ties: chunked scan in index order
+    int tie_base = 0;
+    for (int j0 = 0; j0 < g; j0 += kGirardThreads) {
+      const int j = j0 + tid;
+      const int is_tie = (j < g && flag[j] && key[j] == thr) ? 1 : 0;
+      int tot;
+      const int rank = tie_base + block_exclusive_scan(is_tie, warp_tot, tot);
+      if (j < g && flag[j]) {
+        if (key[j] < thr || (is_tie && rank < ties_needed)) flag[j] = 2;
+      }
+      tie_base += tot;
+    }
+    __syncthreads();
+    // ---- box of the reduced columns: fixed-order block reduction per row (deterministic)
+    for (int r = 0; r < n; ++r) {
+      double acc = 0.0;
+      for (int j = tid; j < g; j += kGirardThreads)
+        if (flag[j] == 2) acc += fabs(G[(size_t)r * g + j]);
+      acc = warp_sum(acc);
+      if ((tid & 31) == 0) red[tid >> 5] = acc;
+      __syncthreads();
+      if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < kGirardThreads / 32; ++w) t += red[w];
+        dbox[r] = t;
+      }
+      __syncthreads();
+    }
+  }
+  // ---- output: centre, kept columns in original order, then diag(d), zero padding
+  for (int r = tid; r < n; r += kGirardThreads) Os[(int64_t)r * ldo] = Zs[(int64_t)r * ldz];
+  int out_base = 0;
+  for (int j0 = 0; j0 < g; j0 += kGirardThreads) {
+    const int j = j0 + tid;
+    const int keep = (j < g && flag[j] == 1) ? 1 : 0;
+    int tot;
+    const int pos = out_base + block_exclusive_scan(keep, warp_tot, tot);
+    if (keep && pos < gout_cap)
+      for (int r = 0; r < n; ++r) Os[(int64_t)r * ldo + 1 + pos] = G[(size_t)r * g + j];
+    out_base += tot;
+  }
+  int written = out_base;
+  if (do_reduce) {
+    for (int i = tid; i < n * n; i += kGirardThreads) {
+      const int r = i / n, c = i - r * n;
+      if (written + c < gout_cap) Os[(int64_t)r * ldo + 1 + written + c] = (r == c) ? dbox[r] : 0.0;
+    }
+    written += n;
+  }
+  if (written > gout_cap) written = -written;          // signals "gout_cap too small"
+  const int wpos = written < 0 ? gout_cap : written;
+  for (int i = tid; i < n * (gout_cap - wpos); i += kGirardThreads) {
+    const int r = i / (gout_cap - wpos), c = i - r * (gout_cap - wpos);
+    Os[(int64_t)r * ldo + 1 + wpos + c] = 0.0;
+  }
+  if (tid == 0) gout[s] = written;
+}
+
+// ---------------------------------------------------------------------------------------
+// identify: one CTA per dataset.  D = [X0; U0] ((n+m) x (T-1)), P = pinv(D) = D'(DD')^{-1}
+// (Jacobi-scaled Gram matrix + Cholesky), AB = (X1 - c_W 1') P, and the order-1 boxes
+//   dAB = (sum_k |g_k|) (sum_j |P[j,:]|)',  dK = (sum_k |g_k|) (sum_j |P[j,:] [I;K]|)'
+// (closed form of tzddpc/tzddpc.py:81-83,119-128 for rank-one generators).
+// ---------------------------------------------------------------------------------------
+constexpr int kIdThreads = 128;
+constexpr int kMaxD = kMaxN + kMaxM;
+
+__global__ void __launch_bounds__(kIdThreads) identify_kernel(int T, int n, int m, int gW, const double* __restrict__ X,
+                                                              const double* __restrict__ U, const double* __restrict__ WZ,
+                                                              const double* __restrict__ K, double* __restrict__ AB,
+                                                              double* __restrict__ dAB, double* __restrict__ dK,
+                                                              double* __restrict__ Pinv, int32_t* __restrict__ status) {
+  extern __shared__ double smd[];                   // D: (T-1) x d  (row j = sample j), X1c: (T-1) x n
+  __shared__ double gram[kMaxD * kMaxD];            // then its scaled Cholesky factor
+  __shared__ double hmat[kMaxN * kMaxD];
+  __shared__ double scale[kMaxD];
+  __shared__ double part[kIdThreads / 32][kMaxD * kMaxD];
+  __shared__ double sP[kMaxD], sPK[kMaxN];
+  __shared__ int bad;
+  const int64_t s = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int d = n + m, Tm = T - 1;
+  double* Dm = smd;
+  double* X1 = smd + (size_t)Tm * d;
+  const double* Xs = X + s * (int64_t)T * n;
+  const double* Us = U + s * (int64_t)T * m;
+  for (int i = tid; i < Tm * n; i += kIdThreads) {
+    const int j = i / n, r = i - j * n;
+    Dm[(size_t)j * d + r] = Xs[i];                                   // Xm = x[:-1]   (tzddpc/tzddpc.py:60)
+    X1[i] = Xs[i + n] - WZ[(int64_t)r * (1 + gW)];                   // Xp = x[1:] minus c_W (:61, App. A.7)
+  }
+  for (int i = tid; i < Tm * m; i += kIdThreads) {
+    const int j = i / m, r = i - j * m;
+    Dm[(size_t)j * d + n + r] = Us[i];                               // Um = u[:-1]   (:62)
+  }
+  if (tid == 0) bad = 0;
+  __syncthreads();
+  // Gram matrix G = D D' and H = X1c D' : every thread accumulates a slice of samples
+  {
+    double acc[kMaxD * kMaxD];
+    for (int pass = 0; pass < 2; ++pass) {
+      const int rows = pass == 0 ? d : n;
+#pragma unroll
+      for (int i = 0; i < kMaxD * kMaxD; ++i) acc[i] = 0.0;
+      for (int j = tid; j < Tm; j += kIdThreads) {
+        const double* dj = Dm + (size_t)j * d;
+        const double* lj = pass == 0 ? dj : X1 + (size_t)j * n;
+        for (int a = 0; a < rows; ++a) {
+          const double la = lj[a];
+          for (int b = 0; b < d; ++b) acc[a * kMaxD + b] = fma(la, dj[b], acc[a * kMaxD + b]);
+        }
+      }
+      for (int a = 0; a < rows; ++a)
+        for (int b = 0; b < d; ++b) {
+          const double v = warp_sum(acc[a * kMaxD + b]);
+          if (lane == 0) part[wid][a * kMaxD + b] = v;
+        }
+      __syncthreads();
+      for (int i = tid; i < rows * d; i += kIdThreads) {
+        const int a = i / d, b = i - a * d;
+        double t = 0.0;
+        for (int w = 0; w < kIdThreads / 32; ++w) t += part[w][a * kMaxD + b];
+        if (pass == 0) gram[a * kMaxD + b] = t;
+        else hmat[a * kMaxD + b] = t;
+      }
+      __syncthreads();
+    }
+  }
+  // Jacobi scaling + Cholesky of the scaled Gram matrix (thread 0; d <= 12)
+  if (tid == 0) {
+    for (int a = 0; a < d; ++a) {
+      const double g = gram[a * kMaxD + a];
+      if (!(g > 0.0)) bad = 1;
+      scale[a] = g > 0.0 ? rsqrt(g) : 1.0;
+    }
+    for (int a = 0; a < d; ++a)
+      for (int b = 0; b < d; ++b) gram[a * kMaxD + b] *= scale[a] * scale[b];
+    for (int j = 0; j < d; ++j) {
+      double dj = gram[j * kMaxD + j];
+      for (int k = 0; k < j; ++k) dj -= gram[j * kMaxD + k] * gram[j * kMaxD + k];
+      if (!(dj > 1e-14)) { bad = 1; dj = 1.0; }
+      const double l = sqrt(dj);
+      gram[j * kMaxD + j] = l;
+      for (int i = j + 1; i < d; ++i) {
+        double v = gram[i * kMaxD + j];
+        for (int k = 0; k < j; ++k) v -= gram[i * kMaxD + k] * gram[j * kMaxD + k];
+        gram[i * kMaxD + j] = v / l;
+      }
+    }
+  }
+  for (int i = tid; i < kMaxD; i += kIdThreads) sP[i] = 0.0;
+  for (int i = tid; i < kMaxN; i += kIdThreads) sPK[i] = 0.0;
+  __syncthreads();
+  auto solve = [&](double* v) {     // v <- G^{-1} v  with G = S^{-1} L L' S^{-1}, S = diag(scale)
+    for (int a = 0; a < d; ++a) v[a] *= scale[a];
+    for (int i = 0; i < d; ++i) {
+      double t = v[i];
+      for (int k = 0; k < i; ++k) t -= gram[i * kMaxD + k] * v[k];
+      v[i] = t / gram[i * kMaxD + i];
+    }
+    for (int i = d - 1; i >= 0; --i) {
+      double t = v[i];
+      for (int k = i + 1; k < d; ++k) t -= gram[k * kMaxD + i] * v[k];
+      v[i] = t / gram[i * kMaxD + i];
+    }
+    for (int a = 0; a < d; ++a) v[a] *= scale[a];
+  };
+  // AB = H G^{-1}: row r of AB solves G ab_r = h_r
+  if (tid < n) {
+    double v[kMaxD];
+    for (int b = 0; b < d; ++b) v[b] = hmat[tid * kMaxD + b];
+    solve(v);
+    for (int b = 0; b < d; ++b) AB[s * (int64_t)n * d + tid * d + b] = v[b];
+  }
+  // rows of the pseudo-inverse and their absolute column sums
+  {
+    double aP[kMaxD], aPK[kMaxN];
+    for (int b = 0; b < kMaxD; ++b) aP[b] = 0.0;
+    for (int b = 0; b < kMaxN; ++b) aPK[b] = 0.0;
+    const double* Ks = K ? K + s * (int64_t)m * n : nullptr;
+    for (int j = tid; j < Tm; j += kIdThreads) {
+      double v[kMaxD];
+      for (int b = 0; b < d; ++b) v[b] = Dm[(size_t)j * d + b];
+      solve(v);
+      for (int b = 0; b < d; ++b) {
+        aP[b] += fabs(v[b]);
+        if (Pinv) Pinv[s * (int64_t)Tm * d + (int64_t)j * d + b] = v[b];
+      }
+      if (Ks)
+        for (int c = 0; c < n; ++c) {
+          double t = v[c];                                        // P[j,:] [I; K] column c
+          for (int k = 0; k < m; ++k) t = fma(v[n + k], Ks[k * n + c], t);
+          aPK[c] += fabs(t);
+        }
+    }
+    for (int b = 0; b < d; ++b) {
+      const double v = warp_sum(aP[b]);
+      if (lane == 0) atomicAdd(&sP[b], v);
+    }
+    for (int c = 0; c < n; ++c) {
+      const double v = warp_sum(aPK[c]);
+      if (lane == 0) atomicAdd(&sPK[c], v);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < n * d; i += kIdThreads) {
+    const int r = i / d, c = i - r * d;
+    double gw = 0.0;
+    for (int k = 0; k < gW; ++k) gw += fabs(WZ[(int64_t)r * (1 + gW) + 1 + k]);
+    dAB[s * (int64_t)n * d + i] = gw * sP[c];
+  }
+  if (K && dK)
+    for (int i = tid; i < n * n; i += kIdThreads) {
+      const int r = i / n, c = i - r * n;
+      double gw = 0.0;
+      for (int k = 0; k < gW; ++k) gw += fabs(WZ[(int64_t)r * (1 + gW) + 1 + k]);
+      dK[s * (int64_t)n * n + i] = gw * sPK[c];
+    }
+  if (tid == 0 && status) status[s] = bad ? TZ_STATUS_NONFINITE : TZ_STATUS_OK;
+}
+
+}  // namespace tz
+
+using namespace tz;
+
+extern "C" int tz_interval_hull(int64_t S, int32_t n, int32_t g, const double* Z, double* lo, double* hi, void* stream) {
+  TZ_REQUIRE(S >= 0 && n >= 1 && g >= 0, "bad shape");
+  if (S == 0) return TZ_OK;
+  TZ_REQUIRE(Z && lo && hi, "null pointer");
+  const int wpb = 8;
+  hull_kernel<<<(unsigned)((S + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(S, n, g, Z, lo, hi);
+  TZ_CUDA(cudaGetLastError());
+  return TZ_OK;
+}
+
+extern "C" int tz_reach_step(int64_t S, int32_t n, int32_t p, int32_t N, int32_t g, int32_t gW, const double* C,
+                             const double* Gm, int32_t per_scenario_model, const double* Z, const double* W,
+                             double* Zout, void* stream) {
+  TZ_REQUIRE(S >= 0 && n >= 1 && n <= 16 && p >= 1 && N >= 0 && g >= 0 && gW >= 0, "bad shape (n <= 16)");
+  if (S == 0) return TZ_OK;
+  TZ_REQUIRE(C && Z && Zout && (N == 0 || Gm) && (gW == 0 || W), "null pointer");
+  const size_t smem = (size_t)(N + 1) * n * p * sizeof(double);
+  TZ_REQUIRE(smem <= 200 * 1024, "matrix zonotope too large for shared memory");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n <= 8) {
+    if (smem > 48 * 1024) TZ_CUDA(cudaFuncSetAttribute(reach_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    reach_kernel<8><<<(unsigned)S, 256, smem, st>>>(n, p, N, g, gW, C, Gm, per_scenario_model, Z, gW ? W : nullptr, Zout);
+  } else {
+    if (smem > 48 * 1024) TZ_CUDA(cudaFuncSetAttribute(reach_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    reach_kernel<16><<<(unsigned)S, 256, smem, st>>>(n, p, N, g, gW, C, Gm, per_scenario_model, Z, gW ? W : nullptr, Zout);
+  }
+  TZ_CUDA(cudaGetLastError());
+  return TZ_OK;
+}
+
+extern "C" int tz_girard_reduce(int64_t S, int32_t n, int32_t g, double order, int32_t metric, const double* Z,
+                                int32_t gout_cap, double* Zout, int32_t* gout, void* stream) {
+  TZ_REQUIRE(S >= 0 && n >= 1 && n <= kGirardMaxDim && g >= 0 && gout_cap >= 0 && order > 0, "bad shape (n <= 128)");
+  TZ_REQUIRE(metric >= 0 && metric <= 2, "metric must be 0 (l1-linf), 1 (l1) or 2 (l2)");
+  if (S == 0) return TZ_OK;
+  TZ_REQUIRE(Z && Zout && gout, "null pointer");
+  const size_t smem = (size_t)n * g * sizeof(double) + (size_t)g * sizeof(unsigned long long) + (size_t)g + 16;
+  TZ_REQUIRE(smem <= 220 * 1024, "zonotope (n=%d, g=%d) does not fit in shared memory", n, g);
+  if (smem > 48 * 1024) TZ_CUDA(cudaFuncSetAttribute(girard_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  girard_kernel<<<(unsigned)S, kGirardThreads, smem, (cudaStream_t)stream>>>(n, g, order, metric, Z, gout_cap, Zout, gout);
+  TZ_CUDA(cudaGetLastError());
+  return TZ_OK;
+}
+
+extern "C" int tz_identify(int64_t S, int32_t T, int32_t n, int32_t m, int32_t gW, const double* X, const double* U,
+                           const double* WZ, const double* K, double* AB, double* dAB, double* dK, double* Pinv,
+                           int32_t* status, void* stream) {
+  TZ_REQUIRE(S >= 0 && T >= 2 && n >= 1 && n <= kMaxN && m >= 1 && m <= kMaxM && gW >= 0, "bad shape");
+  if (S == 0) return TZ_OK;
+  TZ_REQUIRE(X && U && WZ && AB && dAB, "null pointer");
+  TZ_REQUIRE(!dK || K, "dK needs K");
+  const size_t smem = (size_t)(T - 1) * (2 * n + m) * sizeof(double);
+  TZ_REQUIRE(smem <= 200 * 1024, "dataset too long for shared memory (T=%d)", T);
+  if (smem > 48 * 1024) TZ_CUDA(cudaFuncSetAttribute(identify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  identify_kernel<<<(unsigned)S, kIdThreads, smem, (cudaStream_t)stream>>>(T, n, m, gW, X, U, WZ, K, AB, dAB, dK, Pinv, status);
+  TZ_CUDA(cudaGetLastError());
+  return TZ_OK;
+}

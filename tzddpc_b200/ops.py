@@ -1,0 +1,188 @@
+"""PyTorch custom ops `torch.ops.tzddpc.*`: thin shims from CUDA tensors to the C ABI.
+
+PyTorch is plumbing here (device memory, streams); the arithmetic is in libtzddpc.so.
+Every op is registered for CUDA only -- there is deliberately no CPU kernel.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _abi
+
+
+@dataclass
+class SolverOptions:
+    """Mirror of TzSolverOpts (include/tzddpc.h); the reference passes **cvxpy_kwargs (tzddpc/tzddpc.py:361)."""
+    rho: float = 0.1
+    rho_active: float = 100.0
+    rho_inactive: float = 0.1
+    sigma: float = 1e-6
+    alpha: float = 1.6
+    eps_abs: float = 1e-6
+    eps_rel: float = 1e-6
+    max_iter: int = 4000
+    check_every: int = 4
+    polish: bool = True
+    warm_start: bool = False
+
+    def pack(self) -> List[float]:
+        return [self.rho, self.rho_active, self.rho_inactive, self.sigma, self.alpha, self.eps_abs, self.eps_rel,
+                float(self.max_iter), float(self.check_every), float(self.polish), float(self.warm_start)]
+
+
+def _opts(o: List[float]) -> _abi.TzSolverOpts:
+    s = _abi.TzSolverOpts()
+    s.rho, s.rho_active, s.rho_inactive, s.sigma, s.alpha, s.eps_abs, s.eps_rel = o[:7]
+    s.max_iter, s.check_every, s.polish, s.warm_start = int(o[7]), int(o[8]), int(o[9]), int(o[10])
+    return s
+
+
+def _ptr(t: Optional[Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(t: Tensor):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _chk(t: Tensor, dtype=torch.float64):
+    assert t.is_cuda and t.dtype == dtype and t.is_contiguous(), "expected a contiguous CUDA tensor of " + str(dtype)
+
+
+def warm_rows(nz_bucket: int, nc_bucket: int) -> int:
+    return nz_bucket + nc_bucket + (nc_bucket + 31) // 32 + 1
+
+
+@torch.library.custom_op("tzddpc::solve", mutates_args=("warm",), device_types="cuda")
+def solve(prog: int, dims: List[int], xbar0: Tensor, e0: Tensor, warm: Optional[Tensor], want_tube: bool,
+          opts: List[float]) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """Batched TZDDPC.solve (tzddpc/tzddpc.py:357-377).  xbar0, e0: (n, S).  dims = [n, nv, (N+1)n, n(1+g1)].
+    Returns cost (S), v (nv, S), xbar (., S), Ze1.Z (n(1+g1), S), status (S), iters (S)."""
+    _chk(xbar0), _chk(e0)
+    n, nv, nt, nent = dims
+    S = xbar0.shape[1]
+    dev = xbar0.device
+    cost = torch.empty(S, dtype=torch.float64, device=dev)
+    v = torch.empty((nv, S), dtype=torch.float64, device=dev)
+    traj = torch.empty((nt, S), dtype=torch.float64, device=dev)
+    ze1 = torch.empty((nent if want_tube else 0, S), dtype=torch.float64, device=dev)
+    status = torch.empty(S, dtype=torch.int32, device=dev)
+    iters = torch.empty(S, dtype=torch.int32, device=dev)
+    o = _opts(opts)
+    with torch.cuda.device(dev):
+        rc = _abi.lib().tz_solve(C.c_void_p(prog), C.byref(o), S, _ptr(xbar0), _ptr(e0), _ptr(cost), _ptr(v), _ptr(traj),
+                                 _ptr(ze1) if want_tube else None, _ptr(status), _ptr(iters), _ptr(warm), _stream(xbar0))
+    _abi.check(rc, "tz_solve")
+    return cost, v, traj, ze1, status, iters
+
+
+@torch.library.custom_op("tzddpc::closed_loop_step",
+                         mutates_args=("x", "xbar", "e", "cost", "v", "traj", "ze1", "u", "status", "iters", "warm", "stats"),
+                         device_types="cuda")
+def closed_loop_step(prog: int, x: Tensor, xbar: Tensor, e: Tensor, noise: Tensor, A_true: Tensor, B_true: Tensor,
+                     status: Tensor, cost: Optional[Tensor], v: Optional[Tensor], traj: Optional[Tensor],
+                     ze1: Optional[Tensor], u: Optional[Tensor], iters: Optional[Tensor], warm: Optional[Tensor],
+                     stats: Optional[Tensor], opts: List[float]) -> None:
+    # (no default values: torch strips trailing defaulted arguments, which breaks mutated Optional[Tensor] args)
+    """One fused closed-loop step, in place on (x, xbar, e) -- examples/2.pulley_sim.py:81-96."""
+    _chk(x), _chk(xbar), _chk(e), _chk(noise), _chk(A_true), _chk(B_true), _chk(status, torch.int32)
+    S = x.shape[1]
+    o = _opts(opts)
+    with torch.cuda.device(x.device):
+        rc = _abi.lib().tz_closed_loop_step(C.c_void_p(prog), C.byref(o), S, _ptr(x), _ptr(xbar), _ptr(e), _ptr(noise),
+                                            _ptr(A_true), _ptr(B_true), _ptr(cost), _ptr(v), _ptr(traj), _ptr(ze1),
+                                            _ptr(u), _ptr(status), _ptr(iters), _ptr(warm), _ptr(stats), _stream(x))
+    _abi.check(rc, "tz_closed_loop_step")
+
+
+@torch.library.custom_op("tzddpc::interval_hull", mutates_args=(), device_types="cuda")
+def interval_hull(Z: Tensor) -> Tuple[Tensor, Tensor]:
+    """Z: (S, n, 1+g) -> lo, hi (S, n).  Zonotope.interval (tzddpc/tzddpc.py:191-197)."""
+    _chk(Z)
+    S, n, ld = Z.shape
+    lo = torch.empty((S, n), dtype=torch.float64, device=Z.device)
+    hi = torch.empty_like(lo)
+    with torch.cuda.device(Z.device):
+        rc = _abi.lib().tz_interval_hull(S, n, ld - 1, _ptr(Z), _ptr(lo), _ptr(hi), _stream(Z))
+    _abi.check(rc, "tz_interval_hull")
+    return lo, hi
+
+
+@torch.library.custom_op("tzddpc::reach_step", mutates_args=(), device_types="cuda")
+def reach_step(Cm: Tensor, Gm: Tensor, Z: Tensor, W: Optional[Tensor]) -> Tensor:
+    """MatrixZonotope x Zonotope (+ W).  Cm: (n, p) or (S, n, p); Gm: (N, n, p) or (S, N, n, p);
+    Z: (S, p, 1+g); W: (n, 1+gW).  Returns (S, n, (N+1)(1+g)+gW)  (tzddpc/tzddpc.py:175-176,181,185,205)."""
+    _chk(Cm), _chk(Gm), _chk(Z)
+    per = Cm.dim() == 3
+    S, p, ld = Z.shape
+    n = Cm.shape[-2]
+    N = Gm.shape[-3]
+    assert Cm.shape[-1] == p and (N == 0 or Gm.shape[-1] == p)
+    gW = 0 if W is None else W.shape[1] - 1
+    if W is not None:
+        _chk(W)
+    out = torch.empty((S, n, (N + 1) * ld + gW), dtype=torch.float64, device=Z.device)
+    with torch.cuda.device(Z.device):
+        rc = _abi.lib().tz_reach_step(S, n, p, N, ld - 1, gW, _ptr(Cm), _ptr(Gm), int(per), _ptr(Z), _ptr(W), _ptr(out),
+                                      _stream(Z))
+    _abi.check(rc, "tz_reach_step")
+    return out
+
+
+@torch.library.custom_op("tzddpc::girard_reduce", mutates_args=(), device_types="cuda")
+def girard_reduce(Z: Tensor, order: float, metric: int, gout_cap: int) -> Tuple[Tensor, Tensor]:
+    """Z: (S, n, 1+g) -> (S, n, 1+gout_cap), gout (S).  Zonotope.reduce."""
+    _chk(Z)
+    S, n, ld = Z.shape
+    out = torch.empty((S, n, 1 + gout_cap), dtype=torch.float64, device=Z.device)
+    gout = torch.empty(S, dtype=torch.int32, device=Z.device)
+    with torch.cuda.device(Z.device):
+        rc = _abi.lib().tz_girard_reduce(S, n, ld - 1, float(order), int(metric), _ptr(Z), gout_cap, _ptr(out), _ptr(gout),
+                                         _stream(Z))
+    _abi.check(rc, "tz_girard_reduce")
+    return out, gout
+
+
+@torch.library.custom_op("tzddpc::identify", mutates_args=(), device_types="cuda")
+def identify(X: Tensor, U: Tensor, WZ: Tensor, K: Optional[Tensor], want_pinv: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """X: (S, T, n), U: (S, T, m), WZ: (n, 1+gW), K: (S, m, n).  Returns AB (S,n,n+m), dAB, dK (S,n,n), Pinv, status.
+    M_Sigma = (X1 - M_w) pinv([X0;U0]) and its order-1 boxes (tzddpc/tzddpc.py:81-83,119-128)."""
+    _chk(X), _chk(U), _chk(WZ)
+    S, T, n = X.shape
+    m = U.shape[2]
+    dev = X.device
+    AB = torch.empty((S, n, n + m), dtype=torch.float64, device=dev)
+    dAB = torch.empty_like(AB)
+    dK = torch.zeros((S, n, n), dtype=torch.float64, device=dev)
+    Pinv = torch.empty((S, T - 1, n + m) if want_pinv else (0,), dtype=torch.float64, device=dev)
+    status = torch.empty(S, dtype=torch.int32, device=dev)
+    if K is not None:
+        _chk(K)
+    with torch.cuda.device(dev):
+        rc = _abi.lib().tz_identify(S, T, n, m, WZ.shape[1] - 1, _ptr(X), _ptr(U), _ptr(WZ), _ptr(K), _ptr(AB), _ptr(dAB),
+                                    _ptr(dK) if K is not None else None, _ptr(Pinv) if want_pinv else None,
+                                    _ptr(status), _stream(X))
+    _abi.check(rc, "tz_identify")
+    return AB, dAB, dK, Pinv, status
+
+
+@torch.library.custom_op("tzddpc::qp_solve", mutates_args=(), device_types="cuda")
+def qp_solve(prog: int, q: Tensor, l: Tensor, u: Tensor, opts: List[float]) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """Explicit-instance batched ADMM: q (nz, S), l/u (nc, S) -> z (nz, S), y (nc, S), status, iters."""
+    _chk(q), _chk(l), _chk(u)
+    S = q.shape[1]
+    z = torch.empty_like(q)
+    y = torch.empty_like(l)
+    status = torch.empty(S, dtype=torch.int32, device=q.device)
+    iters = torch.empty(S, dtype=torch.int32, device=q.device)
+    o = _opts(opts)
+    with torch.cuda.device(q.device):
+        rc = _abi.lib().tz_qp_solve(C.c_void_p(prog), C.byref(o), S, _ptr(q), _ptr(l), _ptr(u), _ptr(z), _ptr(y),
+                                    _ptr(status), _ptr(iters), _stream(q))
+    _abi.check(rc, "tz_qp_solve")
+    return z, y, status, iters

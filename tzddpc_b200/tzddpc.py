@@ -1,0 +1,327 @@
+"""`TZDDPC` -- drop-in counterpart of the reference controller class (`tzddpc/tzddpc.py:11-500`).
+
+Same public methods, properties and attributes; behind them every numeric step runs on the
+GPU (sm_100a) through `torch.ops.tzddpc.*` -> libtzddpc.so:
+
+  build_zonotopes / build_zonotopes_theta  -> tz_identify            (tzddpc/tzddpc.py:67-130)
+  build_problem / build_problem_simplified -> host canonicalisation (program.py) + tz_program_create
+                                                                     (tzddpc/tzddpc.py:132-355)
+  solve                                    -> tz_solve               (tzddpc/tzddpc.py:357-377)
+  simulate (new, batched closed loop)      -> tz_closed_loop_step    (examples/2.pulley_sim.py:81-96)
+
+Additive extensions: `solve` accepts (S, n) batches; `simulate` runs S scenarios in lock step.
+Deviations (documented in DESIGN.md): the loss/constraint callbacks receive this package's
+affine-expression variables (`tzddpc_b200.cvx`) instead of cvxpy ones, or a structured
+`StageCost`/`BoxConstraint`; `compute_theta` needs K from the caller or uses an LQR gain
+(the reference's SDP + DCCP/MOSEK synthesis, tzddpc/utils.py:13-103, is out of scope).
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _abi, ops
+from .objects import Data, DataDrivenDataset, OptimizationProblem, SystemZonotopes, Theta
+from .ops import SolverOptions
+from .program import BoxConstraint, CompiledProgram, StageCost, TubeModel, compile_program
+from .zonotope import Interval, MatrixZonotope, Zonotope, boxed_generators, concatenate_zonotope
+
+
+class _Value:
+    """Mimics a cvxpy expression's `.value` (callers read `Ze[1].Z.value`, examples/2.pulley_sim.py:96)."""
+
+    def __init__(self, value):
+        self.value = value
+
+
+class TubeHandle:
+    """What `solve` returns in place of the reference's `CVXZonotope` Ze[1] (`tzddpc/tzddpc.py:377`):
+    `.Z.value` is the n x (1+g1) array [c, G] (batched: S x n x (1+g1)), fetched from the GPU lazily."""
+
+    def __init__(self, ze1: torch.Tensor, n: int, g1: int, batched: bool):
+        self._ze1, self._n, self._g1, self._batched = ze1, n, g1, batched
+        self._host = None
+
+    @property
+    def Z(self) -> _Value:
+        if self._host is None:
+            S = self._ze1.shape[1]
+            a = self._ze1.reshape(self._n, 1 + self._g1, S).permute(2, 0, 1).cpu().numpy()
+            self._host = a if self._batched else a[0]
+        return _Value(self._host)
+
+    @property
+    def device_tensor(self) -> torch.Tensor:
+        """(n, 1+g1, S) view of the device buffer (entry (r, j) of scenario s at [r, j, s])."""
+        return self._ze1.reshape(self._n, 1 + self._g1, -1)
+
+    @property
+    def center(self) -> _Value:
+        return _Value(self.Z.value[..., 0])
+
+    @property
+    def generators(self) -> _Value:
+        return _Value(self.Z.value[..., 1:])
+
+    @property
+    def num_generators(self) -> int:
+        return self._g1
+
+
+class BatchSolveResult:
+    def __init__(self, cost, v, xbar, tube, status, iters):
+        self.cost, self.v, self.xbar, self.tube, self.status, self.iters = cost, v, xbar, tube, status, iters
+
+
+class TZDDPC(object):
+    optimization_problem: Union[OptimizationProblem, None] = None
+    dataset: DataDrivenDataset
+    zonotopes: SystemZonotopes
+    Mdata: MatrixZonotope
+    Mdelta: MatrixZonotope
+    MdataK: MatrixZonotope
+    theta: Theta
+
+    def __init__(self, data: Data, device: Optional[Union[str, torch.device]] = None):
+        """:param data: input/state data, each T x dim (tzddpc/tzddpc.py:20-28)."""
+        _abi.lib()                               # fail loudly when the CUDA library is missing
+        if not torch.cuda.is_available():
+            raise RuntimeError("tzddpc_b200.TZDDPC needs a CUDA device (no CPU fallback)")
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.solver_options = SolverOptions()
+        self.verbose = True
+        self._program: Optional[_abi.Program] = None
+        self.update_identification_data(data)
+
+    # ---- tzddpc/tzddpc.py:30-43 -------------------------------------------------------------
+    @property
+    def num_samples(self) -> int:
+        return self.dataset.Um.shape[0] + 1
+
+    @property
+    def dim_u(self) -> int:
+        return self.dataset.Um.shape[1]
+
+    @property
+    def dim_x(self) -> int:
+        return self.dataset.Xp.shape[1]
+
+    # ---- tzddpc/tzddpc.py:45-65 -------------------------------------------------------------
+    def update_identification_data(self, data: Data):
+        assert len(data.u.shape) == 2, \
+            "Data needs to be shaped as a TxM matrix (T is the number of samples and M is the number of features)"
+        assert len(data.x.shape) == 2, \
+            "Data needs to be shaped as a TxM matrix (T is the number of samples and M is the number of features)"
+        assert data.x.shape[0] == data.u.shape[0], "Input/state data must have the same length"
+        Xm, Xp, Um = data.x[:-1], data.x[1:], data.u[:-1]
+        self.dataset = DataDrivenDataset(Xp, Xm, Um, data)
+        self.optimization_problem = None
+        self._program = None
+
+    def _t(self, a) -> torch.Tensor:
+        return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(self.device)
+
+    # ---- tzddpc/tzddpc.py:67-85 -------------------------------------------------------------
+    def build_zonotopes(self, zonotopes: SystemZonotopes) -> MatrixZonotope:
+        X0, W, U, X = zonotopes.X0, zonotopes.W, zonotopes.U, zonotopes.X
+        assert X0.dimension == W.dimension and X0.dimension == self.dim_x \
+            and X.dimension == X0.dimension, 'The zonotopes do not have the correct dimension'
+        if self.verbose:
+            print('--------------------------------------------')
+            print('Building zonotopes')
+        self.optimization_problem = None
+        self._program = None
+        self.zonotopes = zonotopes
+        d = self.dataset.original_data
+        AB, dAB, _, Pinv, status = ops.identify(self._t(d.x)[None], self._t(d.u)[None], self._t(W.Z), None, True)
+        if int(status[0].item()) != 0:
+            raise Exception('Identification failed: [X0; U0] does not have full row rank')
+        self._AB = AB[0].cpu().numpy()
+        self._dAB = dAB[0].cpu().numpy()
+        self._Pinv = Pinv[0]                                   # (T-1) x (n+m), stays on the GPU
+        # generators -g_i P[j,:] (rank one; generator index outer, sample index inner -- App. A.7)
+        GW = self._t(W.generators)                              # n x gW
+        gens = -(GW.t()[:, None, :, None] * self._Pinv[None, :, None, :])       # gW x (T-1) x n x (n+m)
+        self.Mdata = MatrixZonotope(self._AB, gens.reshape(-1, self.dim_x, self.dim_x + self.dim_u).cpu().numpy())
+        if self.verbose:
+            print('--------------------------------------------')
+        return self.Mdata
+
+    # ---- tzddpc/tzddpc.py:87-93 -------------------------------------------------------------
+    def compute_theta(self, tol: float = 1e-5, num_max_iterations: int = 20, num_initial_points: int = 10,
+                      K: Optional[np.ndarray] = None) -> Theta:
+        """The reference alternates an LMI feasibility SDP with a DCCP/MOSEK adversary
+        (tzddpc/utils.py:13-103).  That stack is out of scope: pass `K`, or an LQR gain for the
+        identified centre (Q = I, R = I) is used."""
+        assert self.Mdata is not None, 'Mdata is not defined'
+        n, m = self.dim_x, self.dim_u
+        if K is None:
+            from scipy.linalg import solve_discrete_are
+            A, B = self._AB[:, :n], self._AB[:, n:]
+            P = solve_discrete_are(A, B, np.eye(n), np.eye(m))
+            K = -np.linalg.solve(np.eye(m) + B.T @ P @ B, B.T @ P @ A)
+        self.theta = Theta(np.asarray(K, dtype=np.float64).reshape(m, n), np.zeros((n, n)), np.zeros((n, m)))
+        return self.theta
+
+    # ---- tzddpc/tzddpc.py:95-130 ------------------------------------------------------------
+    def build_zonotopes_theta(self, zonotopes: SystemZonotopes, tol: float = 1e-5, num_max_iterations: int = 20,
+                              num_initial_points: int = 10, K: Optional[np.ndarray] = None
+                              ) -> Tuple[Theta, MatrixZonotope]:
+        self.build_zonotopes(zonotopes)
+        self.compute_theta(tol, num_max_iterations, num_initial_points, K=K)
+        n, m = self.dim_x, self.dim_u
+        d = self.dataset.original_data
+        W = zonotopes.W
+        num_raw = W.num_generators * (self.num_samples - 1)
+        if num_raw > n * (n + m):
+            # order-1 Girard reduction boxes every generator; closed form on the GPU
+            AB, dAB, dK, _, status = ops.identify(self._t(d.x)[None], self._t(d.u)[None], self._t(W.Z),
+                                                  self._t(self.theta.K)[None], False)
+            dAB_h, dK_h = dAB[0].cpu().numpy(), dK[0].cpu().numpy()
+            centreK = MatrixZonotope(self._AB, np.zeros((0, n, n + m))) * np.vstack([np.eye(n), self.theta.K])
+            self.MdataK = MatrixZonotope(centreK.center, boxed_generators(dK_h))                   # :119,127
+            self.Mdelta = MatrixZonotope(np.zeros((n, n + m)), boxed_generators(dAB_h))            # :122-123,128
+            self.Mdata = MatrixZonotope(self._AB, boxed_generators(dAB_h))                         # :126
+        else:
+            # tiny data sets: reduce(1) is a no-op (App. A.5), keep the dense generators
+            MK = self.Mdata * np.vstack([np.eye(n), self.theta.K])
+            Mdelta = self.Mdata + (-1.0 * self._AB)
+            self.Mdata, self.MdataK, self.Mdelta = self.Mdata.reduce(1), MK.reduce(1), Mdelta.reduce(1)
+        return self.theta, self.Mdata
+
+    # ---- tzddpc/tzddpc.py:132-241 / 243-355 -------------------------------------------------
+    def _model(self) -> TubeModel:
+        X, U = self.zonotopes.X.interval, self.zonotopes.U.interval
+        return TubeModel(AB=self.Mdata.center, Acl=self.MdataK.center, GK=self.MdataK.generators,
+                         GD=self.Mdelta.generators, K=self.theta.K, WZ=self.zonotopes.W.Z,
+                         X_lo=X.left_limit, X_hi=X.right_limit, U_lo=U.left_limit, U_hi=U.right_limit)
+
+    def _resolve(self, build_loss, build_constraints, horizon: int, simplified: bool):
+        from . import cvx
+        n, m = self.dim_x, self.dim_u
+        if isinstance(build_loss, StageCost):
+            cost = build_loss
+        else:
+            assert build_loss is not None, "Loss function callback cannot be none"
+            cost = cvx.extract_stage_cost(build_loss, horizon, n, m, simplified)
+        if isinstance(build_constraints, BoxConstraint):
+            box = build_constraints
+        else:
+            # quirk Q1: the reference iterates the fallback `(None, None)` and raises (tzddpc/tzddpc.py:213-217)
+            if build_constraints is None:
+                raise Exception('Constraint 0 is not defined or is not convex.')
+            box = cvx.extract_box_constraints(build_constraints, horizon, n, m, simplified)
+        return cost, box
+
+    def _build(self, horizon: int, build_loss, build_constraints, k0: Optional[int]):
+        cost, box = self._resolve(build_loss, build_constraints, horizon, k0 is not None)
+        prog = compile_program(self._model(), horizon, cost, box, k0=k0)
+        if self.verbose:
+            for k, g in enumerate(prog.gens_per_step):           # tzddpc/tzddpc.py:190,206
+                print(f'Step {k}')
+                print(g)
+        self._program = _abi.Program(prog, self.theta.K)
+        self.problem_full = self._program
+        self.horizon = horizon
+        self.parameters = ("e0", "xbar0")
+        self.variables = ("v", "xbar", "Ze")
+        self._dims = [self.dim_x, prog.nv, (horizon + 1) * self.dim_x, self.dim_x * (1 + prog.g1)]
+        return self.problem_full
+
+    def build_problem(self, horizon: int, build_loss, build_constraints=None, **kwargs):
+        return self._build(int(horizon), build_loss, build_constraints, None)
+
+    def build_problem_simplified(self, k0: int, horizon: int, build_loss, build_constraints=None, **kwargs):
+        return self._build(int(horizon), build_loss, build_constraints, int(k0))
+
+    # ---- tzddpc/tzddpc.py:357-377 -----------------------------------------------------------
+    def solve_batch(self, xbar0: torch.Tensor, e0: torch.Tensor, want_tube: bool = True,
+                    warm: Optional[torch.Tensor] = None, options: Optional[SolverOptions] = None) -> BatchSolveResult:
+        """xbar0, e0: (n, S) float64 CUDA tensors (scenario-fastest)."""
+        assert self._program is not None, "call build_problem first"
+        o = options or self.solver_options
+        cost, v, traj, ze1, status, iters = ops.solve(self._program.handle.value, self._dims, xbar0, e0, warm,
+                                                      want_tube, o.pack())
+        tube = TubeHandle(ze1, self.dim_x, self._program.compiled.g1, True) if want_tube else None
+        return BatchSolveResult(cost, v, traj, tube, status, iters)
+
+    def solve(self, xbar0: np.ndarray, e0: np.ndarray, **kwargs):
+        """Batch 1 (1-D inputs): the reference's return tuple `(result, v, xbar, Ze[1])`.
+        Batched ((S, n) inputs): `(cost[S], v[S,N,m], xbar[S,N+1,n], tube, status[S])`."""
+        n, m, N = self.dim_x, self.dim_u, self.horizon
+        xb = np.asarray(xbar0, dtype=np.float64)
+        ee = np.asarray(e0, dtype=np.float64)
+        batched = xb.ndim == 2
+        xb2, ee2 = np.atleast_2d(xb), np.atleast_2d(ee)
+        assert xb2.shape[1] == n and ee2.shape == xb2.shape, "Invalid size"
+        r = self.solve_batch(self._t(xb2.T), self._t(ee2.T))
+        status = r.status.cpu().numpy()
+        cost = r.cost.cpu().numpy()
+        v = r.v.cpu().numpy().T.reshape(-1, N, m)
+        xbar = r.xbar.cpu().numpy().T.reshape(-1, N + 1, n)
+        if batched:
+            return cost, v, xbar, r.tube, status
+        if status[0] == _abi.TZ_STATUS_NONFINITE:
+            with open('zpc_logs.txt', 'w') as f:                             # tzddpc/tzddpc.py:368-371
+                print('Error while solving the TZDDPC problem. Details: non-finite data', file=f)
+            raise Exception('Error while solving the TZDDPC problem. Details: non-finite data')
+        if np.isinf(cost[0]):
+            raise Exception('Problem is unbounded')                          # tzddpc/tzddpc.py:374-375
+        tube = TubeHandle(r.tube._ze1, n, self._program.compiled.g1, False)
+        return float(cost[0]), v[0], xbar[0], tube
+
+    # ---- batched closed loop (examples/2.pulley_sim.py:62-103, one scenario per column) --------
+    def simulate(self, A_true: np.ndarray, B_true: np.ndarray, x0: np.ndarray, noise, keep_tubes: bool = False,
+                 options: Optional[SolverOptions] = None):
+        """Run the closed loop for S scenarios in lock step.
+        x0: (S, n); noise: (steps, S, n) array or CUDA tensor (steps, n, S).
+        Returns dict with x (steps+1, S, n), xbar, e, u, v0, cost (steps, S), status (steps, S), stats (steps, 8)."""
+        assert self._program is not None, "call build_problem first"
+        n, m = self.dim_x, self.dim_u
+        o = options or self.solver_options
+        x0 = np.atleast_2d(np.asarray(x0, dtype=np.float64))
+        S = x0.shape[0]
+        if isinstance(noise, torch.Tensor):
+            w = noise
+        else:
+            w = self._t(np.transpose(np.asarray(noise, dtype=np.float64), (0, 2, 1)))
+        steps = w.shape[0]
+        dev = self.device
+        f64 = dict(dtype=torch.float64, device=dev)
+        x, xbar = self._t(x0.T), self._t(x0.T)
+        e = torch.zeros((n, S), **f64)
+        At, Bt = self._t(A_true), self._t(B_true)
+        xs = torch.empty((steps + 1, n, S), **f64)
+        xbars = torch.empty_like(xs)
+        es = torch.empty_like(xs)
+        us = torch.empty((steps, m, S), **f64)
+        vs = torch.empty((steps, self._dims[1], S), **f64)
+        costs = torch.empty((steps, S), **f64)
+        stat = torch.empty((steps, S), dtype=torch.int32, device=dev)
+        iters = torch.empty((steps, S), dtype=torch.int32, device=dev)
+        stats = torch.zeros((steps, _abi.TZ_NSTATS), **f64)
+        tubes = torch.empty((steps, self._dims[3], S), **f64) if keep_tubes else None
+        wr = ops.warm_rows(self._program_nz(), self._program_nc())
+        warm = torch.zeros((wr, S), **f64) if o.warm_start else None
+        xs[0], xbars[0], es[0] = x, xbar, e
+        h = self._program.handle.value
+        for t in range(steps):
+            ops.closed_loop_step(h, x, xbar, e, w[t].contiguous(), At, Bt, stat[t], costs[t], vs[t], None,
+                                 tubes[t] if keep_tubes else None, us[t], iters[t], warm, stats[t], o.pack())
+            xs[t + 1], xbars[t + 1], es[t + 1] = x, xbar, e
+        out = {"x": xs.permute(0, 2, 1).cpu().numpy(), "xbar": xbars.permute(0, 2, 1).cpu().numpy(),
+               "e": es.permute(0, 2, 1).cpu().numpy(), "u": us.permute(0, 2, 1).cpu().numpy(),
+               "v": vs.permute(0, 2, 1).cpu().numpy(), "cost": costs.cpu().numpy(), "status": stat.cpu().numpy(),
+               "iters": iters.cpu().numpy(), "stats": stats.cpu().numpy()}
+        if keep_tubes:
+            g1 = self._program.compiled.g1
+            out["tubes"] = tubes.reshape(steps, n, 1 + g1, S).permute(0, 3, 1, 2).cpu().numpy()
+        return out
+
+    def _program_nz(self) -> int:
+        return int(self._program.bucket.split("NZ=")[1].split(",")[0])
+
+    def _program_nc(self) -> int:
+        return int(self._program.bucket.split("NC=")[1].split(")")[0])
