@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""Benchmark of the TZDDPC hot path: closed-loop steps/sec over batched scenarios.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload fivedim|pulley|double_integrator]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A "step" is ONE fused closed-loop step (solve + tube + plant/nominal/error update,
+examples/3.5dimsystem_sim.py:73-89) over the whole scenario batch of a GPU.  Default workload:
+BASELINE.json configs[3], the 5-dim system with 65,536 scenarios (noise realisations) per GPU
+("weak" scaling: every rank simulates its own 65,536 scenarios; no collective in the loop,
+one NCCL all-reduce of the closed-loop statistics after it).
+
+Prints ONE JSON line (rank 0).  `value` = scenario-steps/s with all state resident in HBM;
+`e2e` = the same through the host-buffer C-ABI call (pinned host arrays in, every output of
+`solve` back on the host each step); `roofline` = algorithmic HBM bytes over the
+CUDA-event duration of the fused kernel; `cpu_baseline` = the CPU oracle port timed here.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "closed-loop TZDDPC steps/sec over batched scenarios"
+UNIT = "scenario-steps/s"
+
+
+def algorithmic_bytes_per_scenario_step(n, m, N, g1):
+    """read x, xbar, e; write x+, xbar+, e+, v, xbar trajectory, cost, Ze[1].Z, status."""
+    return 8 * (6 * n + N * m + (N + 1) * n + 1 + n * (1 + g1)) + 4
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU side: the oracle port (the reference itself cannot be imported: cvxpy/pyzonotope are absent)
+# ----------------------------------------------------------------------------------------------
+def _oracle_setup(workload):
+    import oracle
+    from tzddpc_b200 import configs
+    cfg = configs.CONFIGS[workload]()
+    rng = np.random.default_rng(cfg.seed)
+    u, x = configs.generate_dataset(cfg, rng)
+    Z = oracle.Zonotope
+    zon = oracle.SystemZonotopes(Z(*cfg.X0), Z(*cfg.U), Z(*cfg.X), Z(*cfg.W))
+    o = oracle.OracleTZDDPC(oracle.Data(u, x))
+    o.build_zonotopes(zon)
+    C = o.Mdata.center
+    K = configs.lqr_gain(C[:, :cfg.n], C[:, cfg.n:])
+    o.build_zonotopes_theta(zon, K)
+    box = oracle.BoxConstraint(**cfg.box) if cfg.box else None
+    o.build_problem(cfg.horizon, oracle.StageCost(**cfg.cost), box)
+    return cfg, o
+
+
+def _oracle_worker(args):
+    """Closed loop of `scen` scenarios for warmup+steps steps; returns seconds spent in the timed steps."""
+    workload, scen, warmup, steps, seed = args
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    cfg, o = _oracle_setup(workload)
+    rng = np.random.default_rng(seed)
+    cW, GW = cfg.W
+    n, K = cfg.n, o.theta.K
+    x = np.tile(np.asarray(cfg.X0[0], dtype=np.float64), (scen, 1))
+    xbar, e = x.copy(), np.zeros_like(x)
+    t_timed = 0.0
+    for t in range(warmup + steps):
+        w = cW[None] + rng.uniform(-1, 1, size=(scen, GW.shape[1])) @ GW.T
+        t0 = time.perf_counter()
+        for s in range(scen):
+            r = o.solve_status(xbar[s], e[s], check_feasibility=False)
+            if r.status == 2:
+                continue
+            u = K @ e[s] + r.v[0]
+            x[s] = cfg.A @ x[s] + cfg.B @ u + w[s]
+            xbar[s] = r.xbar[1]
+            e[s] = x[s] - xbar[s]
+        if t >= warmup:
+            t_timed += time.perf_counter() - t0
+    return t_timed
+
+
+def cpu_oracle_throughput(workload, cores, scen_per_core, warmup, steps):
+    """scenario-steps/s of the oracle port on `cores` host processes (one per core)."""
+    jobs = [(workload, scen_per_core, warmup, steps, 1000 + i) for i in range(cores)]
+    if cores == 1:
+        times = [_oracle_worker(jobs[0])]
+    else:
+        import multiprocessing as mp
+        with mp.get_context("spawn").Pool(cores) as pool:
+            times = pool.map(_oracle_worker, jobs)
+    return cores * scen_per_core * steps / max(times), max(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0))
+    # a "step" here is one closed-loop step over a bounded sample of 2 scenarios per core
+    scen_per_core = 2
+    val, secs = cpu_oracle_throughput(args.workload, cores, scen_per_core, args.warmup, args.steps)
+    sample = f"{cores * scen_per_core} scenarios x {args.steps} closed-loop steps, one process per core"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "note": "CPU oracle port of the reference path (the reference needs "
+                       "cvxpy/pyzonotope, absent here); bounded sample of the same workload"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, uuid):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", uuid], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, val in zip(names, r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import tzddpc_b200 as tz
+    from tzddpc_b200 import _abi, configs, ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = configs.CONFIGS[args.workload]()
+    S, K_steps, W_steps = args.scenarios, args.steps, args.warmup
+    n, m, N = cfg.n, cfg.m, cfg.horizon
+
+    # ---- setup (not timed): identify on the GPU, canonicalise, upload the program
+    rng = np.random.default_rng(cfg.seed)
+    u_data, x_data = configs.generate_dataset(cfg, rng)
+    ctl = tz.TZDDPC(tz.Data(u_data, x_data), device=dev)
+    ctl.verbose = False
+    Z = tz.Zonotope
+    zon = tz.SystemZonotopes(Z(*cfg.X0), Z(*cfg.U), Z(*cfg.X), Z(*cfg.W))
+    ctl.build_zonotopes(zon)
+    Kgain = configs.lqr_gain(ctl.Mdata.center[:, :n], ctl.Mdata.center[:, n:])
+    ctl.build_zonotopes_theta(zon, K=Kgain)
+    ctl.build_problem(N, tz.StageCost(**cfg.cost), tz.BoxConstraint(**cfg.box) if cfg.box else tz.BoxConstraint())
+    prog = ctl._program
+    g1 = prog.compiled.g1
+    nent, nt, nv = n * (1 + g1), (N + 1) * n, prog.compiled.nv
+    opts = tz.SolverOptions(warm_start=bool(args.warm_start))
+    po = opts.pack()
+
+    f64 = dict(dtype=torch.float64, device=dev)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(cfg.seed + 7919 * rank)
+    cW, GW = torch.tensor(cfg.W[0], **f64), torch.tensor(cfg.W[1], **f64)
+    total = W_steps + K_steps
+    beta = torch.rand((total, GW.shape[1], S), generator=gen, **f64) * 2 - 1
+    if cfg.noise == "vertex":
+        beta = torch.sign(beta)
+    noise = (cW[None, :, None] + torch.einsum("rg,tgs->trs", GW, beta)).contiguous()      # (total, n, S)
+    del beta
+    x0 = torch.tensor(cfg.X0[0], **f64)
+    x = x0[:, None].repeat(1, S).contiguous()
+    xbar = x.clone()
+    e = torch.zeros((n, S), **f64)
+    At, Bt = torch.tensor(cfg.A, **f64), torch.tensor(cfg.B, **f64)
+    ring = 4
+    ze1 = torch.empty((ring, nent, S), **f64)
+    traj = torch.empty((ring, nt, S), **f64)
+    vbuf = torch.empty((ring, nv, S), **f64)
+    cost = torch.empty((ring, S), **f64)
+    status = torch.zeros((total, S), dtype=torch.int32, device=dev)
+    iters = torch.zeros((total, S), dtype=torch.int32, device=dev)
+    stats = torch.zeros((total, _abi.TZ_NSTATS), **f64)
+    warm = torch.zeros((ops.warm_rows(ctl._program_nz(), ctl._program_nc()), S), **f64) if args.warm_start else None
+    h = prog.handle.value
+
+    def step(t):
+        r = t % ring
+        ops.closed_loop_step(h, x, xbar, e, noise[t], At, Bt, status[t], cost[r], vbuf[r], traj[r], ze1[r], None,
+                             iters[t], warm, stats[t], po)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for t in range(W_steps):
+        step(t)
+    barrier()
+    sampler = ClockSampler("GPU-" + str(torch.cuda.get_device_properties(dev).uuid)) if rank == 0 else None
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K_steps + 1)]
+    t_wall0 = time.perf_counter()
+    ev[0].record()
+    for k in range(K_steps):
+        step(W_steps + k)
+        ev[k + 1].record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    elapsed_ms = ev[0].elapsed_time(ev[-1])
+    kern_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(K_steps)]
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    el = torch.tensor([elapsed_ms], **f64)
+    if world > 1:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(el.item())
+    # final statistics: the only collective of the path
+    tot_stats = stats[W_steps:].sum(0)
+    if world > 1:
+        dist.all_reduce(tot_stats, op=dist.ReduceOp.SUM)
+    tot_stats = tot_stats.cpu().numpy()
+    st = status[W_steps:]
+    it = iters[W_steps:].double()
+
+    value = world * S * K_steps / (elapsed_ms * 1e-3)
+    bstep = algorithmic_bytes_per_scenario_step(n, m, N, g1)
+    peak, peak_src = measured_hbm_peak()
+    avg_kernel_ms = float(np.mean(kern_ms))
+    achieved = bstep * S / (avg_kernel_ms * 1e-3) / 1e9
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K_steps, "warmup": W_steps,
+            "ms_per_step": elapsed_ms / K_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{cfg.name}: n={n} m={m} T={cfg.T} horizon={N}, {S} scenarios per GPU (noise realisations, "
+                                   f"shared data set), closed loop", "scenarios_per_gpu": S, "parallelism": f"scenario-dp{world}",
+                       "l2": f"per-step HBM traffic {bstep * S / 1e6:.0f} MB > 126 MB L2 (inputs larger than L2)",
+                       "solver": {"warm_start": bool(args.warm_start), "eps": opts.eps_abs, "polish": True},
+                       "kernel_bucket": prog.bucket},
+            "gpu_launches": K_steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "bytes_per_scenario_step": bstep,
+                         "kernel_ms_avg": avg_kernel_ms, "kernel": "tz::step_kernel_param"},
+            "solver_stats": {"iters_mean": float(it.mean().item()), "iters_max": int(it.max().item()),
+                             "status_ok_frac": float((st == 0).double().mean().item()),
+                             "infeasible": int((st == 2).sum().item()), "maxiter": int((st == 1).sum().item()),
+                             "mean_norm_x": float(tot_stats[0] / max(tot_stats[7], 1.0))},
+            "clocks": clocks}
+
+    # ---- e2e: host buffers through the C-ABI host entry point, every output back on the host
+    if not args.no_e2e:
+        Ke = max(3, min(args.e2e_steps, K_steps))
+        pin = lambda *shape, dt=torch.float64: torch.empty(shape, dtype=dt).pin_memory()     # noqa: E731
+        hx, hxb, he = pin(n, S), pin(n, S), pin(n, S)
+        hx.copy_(x0[:, None].cpu().expand(n, S)); hxb.copy_(hx); he.zero_()
+        hnoise = pin(Ke + 2, n, S)
+        hnoise.copy_(noise[:Ke + 2].cpu())
+        hcost, hv, htraj, hze = pin(S), pin(nv, S), pin(nt, S), pin(nent, S)
+        hstat = pin(S, dt=torch.int32)
+        scratch = torch.empty(_abi.lib().tz_closed_loop_step_host_scratch_bytes(h, S) // 8 + 8, **f64)
+        import ctypes as C
+        o_ = ops._opts(po)
+        Ah, Bh = np.ascontiguousarray(cfg.A), np.ascontiguousarray(cfg.B)
+
+        def host_step(t):
+            rc = _abi.lib().tz_closed_loop_step_host(
+                C.c_void_p(h), C.byref(o_), S, C.c_void_p(hx.data_ptr()), C.c_void_p(hxb.data_ptr()), C.c_void_p(he.data_ptr()),
+                C.c_void_p(hnoise[t].data_ptr()), C.c_void_p(Ah.ctypes.data), C.c_void_p(Bh.ctypes.data),
+                C.c_void_p(hcost.data_ptr()), C.c_void_p(hv.data_ptr()), C.c_void_p(htraj.data_ptr()), C.c_void_p(hze.data_ptr()),
+                C.c_void_p(hstat.data_ptr()), C.c_void_p(scratch.data_ptr()), args.e2e_chunks)
+            _abi.check(rc, "tz_closed_loop_step_host")
+
+        for t in range(2):
+            host_step(t)
+        barrier()
+        t0 = time.perf_counter()
+        for t in range(Ke):
+            host_step(2 + t)
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], **f64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        line["e2e"] = {"value": world * S * Ke / dt, "unit": UNIT, "h2d_bytes_per_step": int(4 * n * S * 8 + 8 * (n * n + n * m)),
+                       "d2h_bytes_per_step": int(S * (8 * (3 * n + 1 + nv + nt + nent) + 4)), "steps": Ke,
+                       "ms_per_step": 1e3 * dt / Ke, "api": "tz_closed_loop_step_host (pinned host buffers)",
+                       "status_ok_frac": float((hstat == 0).double().mean().item())}
+
+    # ---- CPU baseline on this box's host cores (rank 0, N = 1 only): the oracle port, single core
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        scen, cpu_steps = 1, args.cpu_steps
+        val, secs = cpu_oracle_throughput(args.workload, 1, scen, 2, cpu_steps)
+        line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": f"{scen} scenario x {cpu_steps} closed-loop steps of the same workload "
+                                          f"({secs:.1f} s), numpy oracle", "host_cores_available": len(os.sched_getaffinity(0))}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="fivedim", choices=["fivedim", "pulley", "double_integrator"])
+    ap.add_argument("--scenarios", type=int, default=65536, help="scenarios per GPU")
+    ap.add_argument("--warm-start", type=int, default=0)
+    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--e2e-chunks", type=int, default=4)
+    ap.add_argument("--cpu-steps", type=int, default=1500)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()
