@@ -200,7 +200,7 @@ def run_gpu(args):
     prog = ctl._program
     g1 = prog.compiled.g1
     nent, nt, nv = n * (1 + g1), (N + 1) * n, prog.compiled.nv
-    opts = tz.SolverOptions(warm_start=bool(args.warm_start))
+    opts = tz.SolverOptions(warm_start=bool(args.warm_start), check_every=args.check_every, eps_abs=args.eps, eps_rel=args.eps)
     po = opts.pack()
 
     f64 = dict(dtype=torch.float64, device=dev)
@@ -226,7 +226,7 @@ def run_gpu(args):
     status = torch.zeros((total, S), dtype=torch.int32, device=dev)
     iters = torch.zeros((total, S), dtype=torch.int32, device=dev)
     stats = torch.zeros((total, _abi.TZ_NSTATS), **f64)
-    warm = torch.zeros((ops.warm_rows(ctl._program_nz(), ctl._program_nc()), S), **f64) if args.warm_start else None
+    warm = torch.zeros((prog.warm_rows, S), **f64) if args.warm_start else None
     h = prog.handle.value
 
     def step(t):
@@ -351,6 +351,8 @@ def main():
     ap.add_argument("--workload", default="fivedim", choices=["fivedim", "pulley", "double_integrator"])
     ap.add_argument("--scenarios", type=int, default=65536, help="scenarios per GPU")
     ap.add_argument("--warm-start", type=int, default=0)
+    ap.add_argument("--check-every", type=int, default=4)
+    ap.add_argument("--eps", type=float, default=1e-6)
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--e2e-chunks", type=int, default=4)
     ap.add_argument("--cpu-steps", type=int, default=1500)

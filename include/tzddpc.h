@@ -91,8 +91,10 @@ typedef struct TzProgram TzProgram;   /* opaque */
 
 int tz_program_create(const TzProgramDesc* desc, TzProgram** out);
 void tz_program_destroy(TzProgram* prog);
-/* which compiled kernel bucket serves this program: writes "NZxNCx..." into buf */
+/* which compiled kernel bucket serves this program: writes e.g. "B2(NZ=2,NC=28,G=4)" into buf */
 int tz_program_bucket(const TzProgram* prog, char* buf, size_t cap);
+/* rows of the `warm` scratch array (rows x S doubles) that tz_solve / tz_closed_loop_step accept */
+int tz_program_warm_rows(const TzProgram* prog);
 
 typedef struct TzSolverOpts {
   double rho;        /* base ADMM penalty (scaled problem)         default 0.1  */
@@ -102,8 +104,8 @@ typedef struct TzSolverOpts {
   double alpha;      /* over-relaxation                            default 1.6  */
   double eps_abs, eps_rel;   /*                                     default 1e-6 */
   int32_t max_iter;  /*                                            default 4000 */
-  int32_t check_every;/* residual check period                     default 4    */
-  int32_t polish;    /* masked augmented-Lagrangian polish on/off  default 1    */
+  int32_t check_every;/* residual check period                     default 8    */
+  int32_t polish;    /* masked augmented-Lagrangian polish: number of iterations, 0 = off   default 3 */
   int32_t warm_start;/* reuse (z, y) from the `warm` buffer        default 0    */
 } TzSolverOpts;
 
@@ -117,7 +119,7 @@ void tz_solver_opts_default(TzSolverOpts* o);
  *        xbar_traj           ((N+1)*n) x S
  *        ze1                 (n*(1+g1)) x S   Ze[1].Z, entry (r, j) at row r*(1+g1)+j
  *        status, iters       S   (int32)
- *   warm: (nz + nc) x S scratch carrying (zbar, ybar) between calls, or NULL
+ *   warm: tz_program_warm_rows(prog) x S scratch carrying the ADMM iterate between calls, or NULL
  *   any of cost / v / xbar_traj / ze1 / iters may be NULL (not written).
  * ------------------------------------------------------------------------------------ */
 int tz_solve(const TzProgram* prog, const TzSolverOpts* opts, int64_t S,

@@ -7,7 +7,9 @@ from pathlib import Path
 
 import numpy as np
 
-LIB_PATH = Path(__file__).resolve().parent / "lib" / "libtzddpc.so"
+import os
+
+LIB_PATH = Path(os.environ.get("TZDDPC_LIB", Path(__file__).resolve().parent / "lib" / "libtzddpc.so"))
 
 TZ_OK = 0
 TZ_STATUS_OK, TZ_STATUS_MAXITER, TZ_STATUS_INFEASIBLE, TZ_STATUS_NONFINITE = 0, 1, 2, 3
@@ -36,7 +38,7 @@ class TzddpcLibraryMissing(RuntimeError):
 _lib = None
 
 # every symbol include/tzddpc.h declares (tests/test_abi.py checks the library exports all of them)
-EXPORTS = ["tz_version", "tz_last_error", "tz_device_cc", "tz_program_create", "tz_program_destroy", "tz_program_bucket",
+EXPORTS = ["tz_version", "tz_last_error", "tz_device_cc", "tz_program_create", "tz_program_destroy", "tz_program_bucket", "tz_program_warm_rows",
            "tz_solver_opts_default", "tz_solve", "tz_closed_loop_step", "tz_closed_loop_step_host_scratch_bytes",
            "tz_closed_loop_step_host", "tz_interval_hull", "tz_reach_step", "tz_girard_reduce", "tz_identify",
            "tz_qp_solve"]
@@ -62,6 +64,8 @@ def lib() -> C.CDLL:
     L.tz_program_destroy.argtypes = [vp]
     L.tz_program_bucket.restype = C.c_int
     L.tz_program_bucket.argtypes = [vp, C.c_char_p, C.c_size_t]
+    L.tz_program_warm_rows.restype = C.c_int
+    L.tz_program_warm_rows.argtypes = [vp]
     L.tz_solver_opts_default.restype = None
     L.tz_solver_opts_default.argtypes = [C.POINTER(TzSolverOpts)]
     L.tz_solve.restype = C.c_int
@@ -130,6 +134,7 @@ class Program:
         buf = C.create_string_buffer(64)
         L.tz_program_bucket(h, buf, 64)
         self.bucket = buf.value.decode()
+        self.warm_rows = int(L.tz_program_warm_rows(h))
 
     def __del__(self):
         try:

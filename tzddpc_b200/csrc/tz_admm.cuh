@@ -1,61 +1,105 @@
-// Batched ADMM QP core: one scenario per thread, the whole KKT system of that scenario in
-// registers (NZ x NZ Cholesky factor, z, y) and its bounds in shared memory.
+// Batched ADMM QP core: G adjacent lanes of a warp cooperate on one scenario.
 //
 // Replaces `problem_full.solve(**kw)` of the reference (tzddpc/tzddpc.py:367), which hands a
 // cvxpy-canonicalised cone program to a CPU interior-point solver.  Here the program is the
 // parametric QP of tzddpc_b200/program.py in OSQP form, already Ruiz-scaled on the host:
 //
-//     min 0.5 x'Px + q'x + sum_{i<NKINK} w_i |(Ax)_i - k_i|    s.t.  l <= Ax <= u
+//     min 0.5 x'Px + q'x + sum_{kink rows} w_i |(Ax)_i - k_i|    s.t.  l <= Ax <= u
 //
-// Algorithm: OSQP-style ADMM (x-update through the reduced NZ x NZ system
-// P + sigma I + A' diag(rho) A, over-relaxation alpha) with
+// Work split: the rows are sorted by class on the host (two-sided / |.|-cost rows, upper-only
+// rows, lower-only rows; each class padded to a multiple of G) and row slot i belongs to lane
+// (i mod G) of the scenario's lane group, so every lane owns N2 two-sided, NU upper-only and
+// NL lower-only rows -- known at compile time, which removes the dead half of every clip --
+// and keeps its rows of (alpha A, bound, z, w, rho) in registers.  The NZ-vector x and the
+// NZ x NZ Cholesky factor of the reduced KKT matrix  K = P + sigma I + A' diag(rho) A  are
+// replicated in every lane of the group; A'(.) products are group all-reduces with
+// xor-shuffles (bitwise identical in every lane, so control flow stays group-uniform).
+// ncu evidence for this layout: profiles/r1_v0_* (one thread per scenario: 255 registers,
+// spills, 13 % FP64 pipe) and profiles/r1_v1_* (lane groups, un-tuned loop: 20 % of the
+// issued instructions were FP64).
+//
+// Algorithm: OSQP-style ADMM with over-relaxation alpha, plus
 //   * the |.| cost rows handled by their prox (soft threshold) inside the z-update, so an
-//     LP cost needs no slack variable,
+//     LP cost needs no slack variable;
 //   * a per-row penalty rho_i switched between rho*rho_active / rho*rho_inactive by the
 //     detected activity of the row, on a geometrically growing schedule (updates stop
-//     changing once the active set has settled, after which this is plain ADMM),
-//   * OSQP's primal-infeasibility certificate on the dual increments,
+//     changing once the active set has settled, after which this is plain ADMM);
+//   * OSQP's primal-infeasibility certificate on the dual increments;
 //   * a masked augmented-Lagrangian polish on the detected active set.
-// The matrices (P, A, ...) are shared by all scenarios of a launch and are read straight
-// from the constant bank (the program is a __grid_constant__ kernel parameter), so every
-// DFMA of the inner loops takes its matrix operand without a load instruction.
+// Inner-loop algebra (per row, 9 FP64 instructions + one 3-instruction clip):
+//   the scaled dual w = y / rho is stored instead of y;  Aa = alpha A is stored instead of A
+//   and rq = rho / alpha instead of rho, so that  zr = Aa xt + (1-alpha) z  is one chain of
+//   FMAs and  A'(rho (z - w)) = Aa'(rq (2 z+ - xi)).
 #pragma once
 #include "tz_common.cuh"
 
 namespace tz {
 
-template <int NZ_, int NC_, int NPAR_, int NA_, int NCHK_, int NKINK_, int TPB_>
+template <int NZ_, int N2_, int NU_, int NL_, int G_, int NPAR_, int NAG_, int NCHK_, int MINB_>
 struct Bucket {
-  static constexpr int NZ = NZ_, NC = NC_, NPAR = NPAR_, NA = NA_, NCHK = NCHK_, NKINK = NKINK_, TPB = TPB_;
-  static constexpr int NCOL = 1 + NPAR + NA;
-  static constexpr int NW32 = (NC + 31) / 32;
+  static constexpr int NZ = NZ_, N2 = N2_, NU = NU_, NL = NL_, G = G_, NPAR = NPAR_, NAG = NAG_, NCHK = NCHK_;
+  static constexpr int MINB = MINB_;                  // CTAs per SM the register budget is set for
+  static constexpr int NCL = N2 + NU + NL;            // constraint rows per lane
+  static constexpr int NC = NCL * G;                  // row slots
+  static constexpr int NK = N2 * G;                   // slots that may carry a |.| cost
+  static constexpr int NCOL = 1 + 2 * NPAR + NAG;     // [1 | p | |p| | general atoms]
+  static constexpr int NCHL = (NCHK + G - 1) / G;
+  static constexpr int TPB = 128;
+  static constexpr int WPB = TPB / 32;                // warps per CTA
+  static constexpr int SPW = 32 / G;                  // scenarios per warp tile
+  static_assert(NCL <= 32 && (G & (G - 1)) == 0 && G <= 32 && N2 >= 1 && NAG >= 1, "bad bucket");
 };
 
-// Scaled program, padded to the bucket (padding rows: A = 0, l = -inf, u = +inf).
+// Scaled program, padded to the bucket (padding rows: A = 0, bounds infinite).
 template <class BK>
 struct QpProg {
   double P[BK::NZ][BK::NZ];
-  double A[BK::NC][BK::NZ];
+  double A[BK::NC][BK::NZ];            // E A D (NOT multiplied by alpha)
   double l0[BK::NC], u0[BK::NC];
-  double kink0[BK::NKINK], wabs[BK::NKINK];
+  double kink0[BK::NK], wabs[BK::NK];
   double R[BK::NC][BK::NCOL];
   double q0[BK::NZ];
   double Qp[BK::NZ][BK::NPAR];
-  double Bt[BK::NA][BK::NPAR];
-  double gam[BK::NA];
+  double Bt[BK::NAG][BK::NPAR];        // general atoms |Bt p + gam| (the unit atoms |p_c| are implicit)
+  double gam[BK::NAG];
   double Rchk[BK::NCHK][BK::NCOL];
   double cc[BK::NCOL];
   double CC2[BK::NPAR][BK::NPAR];
   double D[BK::NZ];
   double Einv[BK::NC];
-  double cinv;            // 1 / cost scaling
-  int nz, nc, npar, na, nchk, nkink;
+  double cinv;                          // 1 / cost scaling
+  int row_of_slot[BK::NC];              // original row index of a slot, -1 for padding
+  int nz, nc, npar, nag, nchk, has_cc2;
 };
 
 struct SolverParams {     // TzSolverOpts, device side
   double rho, rho_act, rho_inact, sigma, alpha, eps_abs, eps_rel;
   int max_iter, check_every, polish, warm;
 };
+
+// compare-select min/max: 3 instructions instead of the ~8 of IEEE fmin/fmax (no NaN quieting needed:
+// non-finite inputs are rejected before the solve and NaN iterates are caught by the residual check)
+__device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }
+__device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
+
+template <int G>
+__device__ __forceinline__ double gsum(double v) {
+#pragma unroll
+  for (int o = 1; o < G; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <int G>
+__device__ __forceinline__ double gmax(double v) {
+#pragma unroll
+  for (int o = 1; o < G; o <<= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+template <int G>
+__device__ __forceinline__ int gor(int v) {
+#pragma unroll
+  for (int o = 1; o < G; o <<= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
 
 template <int NZ>
 __device__ __forceinline__ void chol_factor(double (&K)[NZ][NZ]) {
@@ -96,173 +140,208 @@ __device__ __forceinline__ void chol_solve(const double (&L)[NZ][NZ], double (&b
   }
 }
 
+// Per-lane slice of one scenario's QP.  Local row k: k < N2 two-sided / kink, k < N2+NU upper
+// only, else lower only.
 template <class BK>
-struct RhoSet {            // the three penalty levels and their inverses
-  double base, act, inact, ibase, iact, iinact;
+struct LaneQp {
+  double Aa[BK::NCL][BK::NZ];    // alpha * (this lane's rows of the scaled constraint matrix)
+  double lo[BK::N2 + BK::NL];    // lower bounds of the two-sided rows, then of the lower-only rows
+  double hi[BK::N2 + BK::NU];    // upper bounds of the two-sided rows, then of the upper-only rows
+  double kink[BK::N2];
+  double q[BK::NZ];
+  const double* wk;              // shared memory: |.| weights of this lane's two-sided rows, element k at [k * G]
+  const double (*P)[BK::NZ];     // shared memory: the scaled P (only read at factorisations and residual checks)
+  __device__ __forceinline__ double lower(int k) const { return k < BK::N2 ? lo[k] : (k >= BK::N2 + BK::NU ? lo[k - BK::NU] : -INFINITY); }
+  __device__ __forceinline__ double upper(int k) const { return k < BK::N2 + BK::NU ? hi[k] : INFINITY; }
+  __device__ __forceinline__ double clip(int k, double v) const {
+    if (k < BK::N2) return dmin(dmax(v, lo[k]), hi[k]);
+    if (k < BK::N2 + BK::NU) return dmin(v, hi[k]);
+    return dmax(v, lo[k - BK::NU]);
+  }
+  __device__ __forceinline__ bool at_bound(int k, double z) const {
+    if (k < BK::N2) return (z <= lo[k]) || (z >= hi[k]) || (wk[k * BK::G] > 0.0 && z == kink[k]);
+    if (k < BK::N2 + BK::NU) return z >= hi[k];
+    return z <= lo[k - BK::NU];
+  }
 };
 
 template <class BK>
-__device__ __forceinline__ double row_rho(const RhoSet<BK>& r, bool switched, bool active) {
-  return switched ? (active ? r.act : r.inact) : r.base;
-}
-template <class BK>
-__device__ __forceinline__ double row_irho(const RhoSet<BK>& r, bool switched, bool active) {
-  return switched ? (active ? r.iact : r.iinact) : r.ibase;
-}
+struct LaneState {
+  double x[BK::NZ];
+  double z[BK::NCL], w[BK::NCL];  // inside admm_solve w = y / rho_row; y on entry (warm) and exit
+  uint32_t act;                   // activity bits of the local rows
+  bool switched;                  // false: every row still at the base rho
+};
 
-// K = P + sigma I + sum_i rho_i a_i a_i'   (lower triangle), then factor.
-template <class BK, class PG>
-__device__ __forceinline__ void build_factor(const PG& pg, const RhoSet<BK>& rs, double sigma, bool switched,
-                                             const uint32_t (&mask)[BK::NW32], double (&L)[BK::NZ][BK::NZ]) {
-  constexpr int NZ = BK::NZ, NC = BK::NC;
+// K = P + sigma I + sum_i rho_i a_i a_i'  (group all-reduce of the lower triangle), then factor.
+// rq = rho / alpha and Aa = alpha A  =>  rho a a' = (rq / alpha) Aa Aa'.
+template <class BK>
+__device__ __forceinline__ void build_factor(const LaneQp<BK>& qp, const double (&rq)[BK::NCL], double inv_alpha,
+                                             double sigma, double (&L)[BK::NZ][BK::NZ]) {
+  constexpr int NZ = BK::NZ, NCL = BK::NCL, G = BK::G;
 #pragma unroll
   for (int a = 0; a < NZ; ++a)
 #pragma unroll
-    for (int b = 0; b <= a; ++b) L[a][b] = pg.P[a][b] + (a == b ? sigma : 0.0);
+    for (int b = 0; b <= a; ++b) L[a][b] = 0.0;
 #pragma unroll
-  for (int i = 0; i < NC; ++i) {
-    const double rho = row_rho<BK>(rs, switched, (mask[i >> 5] >> (i & 31)) & 1u);
+  for (int k = 0; k < NCL; ++k) {
 #pragma unroll
     for (int a = 0; a < NZ; ++a) {
-      const double ra = rho * pg.A[i][a];
+      const double ra = rq[k] * qp.Aa[k][a];
 #pragma unroll
-      for (int b = 0; b <= a; ++b) L[a][b] = fma(ra, pg.A[i][b], L[a][b]);
+      for (int b = 0; b <= a; ++b) L[a][b] = fma(ra, qp.Aa[k][b], L[a][b]);
     }
   }
+#pragma unroll
+  for (int a = 0; a < NZ; ++a)
+#pragma unroll
+    for (int b = 0; b <= a; ++b) L[a][b] = fma(gsum<G>(L[a][b]), inv_alpha, qp.P[a][b] + (a == b ? sigma : 0.0));
   chol_factor<NZ>(L);
 }
 
-// One scenario's ADMM solve.  lb/ub: shared memory, element i at [i * BK::TPB].
-// Every thread of the warp must call this (warp votes inside); `live` = has a real scenario.
-// Returns TZ_STATUS_*.  x is in the scaled space (z_unscaled = D x).
-template <class BK, class PG>
-__device__ int admm_solve(const PG& pg, const SolverParams& sp, bool live, const double (&q)[BK::NZ],
-                          const double* __restrict__ lb, const double* __restrict__ ub,
-                          const double (&kink)[BK::NKINK], double (&x)[BK::NZ], double (&z)[BK::NC],
-                          double (&y)[BK::NC], uint32_t (&mask)[BK::NW32], bool warm, int& iters_out) {
-  constexpr int NZ = BK::NZ, NC = BK::NC, NKINK = BK::NKINK, TPB = BK::TPB;
-  RhoSet<BK> rs;
-  rs.base = sp.rho; rs.act = sp.rho * sp.rho_act; rs.inact = sp.rho * sp.rho_inact;
-  rs.ibase = 1.0 / rs.base; rs.iact = 1.0 / rs.act; rs.iinact = 1.0 / rs.inact;
-  const double alpha = sp.alpha, sigma = sp.sigma;
+// ADMM for the scenario owned by this lane group.  Every lane of the warp must call it
+// (shuffles and warp votes inside); `live` is group-uniform.  On a warm start st.x, st.w
+// (holding y), st.act, st.switched are inputs.  Returns TZ_STATUS_*; st.w holds y on exit.
+template <class BK>
+__device__ int admm_solve(const LaneQp<BK>& qp, const SolverParams& sp, bool live, LaneState<BK>& st, bool warm,
+                          double* __restrict__ ysave /* lane-private shared scratch, element k at [k * 32] */,
+                          int& iters_out) {
+  constexpr int NZ = BK::NZ, NCL = BK::NCL, N2 = BK::N2, G = BK::G;
+  const double alpha = sp.alpha, sigma = sp.sigma, oma = 1.0 - sp.alpha, inv_alpha = 1.0 / sp.alpha;
+  const double rq_base = sp.rho * inv_alpha, rq_act = sp.rho * sp.rho_act * inv_alpha,
+               rq_inact = sp.rho * sp.rho_inact * inv_alpha;
 
-  bool switched = warm;
+  double rq[NCL];                     // rho_row / alpha
   if (!warm) {
 #pragma unroll
-    for (int j = 0; j < NZ; ++j) x[j] = 0.0;
+    for (int j = 0; j < NZ; ++j) st.x[j] = 0.0;
 #pragma unroll
-    for (int i = 0; i < NC; ++i) y[i] = 0.0;
+    for (int k = 0; k < NCL; ++k) { st.w[k] = 0.0; rq[k] = rq_base; }
+    st.act = 0u;
+    st.switched = false;
+  } else {
 #pragma unroll
-    for (int w = 0; w < BK::NW32; ++w) mask[w] = 0u;
+    for (int k = 0; k < NCL; ++k) {
+      rq[k] = ((st.act >> k) & 1u) ? rq_act : rq_inact;
+      st.w[k] = st.w[k] / (rq[k] * alpha);                 // y -> w
+    }
   }
+  // initial z = clip(A x)
 #pragma unroll
-  for (int i = 0; i < NC; ++i) {
+  for (int k = 0; k < NCL; ++k) {
     double ax = 0.0;
 #pragma unroll
-    for (int j = 0; j < NZ; ++j) ax = fma(pg.A[i][j], x[j], ax);
-    z[i] = fmin(fmax(ax, lb[i * TPB]), ub[i * TPB]);
+    for (int j = 0; j < NZ; ++j) ax = fma(qp.Aa[k][j], st.x[j], ax);
+    st.z[k] = qp.clip(k, ax * inv_alpha);
   }
   double qn = 0.0;
 #pragma unroll
-  for (int j = 0; j < NZ; ++j) qn = fmax(qn, fabs(q[j]));
+  for (int j = 0; j < NZ; ++j) qn = fmax(qn, fabs(qp.q[j]));
 
   double L[NZ][NZ];
-  build_factor<BK>(pg, rs, sigma, switched, mask, L);
+  build_factor<BK>(qp, rq, inv_alpha, sigma, L);
+  double th[N2];                      // soft thresholds wk / rho of the |.| rows
+#pragma unroll
+  for (int k = 0; k < N2; ++k) th[k] = qp.wk[k * G] / (rq[k] * alpha);
 
   int status = TZ_STATUS_MAXITER;
   bool done = !live;
   int iters = 0;
   int next_upd = 2, gap = 2;
   const int check_every = sp.check_every > 0 ? sp.check_every : 1;
+  int until_check = check_every;
+  bool have_prev = false;             // ysave holds the duals of the previous check
 
-  for (int k = 1; k <= sp.max_iter; ++k) {
-    // ---- x-update: (P + sigma I + A' diag(rho) A) xt = sigma x - q + A'(rho z - y)
+  for (int it = 1; it <= sp.max_iter; ++it) {
+    // ---- x-update: K xt = sigma x - q + A'(rho (z - w))     [shuffles: whole warp]
     double xt[NZ];
 #pragma unroll
-    for (int j = 0; j < NZ; ++j) xt[j] = sigma * x[j] - q[j];
+    for (int j = 0; j < NZ; ++j) xt[j] = 0.0;
 #pragma unroll
-    for (int i = 0; i < NC; ++i) {
-      const double rho = row_rho<BK>(rs, switched, (mask[i >> 5] >> (i & 31)) & 1u);
-      const double t = rho * z[i] - y[i];
+    for (int k = 0; k < NCL; ++k) {
+      const double t = rq[k] * (st.z[k] - st.w[k]);
 #pragma unroll
-      for (int j = 0; j < NZ; ++j) xt[j] = fma(pg.A[i][j], t, xt[j]);
+      for (int j = 0; j < NZ; ++j) xt[j] = fma(qp.Aa[k][j], t, xt[j]);
     }
-    chol_solve<NZ>(L, xt);
-    const bool check = (k % check_every == 0) || (k == next_upd) || (k == sp.max_iter);
-    // ---- z / y update (with the prox of the |.| rows), dual increment statistics on check iterations
-    double xn[NZ];
 #pragma unroll
-    for (int j = 0; j < NZ; ++j) xn[j] = alpha * xt[j] + (1.0 - alpha) * x[j];
-    double atdy[NZ];
-    double dy_norm = 0.0, supp = 0.0, dy_inf = 0.0;
-#pragma unroll
-    for (int j = 0; j < NZ; ++j) atdy[j] = 0.0;
-#pragma unroll
-    for (int i = 0; i < NC; ++i) {
-      const bool act = (mask[i >> 5] >> (i & 31)) & 1u;
-      const double rho = row_rho<BK>(rs, switched, act);
-      const double irho = row_irho<BK>(rs, switched, act);
-      double zt = 0.0;
-#pragma unroll
-      for (int j = 0; j < NZ; ++j) zt = fma(pg.A[i][j], xt[j], zt);
-      const double zr = alpha * zt + (1.0 - alpha) * z[i];
-      double xi = fma(y[i], irho, zr);
-      if (i < NKINK) {                       // prox of w|z - k| : soft threshold around the kink
-        const double d = xi - kink[i < NKINK ? i : 0];
-        const double th = pg.wabs[i < NKINK ? i : 0] * irho;
-        xi = kink[i < NKINK ? i : 0] + copysign(fmax(fabs(d) - th, 0.0), d);
-      }
-      const double l = lb[i * TPB], u = ub[i * TPB];
-      const double zn = fmin(fmax(xi, l), u);
-      const double dy = rho * (zr - zn);
-      if (!done) {
-        y[i] += dy;
-        z[i] = zn;
-      }
-      if (check) {
-        dy_norm = fmax(dy_norm, fabs(dy));
-#pragma unroll
-        for (int j = 0; j < NZ; ++j) atdy[j] = fma(pg.A[i][j], dy, atdy[j]);
-        // support function of [l, u] along dy; a component pushing against an infinite bound
-        // must vanish for dy to be a certificate (rounding leaves O(eps) residues there)
-        if (dy > 0.0) { if (u < 1e300) supp = fma(u, dy, supp); else dy_inf = fmax(dy_inf, dy); }
-        if (dy < 0.0) { if (l > -1e300) supp = fma(l, dy, supp); else dy_inf = fmax(dy_inf, -dy); }
-      }
-    }
+    for (int j = 0; j < NZ; ++j) xt[j] = gsum<G>(xt[j]) + fma(sigma, st.x[j], -qp.q[j]);
     if (!done) {
+      chol_solve<NZ>(L, xt);
+      // ---- z / w update (prox of the |.| rows), row by row
 #pragma unroll
-      for (int j = 0; j < NZ; ++j) x[j] = xn[j];
-      iters = k;
+      for (int k = 0; k < NCL; ++k) {
+        double zr = oma * st.z[k];
+#pragma unroll
+        for (int j = 0; j < NZ; ++j) zr = fma(qp.Aa[k][j], xt[j], zr);        // alpha (A xt) + (1-alpha) z
+        const double xi = zr + st.w[k];
+        double pr = xi;
+        if (k < N2) {                           // prox of wk|z - kink| : soft threshold around the kink
+          const double d = xi - qp.kink[k < N2 ? k : 0];
+          pr = qp.kink[k < N2 ? k : 0] + copysign(dmax(fabs(d) - th[k < N2 ? k : 0], 0.0), d);
+        }
+        const double zn = qp.clip(k, pr);
+        st.w[k] = xi - zn;
+        st.z[k] = zn;
+      }
+#pragma unroll
+      for (int j = 0; j < NZ; ++j) st.x[j] = fma(alpha, xt[j], oma * st.x[j]);
+      iters = it;
     }
+    const bool check = (--until_check == 0) || (it == sp.max_iter);
     if (check) {
-      // ---- residuals (scaled space)
-      double rp = 0.0, axn = 0.0, zn_ = 0.0;
-      double aty[NZ];
+      until_check = check_every;
+      // ---- residuals (scaled space); dual increment since the previous check for the certificate
+      double rp = 0.0, pn = 0.0, dy_norm = 0.0, supp = 0.0, dy_inf = 0.0;
+      double aty[NZ], atdy[NZ];
 #pragma unroll
-      for (int j = 0; j < NZ; ++j) aty[j] = 0.0;
+      for (int j = 0; j < NZ; ++j) aty[j] = atdy[j] = 0.0;
 #pragma unroll
-      for (int i = 0; i < NC; ++i) {
+      for (int k = 0; k < NCL; ++k) {
         double ax = 0.0;
 #pragma unroll
-        for (int j = 0; j < NZ; ++j) ax = fma(pg.A[i][j], x[j], ax);
-        rp = fmax(rp, fabs(ax - z[i]));
-        axn = fmax(axn, fabs(ax));
-        zn_ = fmax(zn_, fabs(z[i]));
+        for (int j = 0; j < NZ; ++j) ax = fma(qp.Aa[k][j], st.x[j], ax);
+        ax *= inv_alpha;
+        rp = fmax(rp, fabs(ax - st.z[k]));
+        pn = fmax(pn, fmax(fabs(ax), fabs(st.z[k])));
+        const double yk = rq[k] * st.w[k];                   // y / alpha (invariant under rho switches)
+        const double dy = yk - ysave[k * 32];
+        ysave[k * 32] = yk;
+        dy_norm = fmax(dy_norm, fabs(dy));
 #pragma unroll
-        for (int j = 0; j < NZ; ++j) aty[j] = fma(pg.A[i][j], y[i], aty[j]);
+        for (int j = 0; j < NZ; ++j) {
+          aty[j] = fma(qp.Aa[k][j], yk, aty[j]);
+          atdy[j] = fma(qp.Aa[k][j], dy, atdy[j]);
+        }
+        // support function of [l, u] along dy; a component pushing against an infinite bound
+        // must vanish for dy to be a certificate (rounding leaves O(eps) residues there)
+        if (k < N2) {
+          if (dy > 0.0) { if (qp.upper(k) < 1e300) supp = fma(qp.upper(k), dy, supp); else dy_inf = fmax(dy_inf, dy); }
+          if (dy < 0.0) { if (qp.lower(k) > -1e300) supp = fma(qp.lower(k), dy, supp); else dy_inf = fmax(dy_inf, -dy); }
+        } else if (k < N2 + BK::NU) {
+          if (dy > 0.0) supp = fma(qp.upper(k), dy, supp); else dy_inf = fmax(dy_inf, -dy);
+        } else {
+          if (dy < 0.0) supp = fma(qp.lower(k), dy, supp); else dy_inf = fmax(dy_inf, dy);
+        }
       }
+      rp = gmax<G>(rp);
+      pn = gmax<G>(pn);
+      dy_norm = gmax<G>(dy_norm);
+      dy_inf = gmax<G>(dy_inf);
+      supp = gsum<G>(supp);
       double rd = 0.0, pxn = 0.0, atyn = 0.0, atdyn = 0.0;
 #pragma unroll
       for (int j = 0; j < NZ; ++j) {
+        const double atyj = gsum<G>(aty[j]);
+        const double atdyj = gsum<G>(atdy[j]);
         double px = 0.0;
 #pragma unroll
-        for (int b = 0; b < NZ; ++b) px = fma(pg.P[j][b], x[b], px);
-        rd = fmax(rd, fabs(px + q[j] + aty[j]));
+        for (int b = 0; b < NZ; ++b) px = fma(qp.P[j][b], st.x[b], px);
+        rd = fmax(rd, fabs(px + qp.q[j] + atyj));
         pxn = fmax(pxn, fabs(px));
-        atyn = fmax(atyn, fabs(aty[j]));
-        atdyn = fmax(atdyn, fabs(atdy[j]));
+        atyn = fmax(atyn, fabs(atyj));
+        atdyn = fmax(atdyn, fabs(atdyj));
       }
-      const double ep = sp.eps_abs + sp.eps_rel * fmax(axn, zn_);
+      const double ep = sp.eps_abs + sp.eps_rel * pn;
       const double ed = sp.eps_abs + sp.eps_rel * fmax(fmax(pxn, atyn), qn);
       if (!done) {
         if (!(rp == rp) || !(rd == rd)) {
@@ -271,146 +350,167 @@ __device__ int admm_solve(const PG& pg, const SolverParams& sp, bool live, const
         } else if (rp <= ep && rd <= ed) {
           status = TZ_STATUS_OK;
           done = true;
-        } else if (k >= 10 && dy_norm > 1e-12 && dy_inf <= 1e-6 * dy_norm && atdyn <= 1e-6 * dy_norm &&
+        } else if (have_prev && dy_norm > 1e-12 && dy_inf <= 1e-6 * dy_norm && atdyn <= 1e-6 * dy_norm &&
                    supp < -1e-6 * dy_norm) {
           status = TZ_STATUS_INFEASIBLE;     // Farkas certificate (OSQP, Banjac et al. 2019)
           done = true;
         }
       }
+      have_prev = true;
       if (__all_sync(0xffffffffu, done)) break;
     }
     // ---- activity-driven rho switch on a geometric schedule
-    if (k == next_upd) {
+    if (it == next_upd) {
       gap = (gap * 3 + 1) / 2;
-      next_upd = k + gap;
-      uint32_t nm[BK::NW32];
+      next_upd = it + gap;
+      uint32_t nm = 0u;
 #pragma unroll
-      for (int w = 0; w < BK::NW32; ++w) nm[w] = 0u;
+      for (int k = 0; k < NCL; ++k) nm |= (qp.at_bound(k, st.z[k]) ? 1u : 0u) << k;
+      const int changed = gor<G>((!st.switched || nm != st.act) ? 1 : 0);
+      const bool apply = changed && !done;
+      if (apply) {
 #pragma unroll
-      for (int i = 0; i < NC; ++i) {
-        bool act = (z[i] <= lb[i * TPB]) || (z[i] >= ub[i * TPB]);
-        if (i < NKINK) act = act || (pg.wabs[i < NKINK ? i : 0] > 0.0 && z[i] == kink[i < NKINK ? i : 0]);
-        nm[i >> 5] |= (act ? 1u : 0u) << (i & 31);
+        for (int k = 0; k < NCL; ++k) {      // keep y = rho w invariant under the switch
+          const double nr = ((nm >> k) & 1u) ? rq_act : rq_inact;
+          st.w[k] *= rq[k] / nr;
+          rq[k] = nr;
+        }
+        st.act = nm;
+        st.switched = true;
+#pragma unroll
+        for (int k = 0; k < N2; ++k) th[k] = qp.wk[k * G] / (rq[k] * alpha);
       }
-      bool changed = !switched;
+      // the factor is rebuilt with group shuffles, so the whole warp takes the branch together
+      if (__any_sync(0xffffffffu, apply)) {
+        double Lt[NZ][NZ];
+        build_factor<BK>(qp, rq, inv_alpha, sigma, Lt);
+        if (apply) {
 #pragma unroll
-      for (int w = 0; w < BK::NW32; ++w) changed = changed || (nm[w] != mask[w]);
-      if (changed && !done) {
+          for (int a = 0; a < NZ; ++a)
 #pragma unroll
-        for (int w = 0; w < BK::NW32; ++w) mask[w] = nm[w];
-        switched = true;
-        build_factor<BK>(pg, rs, sigma, switched, mask, L);
+            for (int c = 0; c <= a; ++c) L[a][c] = Lt[a][c];
+        }
       }
     }
   }
+  // hand y (not w) back to the caller
+#pragma unroll
+  for (int k = 0; k < NCL; ++k) st.w[k] *= rq[k] * alpha;
   iters_out = iters;
   return live ? status : TZ_STATUS_OK;
 }
 
 // Polish: solve the equality-constrained QP on the detected active set with a masked
-// augmented-Lagrangian iteration (only NZ x NZ systems, no index compaction, branch-free):
+// augmented-Lagrangian iteration (only NZ x NZ systems, no index compaction):
 //   K = P + delta I + mu sum_{i active} a_i a_i',  x <- K^{-1}(delta x - qt + sum_act a_i (mu b_i - lam_i)),
 //   lam_i <- lam_i + mu (a_i x - b_i).   Accepted only if the result is feasible.
-template <class BK, class PG>
-__device__ bool admm_polish(const PG& pg, const double (&q)[BK::NZ], const double* __restrict__ lb,
-                            const double* __restrict__ ub, const double (&kink)[BK::NKINK], double (&x)[BK::NZ],
-                            const double (&z)[BK::NC], double (&y)[BK::NC]) {
-  constexpr int NZ = BK::NZ, NC = BK::NC, NKINK = BK::NKINK, TPB = BK::TPB;
+// st.w holds y on entry and on exit.  Must be called by whole warps (shuffles).
+template <class BK>
+__device__ bool admm_polish(const LaneQp<BK>& qp, double inv_alpha, LaneState<BK>& st, bool apply, int n_iter) {
+  constexpr int NZ = BK::NZ, NCL = BK::NCL, N2 = BK::N2, G = BK::G;
   const double delta = 1e-9, mu = 1e6;
-  double L[NZ][NZ], qt[NZ], xk[NZ];
-  uint32_t act[BK::NW32];
-#pragma unroll
-  for (int w = 0; w < BK::NW32; ++w) act[w] = 0u;
+  double L[NZ][NZ], qt[NZ], xk[NZ], tgt[NCL];
+  uint32_t act = 0u;
 #pragma unroll
   for (int a = 0; a < NZ; ++a) {
-    qt[a] = q[a];
-    xk[a] = x[a];
+    qt[a] = 0.0;
+    xk[a] = st.x[a];
 #pragma unroll
-    for (int b = 0; b <= a; ++b) L[a][b] = pg.P[a][b] + (a == b ? delta : 0.0);
+    for (int b = 0; b <= a; ++b) L[a][b] = 0.0;
   }
-  // active targets b_i are recomputed on the fly: lower bound, upper bound or kink
-  auto target = [&](int i, bool& is_act) -> double {
-    const double l = lb[i * TPB], u = ub[i * TPB];
-    double b = 0.0;
-    is_act = false;
-    if (z[i] <= l) { b = l; is_act = true; }
-    else if (z[i] >= u) { b = u; is_act = true; }
-    else if (i < NKINK) {
-      const double kk = kink[i < NKINK ? i : 0];
-      if (pg.wabs[i < NKINK ? i : 0] > 0.0 && z[i] == kk) { b = kk; is_act = true; }
-    }
-    return b;
-  };
 #pragma unroll
-  for (int i = 0; i < NC; ++i) {
-    bool ia;
-    (void)target(i, ia);
+  for (int k = 0; k < NCL; ++k) {
+    bool ia = false;
+    double b = 0.0;
+    if (st.z[k] <= qp.lower(k)) { b = qp.lower(k); ia = true; }
+    else if (st.z[k] >= qp.upper(k)) { b = qp.upper(k); ia = true; }
+    else if (k < N2) {
+      const double kk = qp.kink[k < N2 ? k : 0];
+      if (qp.wk[(k < N2 ? k : 0) * G] > 0.0 && st.z[k] == kk) { b = kk; ia = true; }
+    }
+    tgt[k] = b * (1.0 / inv_alpha);          // compare against Aa x = alpha (A x)
     if (ia) {
-      act[i >> 5] |= 1u << (i & 31);
+      act |= 1u << k;
 #pragma unroll
       for (int a = 0; a < NZ; ++a) {
-        const double ra = mu * pg.A[i][a];
+        const double ra = mu * qp.Aa[k][a];
 #pragma unroll
-        for (int b = 0; b <= a; ++b) L[a][b] = fma(ra, pg.A[i][b], L[a][b]);
+        for (int c = 0; c <= a; ++c) L[a][c] = fma(ra, qp.Aa[k][c], L[a][c]);
       }
     } else {
-      y[i] = 0.0;
-      if (i < NKINK) {           // |.| row away from its kink: a linear cost term
-        const double w = pg.wabs[i < NKINK ? i : 0];
-        if (w > 0.0) {
-          const double sg = z[i] > kink[i < NKINK ? i : 0] ? w : -w;
-          y[i] = sg;             // its multiplier is the subgradient
+      st.w[k] = 0.0;
+      if (k < N2) {              // |.| row away from its kink: a linear cost term
+        const double wgt = qp.wk[(k < N2 ? k : 0) * G];
+        if (wgt > 0.0) {
+          const double sg = st.z[k] > qp.kink[k < N2 ? k : 0] ? wgt : -wgt;
+          st.w[k] = sg;          // its multiplier is the subgradient
 #pragma unroll
-          for (int a = 0; a < NZ; ++a) qt[a] = fma(sg, pg.A[i][a], qt[a]);
+          for (int a = 0; a < NZ; ++a) qt[a] = fma(sg * inv_alpha, qp.Aa[k][a], qt[a]);
         }
       }
     }
   }
+  // work with B = Aa (= alpha A): the active equalities B x = alpha b, multipliers lamB = y / alpha
+#pragma unroll
+  for (int k = 0; k < NCL; ++k)
+    if ((act >> k) & 1u) st.w[k] *= inv_alpha;
+#pragma unroll
+  for (int a = 0; a < NZ; ++a) {
+    qt[a] = gsum<G>(qt[a]) + qp.q[a];
+#pragma unroll
+    for (int b = 0; b <= a; ++b) L[a][b] = gsum<G>(L[a][b]) + qp.P[a][b] + (a == b ? delta : 0.0);
+  }
   chol_factor<NZ>(L);
 #pragma unroll 1
-  for (int it = 0; it < 4; ++it) {
+  for (int it = 0; it < n_iter; ++it) {
     double rhs[NZ];
 #pragma unroll
-    for (int a = 0; a < NZ; ++a) rhs[a] = delta * xk[a] - qt[a];
+    for (int a = 0; a < NZ; ++a) rhs[a] = 0.0;
 #pragma unroll
-    for (int i = 0; i < NC; ++i) {
-      if ((act[i >> 5] >> (i & 31)) & 1u) {
-        bool ia;
-        const double t = mu * target(i, ia) - y[i];
+    for (int k = 0; k < NCL; ++k) {
+      if ((act >> k) & 1u) {
+        const double t = fma(mu, tgt[k], -st.w[k]);
 #pragma unroll
-        for (int a = 0; a < NZ; ++a) rhs[a] = fma(pg.A[i][a], t, rhs[a]);
+        for (int a = 0; a < NZ; ++a) rhs[a] = fma(qp.Aa[k][a], t, rhs[a]);
       }
     }
+#pragma unroll
+    for (int a = 0; a < NZ; ++a) rhs[a] = gsum<G>(rhs[a]) + fma(delta, xk[a], -qt[a]);
     chol_solve<NZ>(L, rhs);
 #pragma unroll
     for (int a = 0; a < NZ; ++a) xk[a] = rhs[a];
 #pragma unroll
-    for (int i = 0; i < NC; ++i) {
-      if ((act[i >> 5] >> (i & 31)) & 1u) {
+    for (int k = 0; k < NCL; ++k) {
+      if ((act >> k) & 1u) {
         double ax = 0.0;
 #pragma unroll
-        for (int a = 0; a < NZ; ++a) ax = fma(pg.A[i][a], xk[a], ax);
-        bool ia;
-        y[i] = fma(mu, ax - target(i, ia), y[i]);
+        for (int a = 0; a < NZ; ++a) ax = fma(qp.Aa[k][a], xk[a], ax);
+        st.w[k] = fma(mu, ax - tgt[k], st.w[k]);
       }
     }
   }
+#pragma unroll
+  for (int k = 0; k < NCL; ++k)
+    if ((act >> k) & 1u) st.w[k] *= (1.0 / inv_alpha);      // back to y
   // accept only a feasible polished point
   double viol = 0.0, scale = 1.0;
 #pragma unroll
-  for (int i = 0; i < NC; ++i) {
+  for (int k = 0; k < NCL; ++k) {
     double ax = 0.0;
 #pragma unroll
-    for (int a = 0; a < NZ; ++a) ax = fma(pg.A[i][a], xk[a], ax);
-    viol = fmax(viol, fmax(lb[i * TPB] - ax, ax - ub[i * TPB]));
+    for (int a = 0; a < NZ; ++a) ax = fma(qp.Aa[k][a], xk[a], ax);
+    ax *= inv_alpha;
+    viol = fmax(viol, fmax(qp.lower(k) - ax, ax - qp.upper(k)));
     scale = fmax(scale, fabs(ax));
   }
+  viol = gmax<G>(viol);
+  scale = gmax<G>(scale);
   bool ok = (viol <= 1e-9 * scale);
 #pragma unroll
   for (int a = 0; a < NZ; ++a) ok = ok && (xk[a] == xk[a]);
-  if (ok) {
+  if (ok && apply) {
 #pragma unroll
-    for (int a = 0; a < NZ; ++a) x[a] = xk[a];
+    for (int a = 0; a < NZ; ++a) st.x[a] = xk[a];
   }
   return ok;
 }

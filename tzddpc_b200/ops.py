@@ -26,13 +26,13 @@ class SolverOptions:
     eps_abs: float = 1e-6
     eps_rel: float = 1e-6
     max_iter: int = 4000
-    check_every: int = 4
-    polish: bool = True
+    check_every: int = 8
+    polish: int = 3          # iterations of the active-set polish, 0 = off
     warm_start: bool = False
 
     def pack(self) -> List[float]:
         return [self.rho, self.rho_active, self.rho_inactive, self.sigma, self.alpha, self.eps_abs, self.eps_rel,
-                float(self.max_iter), float(self.check_every), float(self.polish), float(self.warm_start)]
+                float(self.max_iter), float(self.check_every), float(int(self.polish)), float(self.warm_start)]
 
 
 def _opts(o: List[float]) -> _abi.TzSolverOpts:
@@ -52,10 +52,6 @@ def _stream(t: Tensor):
 
 def _chk(t: Tensor, dtype=torch.float64):
     assert t.is_cuda and t.dtype == dtype and t.is_contiguous(), "expected a contiguous CUDA tensor of " + str(dtype)
-
-
-def warm_rows(nz_bucket: int, nc_bucket: int) -> int:
-    return nz_bucket + nc_bucket + (nc_bucket + 31) // 32 + 1
 
 
 @torch.library.custom_op("tzddpc::solve", mutates_args=("warm",), device_types="cuda")

@@ -303,8 +303,7 @@ class TZDDPC(object):
         iters = torch.empty((steps, S), dtype=torch.int32, device=dev)
         stats = torch.zeros((steps, _abi.TZ_NSTATS), **f64)
         tubes = torch.empty((steps, self._dims[3], S), **f64) if keep_tubes else None
-        wr = ops.warm_rows(self._program_nz(), self._program_nc())
-        warm = torch.zeros((wr, S), **f64) if o.warm_start else None
+        warm = torch.zeros((self._program.warm_rows, S), **f64) if o.warm_start else None
         xs[0], xbars[0], es[0] = x, xbar, e
         h = self._program.handle.value
         for t in range(steps):
@@ -319,9 +318,3 @@ class TZDDPC(object):
             g1 = self._program.compiled.g1
             out["tubes"] = tubes.reshape(steps, n, 1 + g1, S).permute(0, 3, 1, 2).cpu().numpy()
         return out
-
-    def _program_nz(self) -> int:
-        return int(self._program.bucket.split("NZ=")[1].split(",")[0])
-
-    def _program_nc(self) -> int:
-        return int(self._program.bucket.split("NC=")[1].split(")")[0])
