@@ -39,6 +39,17 @@ def algorithmic_bytes_per_scenario_step(n, m, N, g1):
     return 8 * (6 * n + N * m + (N + 1) * n + 1 + n * (1 + g1)) + 4
 
 
+def measured_traffic(bucket: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the step kernel from the committed
+    `ncu --set full` capture (profiles/step_kernel_traffic.json, written by profiles/summarise.py), or None."""
+    p = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
+    try:
+        d = json.load(open(p))
+        return d.get(bucket, d.get("default"))
+    except Exception:
+        return None
+
+
 def measured_hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -109,10 +120,17 @@ def cpu_oracle_throughput(workload, cores, scen_per_core, warmup, steps):
     return cores * scen_per_core * steps / max(times), max(times)
 
 
+def workload_name(cfg, S):
+    return (f"{cfg.name}: n={cfg.n} m={cfg.m} T={cfg.T} horizon={cfg.horizon}, {S} scenarios per GPU (noise realisations, "
+            f"shared data set), closed loop")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from tzddpc_b200 import configs
+    cfg = configs.CONFIGS[args.workload]()
     cores = len(os.sched_getaffinity(0))
     # a "step" here is one closed-loop step over a bounded sample of 2 scenarios per core
     scen_per_core = 2
@@ -121,8 +139,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "note": "CPU oracle port of the reference path (the reference needs "
-                       "cvxpy/pyzonotope, absent here); bounded sample of the same workload"},
+            "config": {"workload": workload_name(cfg, args.scenarios), "scenarios_per_gpu": args.scenarios,
+                       "note": "CPU oracle port of the reference path (the reference itself needs cvxpy / pyzonotope / "
+                               "pydatadrivenreachability, absent here); each step is a bounded sample of the workload: "
+                               + sample},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -173,7 +193,7 @@ def run_gpu(args):
     import torch
     import torch.distributed as dist
     import tzddpc_b200 as tz
-    from tzddpc_b200 import _abi, configs, ops
+    from tzddpc_b200 import _abi, configs, ops, shard
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -208,7 +228,8 @@ def run_gpu(args):
     gen.manual_seed(cfg.seed + 7919 * rank)
     cW, GW = torch.tensor(cfg.W[0], **f64), torch.tensor(cfg.W[1], **f64)
     total = W_steps + K_steps
-    beta = torch.rand((total, GW.shape[1], S), generator=gen, **f64) * 2 - 1
+    nring = min(total, 64)          # noise realisations are drawn for 64 steps and cycled (bounded memory for long runs)
+    beta = torch.rand((nring, GW.shape[1], S), generator=gen, **f64) * 2 - 1
     if cfg.noise == "vertex":
         beta = torch.sign(beta)
     noise = (cW[None, :, None] + torch.einsum("rg,tgs->trs", GW, beta)).contiguous()      # (total, n, S)
@@ -223,16 +244,16 @@ def run_gpu(args):
     traj = torch.empty((ring, nt, S), **f64)
     vbuf = torch.empty((ring, nv, S), **f64)
     cost = torch.empty((ring, S), **f64)
-    status = torch.zeros((total, S), dtype=torch.int32, device=dev)
-    iters = torch.zeros((total, S), dtype=torch.int32, device=dev)
+    status = torch.zeros((ring, S), dtype=torch.int32, device=dev)
+    iters = torch.zeros((ring, S), dtype=torch.int32, device=dev)
     stats = torch.zeros((total, _abi.TZ_NSTATS), **f64)
     warm = torch.zeros((prog.warm_rows, S), **f64) if args.warm_start else None
     h = prog.handle.value
 
     def step(t):
         r = t % ring
-        ops.closed_loop_step(h, x, xbar, e, noise[t], At, Bt, status[t], cost[r], vbuf[r], traj[r], ze1[r], None,
-                             iters[t], warm, stats[t], po)
+        ops.closed_loop_step(h, x, xbar, e, noise[t % nring], At, Bt, status[r], cost[r], vbuf[r], traj[r], ze1[r], None,
+                             iters[r], warm, stats[t], po)
 
     def barrier():
         if world > 1:
@@ -254,39 +275,32 @@ def run_gpu(args):
     elapsed_ms = ev[0].elapsed_time(ev[-1])
     kern_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(K_steps)]
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
-    el = torch.tensor([elapsed_ms], **f64)
-    if world > 1:
-        dist.all_reduce(el, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(el.item())
-    # final statistics: the only collective of the path
-    tot_stats = stats[W_steps:].sum(0)
-    if world > 1:
-        dist.all_reduce(tot_stats, op=dist.ReduceOp.SUM)
-    tot_stats = tot_stats.cpu().numpy()
-    st = status[W_steps:]
-    it = iters[W_steps:].double()
+    elapsed_ms = shard.max_over_ranks(elapsed_ms, dev)
+    # final statistics: the only collective of the path, one all-reduce after the loop
+    tot_stats = shard.reduce_statistics(stats[W_steps:].clone()).sum(0).cpu().numpy()
+    cnt = max(tot_stats[7], 1.0)
 
     value = world * S * K_steps / (elapsed_ms * 1e-3)
     bstep = algorithmic_bytes_per_scenario_step(n, m, N, g1)
     peak, peak_src = measured_hbm_peak()
     avg_kernel_ms = float(np.mean(kern_ms))
     achieved = bstep * S / (avg_kernel_ms * 1e-3) / 1e9
+    traffic = measured_traffic(prog.bucket)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K_steps, "warmup": W_steps,
             "ms_per_step": elapsed_ms / K_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{cfg.name}: n={n} m={m} T={cfg.T} horizon={N}, {S} scenarios per GPU (noise realisations, "
-                                   f"shared data set), closed loop", "scenarios_per_gpu": S, "parallelism": f"scenario-dp{world}",
+            "config": {"workload": workload_name(cfg, S), "scenarios_per_gpu": S, "parallelism": f"scenario-dp{world}",
                        "l2": f"per-step HBM traffic {bstep * S / 1e6:.0f} MB > 126 MB L2 (inputs larger than L2)",
                        "solver": {"warm_start": bool(args.warm_start), "eps": opts.eps_abs, "polish": True},
                        "kernel_bucket": prog.bucket},
             "gpu_launches": K_steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "bytes_per_scenario_step": bstep,
+                         "traffic": traffic, "peak_source": peak_src, "bytes_per_scenario_step": bstep,
                          "kernel_ms_avg": avg_kernel_ms, "kernel": "tz::step_kernel_param"},
-            "solver_stats": {"iters_mean": float(it.mean().item()), "iters_max": int(it.max().item()),
-                             "status_ok_frac": float((st == 0).double().mean().item()),
-                             "infeasible": int((st == 2).sum().item()), "maxiter": int((st == 1).sum().item()),
-                             "mean_norm_x": float(tot_stats[0] / max(tot_stats[7], 1.0))},
+            "solver_stats": {"iters_mean": float(tot_stats[5] / cnt), "iters_max_last_steps": int(iters.max().item()),
+                             "status_ok_frac": float(1.0 - (tot_stats[3] + tot_stats[4] + tot_stats[6]) / cnt),
+                             "infeasible": int(tot_stats[3]), "maxiter": int(tot_stats[4]), "nonfinite": int(tot_stats[6]),
+                             "mean_norm_x": float(tot_stats[0] / cnt)},
             "clocks": clocks}
 
     # ---- e2e: host buffers through the C-ABI host entry point, every output back on the host
@@ -296,7 +310,7 @@ def run_gpu(args):
         hx, hxb, he = pin(n, S), pin(n, S), pin(n, S)
         hx.copy_(x0[:, None].cpu().expand(n, S)); hxb.copy_(hx); he.zero_()
         hnoise = pin(Ke + 2, n, S)
-        hnoise.copy_(noise[:Ke + 2].cpu())
+        hnoise.copy_(noise[torch.arange(Ke + 2, device=dev) % nring].cpu())
         hcost, hv, htraj, hze = pin(S), pin(nv, S), pin(nt, S), pin(nent, S)
         hstat = pin(S, dt=torch.int32)
         scratch = torch.empty(_abi.lib().tz_closed_loop_step_host_scratch_bytes(h, S) // 8 + 8, **f64)
@@ -320,22 +334,21 @@ def run_gpu(args):
             host_step(2 + t)
         barrier()
         dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], **f64)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
+        dt = shard.max_over_ranks(dt, dev)
         line["e2e"] = {"value": world * S * Ke / dt, "unit": UNIT, "h2d_bytes_per_step": int(4 * n * S * 8 + 8 * (n * n + n * m)),
                        "d2h_bytes_per_step": int(S * (8 * (3 * n + 1 + nv + nt + nent) + 4)), "steps": Ke,
                        "ms_per_step": 1e3 * dt / Ke, "api": "tz_closed_loop_step_host (pinned host buffers)",
                        "status_ok_frac": float((hstat == 0).double().mean().item())}
 
-    # ---- CPU baseline on this box's host cores (rank 0, N = 1 only): the oracle port, single core
+    # ---- CPU baseline on this box's host cores (rank 0, N = 1 only): the oracle port, one process per core
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = len(os.sched_getaffinity(0)) if args.cpu_cores <= 0 else args.cpu_cores
         scen, cpu_steps = 1, args.cpu_steps
-        val, secs = cpu_oracle_throughput(args.workload, 1, scen, 2, cpu_steps)
-        line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": 1, "kind": "port",
-                                "sample": f"{scen} scenario x {cpu_steps} closed-loop steps of the same workload "
-                                          f"({secs:.1f} s), numpy oracle", "host_cores_available": len(os.sched_getaffinity(0))}
+        val, secs = cpu_oracle_throughput(args.workload, cores, scen, 2, cpu_steps)
+        line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"{cores * scen} scenarios (one per core) x {cpu_steps} closed-loop steps of the same "
+                                          f"workload ({secs:.1f} s), numpy oracle of the reference path",
+                                "per_core": val / cores}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -356,6 +369,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--e2e-chunks", type=int, default=4)
     ap.add_argument("--cpu-steps", type=int, default=1500)
+    ap.add_argument("--cpu-cores", type=int, default=0, help="processes of the CPU baseline (0 = all host cores)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

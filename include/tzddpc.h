@@ -137,7 +137,7 @@ int tz_solve(const TzProgram* prog, const TzSolverOpts* opts, int64_t S,
  *   A_true,B_true device n*n, n*m row-major (the simulated plant)
  *   u_out         m x S or NULL
  *   stats         TZ_NSTATS doubles accumulated with atomics, or NULL:
- *                 [sum |x+|_2, sum |x+|_2^2, sum cost, #infeasible, #maxiter, sum iters, #X-violations, S]
+ *                 [sum |x+|_2, sum |x+|_2^2, sum cost, #infeasible, #maxiter, sum iters, #non-finite, S]
  *   scenarios whose status is INFEASIBLE/NONFINITE keep their state unchanged.
  * ------------------------------------------------------------------------------------ */
 #define TZ_NSTATS 8

@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel(const QpProg<BK
 
 // ---- compiled buckets: <NZ, N2, NU, NL, G, NPAR, NAG, NCHK, MINB> -------------------------------
 #ifndef TZ_B0_MINB
-#define TZ_B0_MINB 4
+#define TZ_B0_MINB 3
 #endif
 using B0 = Bucket<2, 1, 3, 3, 4, 10, 2, 12, TZ_B0_MINB>;      // N = 2, m = 1, n <= 5: the three shipped examples (28 row slots)
 using B1 = Bucket<4, 2, 4, 4, 8, 16, 8, 16, 3>;      // generic small   (80 row slots)
