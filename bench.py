@@ -220,7 +220,7 @@ def run_gpu(args):
     prog = ctl._program
     g1 = prog.compiled.g1
     nent, nt, nv = n * (1 + g1), (N + 1) * n, prog.compiled.nv
-    opts = tz.SolverOptions(warm_start=bool(args.warm_start), check_every=args.check_every, eps_abs=args.eps, eps_rel=args.eps)
+    opts = tz.SolverOptions(warm_start=int(args.warm_start), check_every=args.check_every, eps_abs=args.eps, eps_rel=args.eps)
     po = opts.pack()
 
     f64 = dict(dtype=torch.float64, device=dev)
@@ -237,6 +237,7 @@ def run_gpu(args):
     x0 = torch.tensor(cfg.X0[0], **f64)
     x = x0[:, None].repeat(1, S).contiguous()
     xbar = x.clone()
+    xrestart = x.clone()         # an infeasible scenario (the reference raises: end of that run) starts a new run from x0
     e = torch.zeros((n, S), **f64)
     At, Bt = torch.tensor(cfg.A, **f64), torch.tensor(cfg.B, **f64)
     ring = 4
@@ -252,7 +253,7 @@ def run_gpu(args):
 
     def step(t):
         r = t % ring
-        ops.closed_loop_step(h, x, xbar, e, noise[t % nring], At, Bt, status[r], cost[r], vbuf[r], traj[r], ze1[r], None,
+        ops.closed_loop_step(h, x, xbar, e, noise[t % nring], xrestart, At, Bt, status[r], cost[r], vbuf[r], traj[r], ze1[r], None,
                              iters[r], warm, stats[t], po)
 
     def barrier():
@@ -279,6 +280,8 @@ def run_gpu(args):
     # final statistics: the only collective of the path, one all-reduce after the loop
     tot_stats = shard.reduce_statistics(stats[W_steps:].clone()).sum(0).cpu().numpy()
     cnt = max(tot_stats[7], 1.0)
+    if args.dump_steps and rank == 0:
+        np.savez(args.dump_steps, kern_ms=np.asarray(kern_ms), stats=stats[W_steps:].cpu().numpy())
 
     value = world * S * K_steps / (elapsed_ms * 1e-3)
     bstep = algorithmic_bytes_per_scenario_step(n, m, N, g1)
@@ -291,7 +294,8 @@ def run_gpu(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(cfg, S), "scenarios_per_gpu": S, "parallelism": f"scenario-dp{world}",
                        "l2": f"per-step HBM traffic {bstep * S / 1e6:.0f} MB > 126 MB L2 (inputs larger than L2)",
-                       "solver": {"warm_start": bool(args.warm_start), "eps": opts.eps_abs, "polish": True},
+                       "solver": {"warm_start": {0: "cold", 1: "previous (x, y)", 2: "active-set hint of the previous step (KKT-certified)"}[int(args.warm_start)],
+                                  "eps": opts.eps_abs, "polish": True, "certificate": "active-set KKT"},
                        "kernel_bucket": prog.bucket},
             "gpu_launches": K_steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -363,13 +367,14 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="fivedim", choices=["fivedim", "pulley", "double_integrator"])
     ap.add_argument("--scenarios", type=int, default=65536, help="scenarios per GPU")
-    ap.add_argument("--warm-start", type=int, default=0)
-    ap.add_argument("--check-every", type=int, default=4)
+    ap.add_argument("--warm-start", type=int, default=2, help="0 cold, 1 previous (x, y), 2 active-set hint (default)")
+    ap.add_argument("--check-every", type=int, default=8)
     ap.add_argument("--eps", type=float, default=1e-6)
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--e2e-chunks", type=int, default=4)
     ap.add_argument("--cpu-steps", type=int, default=1500)
     ap.add_argument("--cpu-cores", type=int, default=0, help="processes of the CPU baseline (0 = all host cores)")
+    ap.add_argument("--dump-steps", default="", help="write per-step kernel ms and solver statistics to this .npz (diagnostics)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

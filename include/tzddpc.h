@@ -106,7 +106,12 @@ typedef struct TzSolverOpts {
   int32_t max_iter;  /*                                            default 4000 */
   int32_t check_every;/* residual check period                     default 8    */
   int32_t polish;    /* masked augmented-Lagrangian polish: number of iterations, 0 = off   default 3 */
-  int32_t warm_start;/* reuse (z, y) from the `warm` buffer        default 0    */
+  int32_t warm_start;/* 0 cold; 1 reuse (x, y) of the previous call from the `warm` buffer; 2 active-set hint:
+                        the previous call's optimal active set is tried first (KKT-certified, so a stale
+                        hint only costs the test); the buffer carries one word per lane        default 0 */
+  int32_t cert_first;/* first iteration at which the active-set KKT certificate is tried (then on a
+                        geometric schedule); a certified iterate is an exact solution and ends the
+                        solve at once.  0 = off (terminate on residuals only)        default 3    */
 } TzSolverOpts;
 
 void tz_solver_opts_default(TzSolverOpts* o);
@@ -134,15 +139,17 @@ int tz_solve(const TzProgram* prog, const TzSolverOpts* opts, int64_t S,
  *     u = K e + v[0];  x+ = A_true x + B_true u + w;  xbar+ = xbar_traj[1];  e+ = x+ - xbar+
  *   x, xbar, e    n x S, updated IN PLACE
  *   noise         n x S   the realisation w_t (an input: W.sample(), :92)
+ *   x_restart     n x S or NULL.  The reference ends a run when a step is infeasible (raises, tzddpc/tzddpc.py:374-375).
+ *                 With x_restart such a scenario starts a new run: x = xbar = x_restart, e = 0
+ *                 (examples/2.pulley_sim.py:66-72); with NULL it keeps its state (and stays infeasible).
  *   A_true,B_true device n*n, n*m row-major (the simulated plant)
  *   u_out         m x S or NULL
  *   stats         TZ_NSTATS doubles accumulated with atomics, or NULL:
  *                 [sum |x+|_2, sum |x+|_2^2, sum cost, #infeasible, #maxiter, sum iters, #non-finite, S]
- *   scenarios whose status is INFEASIBLE/NONFINITE keep their state unchanged.
  * ------------------------------------------------------------------------------------ */
 #define TZ_NSTATS 8
 int tz_closed_loop_step(const TzProgram* prog, const TzSolverOpts* opts, int64_t S,
-                        double* x, double* xbar, double* e, const double* noise,
+                        double* x, double* xbar, double* e, const double* noise, const double* x_restart,
                         const double* A_true, const double* B_true,
                         double* cost, double* v, double* xbar_traj, double* ze1, double* u_out,
                         int32_t* status, int32_t* iters, double* warm, double* stats, void* stream);

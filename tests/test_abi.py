@@ -54,7 +54,7 @@ def test_host_only_entry_points(cuda_lib):
 def test_struct_layouts_match_the_header(cuda_lib):
     """ctypes mirrors of TzProgramDesc / TzSolverOpts: field order and sizes as in include/tzddpc.h."""
     from tzddpc_b200 import _abi
-    assert C.sizeof(_abi.TzSolverOpts) == 7 * 8 + 4 * 4
+    assert C.sizeof(_abi.TzSolverOpts) == 80          # 7 doubles + 5 int32, padded to 8
     names = [f[0] for f in _abi.TzProgramDesc._fields_]
     src = open(HEADER).read()
     body = src[src.index("typedef struct TzProgramDesc {"):src.index("} TzProgramDesc;")]

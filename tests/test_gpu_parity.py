@@ -96,3 +96,49 @@ def test_closed_loop_matches_oracle(pair):
         np.testing.assert_allclose(out["u"][:last, s], r["u"][:last], rtol=1e-6, atol=1e-6)
         for k in range(last):
             np.testing.assert_allclose(out["tubes"][k, s], r["tubes"][k], rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_warm_start_modes_give_the_cold_result(pair, mode):
+    """warm_start 1 (previous x, y) and 2 (active-set hint, KKT-certified) only change the work, not the answer."""
+    import tzddpc_b200 as tz
+    cfg, o, t = pair
+    rng = np.random.default_rng(5)
+    steps, S = min(cfg.steps, 30), 64
+    noise = common.noise_for(cfg, steps, S, rng)
+    x0 = np.tile(np.asarray(cfg.X0[0], dtype=np.float64), (S, 1))
+    cold = t.simulate(cfg.A, cfg.B, x0, noise, keep_tubes=True)
+    hot = t.simulate(cfg.A, cfg.B, x0, noise, keep_tubes=True, options=tz.SolverOptions(warm_start=mode))
+    assert np.array_equal(cold["status"], hot["status"])
+    np.testing.assert_allclose(hot["x"], cold["x"], rtol=1e-7, atol=1e-7)
+    np.testing.assert_allclose(hot["u"], cold["u"], rtol=1e-7, atol=1e-7)
+    np.testing.assert_allclose(hot["tubes"], cold["tubes"], rtol=1e-7, atol=1e-7)
+    if mode == 2:       # after the first step almost every solve is certified from the hint without iterating
+        assert hot["iters"][1:].mean() < 0.5 * max(cold["iters"][1:].mean(), 1.0)
+
+
+def test_restart_after_an_infeasible_step():
+    """The reference raises when a step is infeasible (tzddpc/tzddpc.py:374-375) and the run ends; with restart=True the
+    scenario starts a new run from its x0.  The 5-dim example runs into its tightened constraints after ~60 steps."""
+    cfg = configs.fivedim()
+    u, x = common.dataset(cfg)
+    o, K = common.make_oracle(cfg, u, x)
+    t = common.make_product(cfg, u, x, K)
+    rng = np.random.default_rng(0)
+    steps, S = 90, 6
+    noise = common.noise_for(cfg, steps, S, rng)
+    x0 = np.tile(np.asarray(cfg.X0[0], dtype=np.float64), (S, 1))
+    out = t.simulate(cfg.A, cfg.B, x0, noise, restart=True)
+    for s in range(S):
+        r = o.closed_loop(cfg.A, cfg.B, x0[s], noise[:, s])
+        bad = np.flatnonzero(r["status"] == 2)
+        assert len(bad), "expected the oracle run to end infeasible"
+        k = bad[0]
+        assert (out["status"][:k, s] == 0).all() and out["status"][k, s] == 2
+        np.testing.assert_allclose(out["x"][:k + 1, s], r["x"][:k + 1], rtol=1e-6, atol=1e-6)
+        # new run from x0: state after the infeasible step, then the oracle again from there
+        np.testing.assert_array_equal(out["x"][k + 1, s], x0[s])
+        np.testing.assert_array_equal(out["xbar"][k + 1, s], x0[s])
+        np.testing.assert_array_equal(out["e"][k + 1, s], 0.0)
+        r2 = o.closed_loop(cfg.A, cfg.B, x0[s], noise[k + 1:k + 11, s])
+        np.testing.assert_allclose(out["x"][k + 1:k + 12, s], r2["x"], rtol=1e-6, atol=1e-6)

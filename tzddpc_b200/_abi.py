@@ -28,7 +28,7 @@ class TzProgramDesc(C.Structure):
 
 class TzSolverOpts(C.Structure):
     _fields_ = [(k, C.c_double) for k in ("rho", "rho_active", "rho_inactive", "sigma", "alpha", "eps_abs", "eps_rel")] + \
-               [(k, C.c_int32) for k in ("max_iter", "check_every", "polish", "warm_start")]
+               [(k, C.c_int32) for k in ("max_iter", "check_every", "polish", "warm_start", "cert_first")]
 
 
 class TzddpcLibraryMissing(RuntimeError):
@@ -71,7 +71,7 @@ def lib() -> C.CDLL:
     L.tz_solve.restype = C.c_int
     L.tz_solve.argtypes = [vp, C.POINTER(TzSolverOpts), i64] + [vp] * 10
     L.tz_closed_loop_step.restype = C.c_int
-    L.tz_closed_loop_step.argtypes = [vp, C.POINTER(TzSolverOpts), i64] + [vp] * 16
+    L.tz_closed_loop_step.argtypes = [vp, C.POINTER(TzSolverOpts), i64] + [vp] * 17
     L.tz_closed_loop_step_host_scratch_bytes.restype = C.c_size_t
     L.tz_closed_loop_step_host_scratch_bytes.argtypes = [vp, i64]
     L.tz_closed_loop_step_host.restype = C.c_int

@@ -46,7 +46,15 @@ struct Bucket {
   static constexpr int NCHL = (NCHK + G - 1) / G;
   static constexpr int TPB = 128;
   static constexpr int WPB = TPB / 32;                // warps per CTA
-  static constexpr int SPW = 32 / G;                  // scenarios per warp tile
+  static constexpr int SPW = 32 / G;                  // scenarios per solve tile of a warp
+  static constexpr int TPO = (SPW >= 16) ? 1 : 16 / SPW;   // solve tiles per output tile: the output phase always covers
+  static constexpr int SPO = SPW * TPO;               //   >= 16 consecutive scenarios = full 128-byte lines of every SoA row
+  // layout of the per-scenario vector om = [1 | v (NZ) | xbar0 (HP) | e0 (HP) | centre of Ze[1] (HP) | x+ (HP)], HP = NPAR/2 >= dim_x
+  static constexpr int HP = NPAR / 2;
+  static constexpr int OM_V = 1, OM_P = 1 + NZ, NW = 1 + NZ + NPAR;
+  static constexpr int OM_C = NW, OM_XP = NW + HP, KOM = NW + 2 * HP;
+  static constexpr int PRE_ROWS = 4 * HP;             // prefetched input rows of an output tile: [xbar0 | e0 | x | noise]
+  static constexpr int NCOLP = (NCOL + 1) & ~1;       // row pitch of R / Rchk (even: 16-byte aligned rows)
   static_assert(NCL <= 32 && (G & (G - 1)) == 0 && G <= 32 && N2 >= 1 && NAG >= 1, "bad bucket");
 };
 
@@ -57,24 +65,26 @@ struct QpProg {
   double A[BK::NC][BK::NZ];            // E A D (NOT multiplied by alpha)
   double l0[BK::NC], u0[BK::NC];
   double kink0[BK::NK], wabs[BK::NK];
-  double R[BK::NC][BK::NCOL];
+  double R[BK::NC][BK::NCOLP];
   double q0[BK::NZ];
   double Qp[BK::NZ][BK::NPAR];
   double Bt[BK::NAG][BK::NPAR];        // general atoms |Bt p + gam| (the unit atoms |p_c| are implicit)
   double gam[BK::NAG];
-  double Rchk[BK::NCHK][BK::NCOL];
+  double Rchk[BK::NCHK][BK::NCOLP];
   double cc[BK::NCOL];
   double CC2[BK::NPAR][BK::NPAR];
   double D[BK::NZ];
   double Einv[BK::NC];
+  double sing_inv[BK::NC];              // rows with a single non-zero A[i][j]: 1 / A[i][j] (scaled), else 0
   double cinv;                          // 1 / cost scaling
+  int sing_var[BK::NC];                 // ... and j, else -1 (singleton presolve: such rows are bounds on x_j)
   int row_of_slot[BK::NC];              // original row index of a slot, -1 for padding
-  int nz, nc, npar, nag, nchk, has_cc2;
+  int nz, nc, npar, nag, nchk, has_cc2, has_qp;
 };
 
 struct SolverParams {     // TzSolverOpts, device side
   double rho, rho_act, rho_inact, sigma, alpha, eps_abs, eps_rel;
-  int max_iter, check_every, polish, warm;
+  int max_iter, check_every, polish, warm, cert_first;
 };
 
 // compare-select min/max: 3 instructions instead of the ~8 of IEEE fmin/fmax (no NaN quieting needed:
@@ -142,14 +152,24 @@ __device__ __forceinline__ void chol_solve(const double (&L)[NZ][NZ], double (&b
 
 // Per-lane slice of one scenario's QP.  Local row k: k < N2 two-sided / kink, k < N2+NU upper
 // only, else lower only.
+// This lane's rows of alpha * A, read from shared memory on every use (the matrix is the same for all
+// scenarios; keeping the rows in registers cost 2*NCL*NZ registers per thread and a CTA per SM of occupancy).
+template <class BK>
+struct ARows {
+  const double* base;            // &Aa[g][0] of the shared-memory table Aa[NC][NZ]; local row k is slot k*G + g
+  __device__ __forceinline__ const double* operator[](int k) const { return base + k * (BK::G * BK::NZ); }
+};
+
 template <class BK>
 struct LaneQp {
-  double Aa[BK::NCL][BK::NZ];    // alpha * (this lane's rows of the scaled constraint matrix)
+  ARows<BK> Aa;                  // alpha * (this lane's rows of the scaled constraint matrix), in shared memory
   double lo[BK::N2 + BK::NL];    // lower bounds of the two-sided rows, then of the lower-only rows
   double hi[BK::N2 + BK::NU];    // upper bounds of the two-sided rows, then of the upper-only rows
   double kink[BK::N2];
   double q[BK::NZ];
   const double* wk;              // shared memory: |.| weights of this lane's two-sided rows, element k at [k * G]
+  const double* sinv;            // shared memory: singleton-row inverse coefficients of this lane's rows, element k at [k * G]
+  const int* svar;               // shared memory: singleton-row variable index (-1: not a singleton), element k at [k * G]
   const double (*P)[BK::NZ];     // shared memory: the scaled P (only read at factorisations and residual checks)
   __device__ __forceinline__ double lower(int k) const { return k < BK::N2 ? lo[k] : (k >= BK::N2 + BK::NU ? lo[k - BK::NU] : -INFINITY); }
   __device__ __forceinline__ double upper(int k) const { return k < BK::N2 + BK::NU ? hi[k] : INFINITY; }
@@ -171,6 +191,7 @@ struct LaneState {
   double z[BK::NCL], w[BK::NCL];  // inside admm_solve w = y / rho_row; y on entry (warm) and exit
   uint32_t act;                   // activity bits of the local rows
   bool switched;                  // false: every row still at the base rho
+  unsigned long long code;        // active-set code of the returned point (see active_code)
 };
 
 // K = P + sigma I + sum_i rho_i a_i a_i'  (group all-reduce of the lower triangle), then factor.
@@ -199,40 +220,235 @@ __device__ __forceinline__ void build_factor(const LaneQp<BK>& qp, const double 
   chol_factor<NZ>(L);
 }
 
+// Singleton presolve: a row with one non-zero coefficient is a bound on one variable; if the
+// bounds on some x_j collected from all such rows are inconsistent the program is infeasible --
+// decided exactly and at once, where ADMM needs ~100 iterations to build its Farkas certificate.
+// (All infeasible closed-loop instances of the shipped examples are of this kind: the tightened
+// state rows at k = 1 depend on v_0 only.)  Whole warps; returns a group-uniform flag.
+template <class BK>
+__device__ __forceinline__ bool singleton_infeasible(const LaneQp<BK>& qp) {
+  constexpr int NZ = BK::NZ, NCL = BK::NCL, G = BK::G;
+  double blo[NZ], bhi[NZ];
+#pragma unroll
+  for (int j = 0; j < NZ; ++j) { blo[j] = -INFINITY; bhi[j] = INFINITY; }
+#pragma unroll
+  for (int k = 0; k < NCL; ++k) {
+    const int sv = qp.svar[k * G];
+    const double inv = qp.sinv[k * G];
+    const double a = qp.lower(k) * inv, b = qp.upper(k) * inv;
+    const double lo = inv > 0.0 ? a : b, hi = inv > 0.0 ? b : a;
+#pragma unroll
+    for (int j = 0; j < NZ; ++j) {
+      blo[j] = (sv == j && lo > blo[j]) ? lo : blo[j];
+      bhi[j] = (sv == j && hi < bhi[j]) ? hi : bhi[j];
+    }
+  }
+  int bad = 0;
+#pragma unroll
+  for (int j = 0; j < NZ; ++j) {
+    const double lo = gmax<G>(blo[j]), hi = -gmax<G>(-bhi[j]);
+    const double sc = fmax(1.0, fmin(fabs(lo), fabs(hi)));
+    bad |= (lo - hi > 1e-9 * sc) ? 1 : 0;
+  }
+  return bad != 0;
+}
+
+// ---- active-set codes: 3 bits per local row, packed into one 64-bit word per lane ----------------
+//   0 inactive   1 on its lower bound   2 on its upper bound   3 on the kink of its |.| cost
+//   4 / 5 |.| row above / below its kink (linear cost)          6 equality row (lower == upper)
+// bit 63 marks a valid word when it travels through the hint buffer.
+constexpr unsigned long long kCodeValid = 1ull << 63;
+
+template <class BK>
+__device__ __forceinline__ unsigned long long active_code(const LaneQp<BK>& qp, const double (&z)[BK::NCL]) {
+  constexpr int NCL = BK::NCL, N2 = BK::N2, G = BK::G;
+  unsigned long long code = 0ull;
+#pragma unroll
+  for (int k = 0; k < NCL; ++k) {
+    const double lo = qp.lower(k), hi = qp.upper(k);
+    unsigned c = 0u;
+    if (z[k] <= lo) c = lo < hi ? 1u : 6u;
+    else if (z[k] >= hi) c = 2u;
+    else if (k < N2) {
+      if (qp.wk[(k < N2 ? k : 0) * G] > 0.0) {
+        const double kk = qp.kink[k < N2 ? k : 0];
+        c = z[k] == kk ? 3u : (z[k] > kk ? 4u : 5u);
+      }
+    }
+    code |= (unsigned long long)c << (3 * k);
+  }
+  return code;
+}
+
+// Active-set certificate: the polish used as a TERMINATION TEST.
+// Given a guess of the active set (the rows ADMM has clipped onto a bound or onto the kink of their |.| cost, or
+// the optimal set of the previous closed-loop step), the equality-constrained problem on that set is solved with
+// n_iter masked augmented-Lagrangian steps
+//   K = P + delta I + mu sum_act b_i b_i',   x <- K^{-1}(delta x - qt + sum_act b_i (mu t_i - lam_i)),   lam_i += mu (b_i x - t_i)
+// (b_i = alpha a_i, t_i = alpha * bound: only NZ x NZ systems, no index compaction), and then the KKT conditions
+// of the ORIGINAL problem are checked: every row feasible, active rows on their bound, multipliers of the right
+// sign (|y| <= w on a kink), |.| rows on the assumed side of their kink.  Stationarity
+// P x + qt + B'lam = delta (x_prev - x) holds by construction.  When all hold, (xk, y) is an exact primal-dual
+// solution whatever the ADMM residuals are -- after 3 ADMM iterations from a cold start for almost every
+// closed-loop instance of the shipped examples, and after none when the previous step's set is still optimal.
+// A wrong guess only costs the test.  Must be called by whole warps.  lam: in y / alpha of the current
+// iterate (or zeros), out y (when accepted).  Returns a group-uniform flag.
+template <class BK>
+__device__ __forceinline__ bool admm_certify(const LaneQp<BK>& qp, double inv_alpha, int n_iter, unsigned long long code,
+                                             const double (&x0)[BK::NZ], double (&lam)[BK::NCL], double (&xk)[BK::NZ]) {
+  constexpr int NZ = BK::NZ, NCL = BK::NCL, N2 = BK::N2, G = BK::G;
+  const double delta = 1e-9, mu = 1e6, alpha = 1.0 / inv_alpha;
+  double L[NZ][NZ], qt[NZ];
+  auto cof = [&](int k) { return (unsigned)(code >> (3 * k)) & 7u; };
+  auto target = [&](int k, unsigned c) {          // alpha * (the bound the row sits on)
+    double b = (c == 2u) ? qp.upper(k) : qp.lower(k);
+    if (k < N2 && c == 3u) b = qp.kink[k < N2 ? k : 0];
+    return b * alpha;
+  };
+#pragma unroll
+  for (int a = 0; a < NZ; ++a) {
+    qt[a] = 0.0;
+    xk[a] = x0[a];
+#pragma unroll
+    for (int b = 0; b <= a; ++b) L[a][b] = 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < NCL; ++k) {
+    const unsigned c = cof(k);
+    const bool ia = (c >= 1u && c <= 3u) || c == 6u;
+    if (k < N2 && (c == 4u || c == 5u)) {           // away from the kink the |.| cost is linear: its multiplier is the subgradient
+      const double wgt = qp.wk[(k < N2 ? k : 0) * G];
+      const double sg = (c == 4u ? wgt : -wgt) * inv_alpha;
+#pragma unroll
+      for (int a = 0; a < NZ; ++a) qt[a] = fma(sg, qp.Aa[k][a], qt[a]);
+    }
+    const double m_ = ia ? mu : 0.0;
+    lam[k] = ia ? lam[k] : 0.0;
+#pragma unroll
+    for (int a = 0; a < NZ; ++a) {
+      const double ra = m_ * qp.Aa[k][a];
+#pragma unroll
+      for (int c2 = 0; c2 <= a; ++c2) L[a][c2] = fma(ra, qp.Aa[k][c2], L[a][c2]);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < NZ; ++a) {
+    qt[a] = gsum<G>(qt[a]) + qp.q[a];
+#pragma unroll
+    for (int b = 0; b <= a; ++b) L[a][b] = gsum<G>(L[a][b]) + qp.P[a][b] + (a == b ? delta : 0.0);
+  }
+  chol_factor<NZ>(L);
+#pragma unroll 1
+  for (int it = 0; it < n_iter; ++it) {
+    double rhs[NZ];
+#pragma unroll
+    for (int a = 0; a < NZ; ++a) rhs[a] = 0.0;
+#pragma unroll
+    for (int k = 0; k < NCL; ++k) {
+      const unsigned c = cof(k);
+      const bool ia = (c >= 1u && c <= 3u) || c == 6u;
+      const double t = ia ? fma(mu, target(k, c), -lam[k]) : 0.0;
+#pragma unroll
+      for (int a = 0; a < NZ; ++a) rhs[a] = fma(qp.Aa[k][a], t, rhs[a]);
+    }
+#pragma unroll
+    for (int a = 0; a < NZ; ++a) rhs[a] = gsum<G>(rhs[a]) + fma(delta, xk[a], -qt[a]);
+    chol_solve<NZ>(L, rhs);
+#pragma unroll
+    for (int a = 0; a < NZ; ++a) xk[a] = rhs[a];
+#pragma unroll
+    for (int k = 0; k < NCL; ++k) {
+      const unsigned c = cof(k);
+      const bool ia = (c >= 1u && c <= 3u) || c == 6u;
+      double ax = 0.0;
+#pragma unroll
+      for (int a = 0; a < NZ; ++a) ax = fma(qp.Aa[k][a], xk[a], ax);
+      lam[k] = ia ? fma(mu, ax - target(k, c), lam[k]) : lam[k];
+    }
+  }
+  // ---- KKT certificate
+  double scale = 1.0, lscale = 1.0;
+  double axs[NCL];
+#pragma unroll
+  for (int k = 0; k < NCL; ++k) {
+    double ax = 0.0;
+#pragma unroll
+    for (int a = 0; a < NZ; ++a) ax = fma(qp.Aa[k][a], xk[a], ax);
+    axs[k] = ax * inv_alpha;
+    scale = fmax(scale, fabs(axs[k]));
+    lscale = fmax(lscale, fabs(lam[k]));
+  }
+  scale = gmax<G>(scale);
+  lscale = gmax<G>(lscale);
+  const double ptol = 1e-9 * scale, ltol = 1e-9 * lscale;
+  int bad = 0;
+#pragma unroll
+  for (int k = 0; k < NCL; ++k) {
+    const double ax = axs[k];
+    const unsigned c = cof(k);
+    bad |= (qp.lower(k) - ax > ptol) || (ax - qp.upper(k) > ptol);                 // primal feasibility
+    if ((c >= 1u && c <= 3u) || c == 6u) {
+      bad |= fabs(ax - target(k, c) * inv_alpha) > 1e-8 * scale;                  // active rows on their bound
+      bad |= (c == 2u) && (lam[k] < -ltol);                                       // multiplier signs
+      bad |= (c == 1u) && (lam[k] > ltol);
+      if (k < N2) bad |= (c == 3u) && (fabs(lam[k]) * alpha > qp.wk[(k < N2 ? k : 0) * G] * (1.0 + 1e-9));
+      lam[k] *= alpha;                                                            // y
+    } else if (k < N2 && (c == 4u || c == 5u)) {
+      const double kk = qp.kink[k < N2 ? k : 0];
+      const double wgt = qp.wk[(k < N2 ? k : 0) * G];
+      bad |= (c == 4u) ? !(ax > kk) : !(ax < kk);                                 // side of the kink as assumed
+      lam[k] = (c == 4u) ? wgt : -wgt;
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < NZ; ++a) bad |= !(xk[a] == xk[a]);
+  return gor<G>(bad) == 0;
+}
+
 // ADMM for the scenario owned by this lane group.  Every lane of the warp must call it
 // (shuffles and warp votes inside); `live` is group-uniform.  On a warm start st.x, st.w
 // (holding y), st.act, st.switched are inputs.  Returns TZ_STATUS_*; st.w holds y on exit.
 template <class BK>
 __device__ int admm_solve(const LaneQp<BK>& qp, const SolverParams& sp, bool live, LaneState<BK>& st, bool warm,
                           double* __restrict__ ysave /* lane-private shared scratch, element k at [k * 32] */,
-                          int& iters_out) {
+                          int& iters_out, bool& certified) {
   constexpr int NZ = BK::NZ, NCL = BK::NCL, N2 = BK::N2, G = BK::G;
   const double alpha = sp.alpha, sigma = sp.sigma, oma = 1.0 - sp.alpha, inv_alpha = 1.0 / sp.alpha;
   const double rq_base = sp.rho * inv_alpha, rq_act = sp.rho * sp.rho_act * inv_alpha,
                rq_inact = sp.rho * sp.rho_inact * inv_alpha;
+  // reciprocals once per solve (a double division costs ~40 instructions): 1 / rho_row and 1 / rq_row
+  const double irho_base = 1.0 / sp.rho, irho_act = 1.0 / (sp.rho * sp.rho_act), irho_inact = 1.0 / (sp.rho * sp.rho_inact);
+  const double irq_act = irho_act * alpha, irq_inact = irho_inact * alpha;
+  auto irho_of = [&](double rqv) { return rqv == rq_act ? irho_act : (rqv == rq_inact ? irho_inact : irho_base); };
 
   double rq[NCL];                     // rho_row / alpha
   if (!warm) {
 #pragma unroll
-    for (int j = 0; j < NZ; ++j) st.x[j] = 0.0;
+    for (int k = 0; k < NCL; ++k) rq[k] = rq_base;
+    if (live) {             // (a lane that is not solved keeps its state: it may hold a hint-certified solution)
 #pragma unroll
-    for (int k = 0; k < NCL; ++k) { st.w[k] = 0.0; rq[k] = rq_base; }
-    st.act = 0u;
-    st.switched = false;
+      for (int j = 0; j < NZ; ++j) st.x[j] = 0.0;
+#pragma unroll
+      for (int k = 0; k < NCL; ++k) st.w[k] = 0.0;
+      st.act = 0u;
+      st.switched = false;
+    }
   } else {
 #pragma unroll
     for (int k = 0; k < NCL; ++k) {
       rq[k] = ((st.act >> k) & 1u) ? rq_act : rq_inact;
-      st.w[k] = st.w[k] / (rq[k] * alpha);                 // y -> w
+      st.w[k] = st.w[k] * irho_of(rq[k]);                  // y -> w
     }
   }
   // initial z = clip(A x)
+  if (live) {
 #pragma unroll
-  for (int k = 0; k < NCL; ++k) {
-    double ax = 0.0;
+    for (int k = 0; k < NCL; ++k) {
+      double ax = 0.0;
 #pragma unroll
-    for (int j = 0; j < NZ; ++j) ax = fma(qp.Aa[k][j], st.x[j], ax);
-    st.z[k] = qp.clip(k, ax * inv_alpha);
+      for (int j = 0; j < NZ; ++j) ax = fma(qp.Aa[k][j], st.x[j], ax);
+      st.z[k] = qp.clip(k, ax * inv_alpha);
+    }
   }
   double qn = 0.0;
 #pragma unroll
@@ -242,12 +458,15 @@ __device__ int admm_solve(const LaneQp<BK>& qp, const SolverParams& sp, bool liv
   build_factor<BK>(qp, rq, inv_alpha, sigma, L);
   double th[N2];                      // soft thresholds wk / rho of the |.| rows
 #pragma unroll
-  for (int k = 0; k < N2; ++k) th[k] = qp.wk[k * G] / (rq[k] * alpha);
+  for (int k = 0; k < N2; ++k) th[k] = qp.wk[k * G] * irho_of(rq[k]);
 
   int status = TZ_STATUS_MAXITER;
   bool done = !live;
   int iters = 0;
   int next_upd = 2, gap = 2;
+  int next_cert = sp.cert_first > 0 ? sp.cert_first : sp.max_iter + 1, cert_gap = 2;     // tests at cert_first + {0, 2, 5, 10, 18, ...}
+  certified = false;
+  bool presolved = false;
   const int check_every = sp.check_every > 0 ? sp.check_every : 1;
   int until_check = check_every;
   bool have_prev = false;             // ysave holds the duals of the previous check
@@ -287,8 +506,38 @@ __device__ int admm_solve(const LaneQp<BK>& qp, const SolverParams& sp, bool liv
       for (int j = 0; j < NZ; ++j) st.x[j] = fma(alpha, xt[j], oma * st.x[j]);
       iters = it;
     }
+    bool sync_point = false;
+    if (it == next_cert) {
+      next_cert += cert_gap;
+      cert_gap = (cert_gap * 3 + 1) / 2;
+      double lam[NCL], xk[NZ];
+#pragma unroll
+      for (int k = 0; k < NCL; ++k) lam[k] = rq[k] * st.w[k];
+      const unsigned long long code = active_code<BK>(qp, st.z);
+      const bool ok = admm_certify<BK>(qp, inv_alpha, sp.polish > 0 ? sp.polish : 3, code, st.x, lam, xk);
+      if (ok && !done) {
+#pragma unroll
+        for (int j = 0; j < NZ; ++j) st.x[j] = xk[j];
+#pragma unroll
+        for (int k = 0; k < NCL; ++k) st.w[k] = lam[k];         // y itself: the final w -> y conversion is skipped
+        st.code = code;
+        status = TZ_STATUS_OK;
+        done = true;
+        certified = true;
+      }
+      if (!presolved && __any_sync(0xffffffffu, !done)) {      // first failed certificate: is the program infeasible outright?
+        presolved = true;
+        const bool inf = singleton_infeasible<BK>(qp);
+        if (inf && !done) {
+          status = TZ_STATUS_INFEASIBLE;
+          done = true;
+        }
+      }
+      sync_point = true;
+    }
     const bool check = (--until_check == 0) || (it == sp.max_iter);
     if (check) {
+      sync_point = true;
       until_check = check_every;
       // ---- residuals (scaled space); dual increment since the previous check for the certificate
       double rp = 0.0, pn = 0.0, dy_norm = 0.0, supp = 0.0, dy_inf = 0.0;
@@ -357,8 +606,8 @@ __device__ int admm_solve(const LaneQp<BK>& qp, const SolverParams& sp, bool liv
         }
       }
       have_prev = true;
-      if (__all_sync(0xffffffffu, done)) break;
     }
+    if (sync_point && __all_sync(0xffffffffu, done)) break;
     // ---- activity-driven rho switch on a geometric schedule
     if (it == next_upd) {
       gap = (gap * 3 + 1) / 2;
@@ -371,14 +620,14 @@ __device__ int admm_solve(const LaneQp<BK>& qp, const SolverParams& sp, bool liv
       if (apply) {
 #pragma unroll
         for (int k = 0; k < NCL; ++k) {      // keep y = rho w invariant under the switch
-          const double nr = ((nm >> k) & 1u) ? rq_act : rq_inact;
-          st.w[k] *= rq[k] / nr;
-          rq[k] = nr;
+          const bool on = (nm >> k) & 1u;
+          st.w[k] *= rq[k] * (on ? irq_act : irq_inact);
+          rq[k] = on ? rq_act : rq_inact;
         }
         st.act = nm;
         st.switched = true;
 #pragma unroll
-        for (int k = 0; k < N2; ++k) th[k] = qp.wk[k * G] / (rq[k] * alpha);
+        for (int k = 0; k < N2; ++k) th[k] = qp.wk[k * G] * irho_of(rq[k]);
       }
       // the factor is rebuilt with group shuffles, so the whole warp takes the branch together
       if (__any_sync(0xffffffffu, apply)) {
@@ -394,8 +643,11 @@ __device__ int admm_solve(const LaneQp<BK>& qp, const SolverParams& sp, bool liv
     }
   }
   // hand y (not w) back to the caller
+  if (!certified && live) {
 #pragma unroll
-  for (int k = 0; k < NCL; ++k) st.w[k] *= rq[k] * alpha;
+    for (int k = 0; k < NCL; ++k) st.w[k] *= rq[k] * alpha;
+    st.code = active_code<BK>(qp, st.z);
+  }
   iters_out = iters;
   return live ? status : TZ_STATUS_OK;
 }

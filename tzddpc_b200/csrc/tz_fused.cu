@@ -21,29 +21,30 @@
 
 namespace tz {
 
-constexpr int kMaxOm = 1 + 16 + 2 * kMaxN + 2 * kMaxN;   // [1; v; p; centre of Ze[1]; staged x+]
-
-struct Aux {                       // device-resident tables with run-time sizes
-  const double* XB;                // (N+1)n x nw : xbar_0..xbar_N = XB [1; v; p]
-  const double* CZ;                // n x nw      : centre of Ze[1] = CZ [1; v; p]
-  const double* K;                 // m x n
-  const double* nz_coef;           // Ze[1] entries with one term: value = coef * om[idx]
-  const int32_t* nz_ent;           //   their entry index r*(1+g1)+j
-  const int32_t* nz_idx;           //   index into om = [1; v; p; centre]
-  const int32_t* zero_ent;         // entries that are structurally zero
-  int n_nz, n_zero;
-  int n, m, N, nv, g1, nw;         // nw = 1 + nv + npar
+// Run-time sized tables of a program, one device blob staged into shared memory by every CTA:
+//   doubles: XB ((N+1)n x NW) | CZ (n x NW) | K (m x n) | nz_coef (n_nz)      [+ A_true, B_true appended in smem]
+//   int32  : nz_ent (n_nz) | nz_idx (n_nz)
+// XB / CZ columns and nz_idx address the per-scenario vector om (layout in Bucket: OM_*).
+struct Aux {
+  const double* tab;
+  int n_dbl, n_int;                // sizes of the two parts
+  int o_XB, o_CZ, o_K, o_coef;     // offsets (doubles)
+  int o_ent, o_idx;                // offsets (int32, from the start of the int part)
+  int n_nz;                        // entries of Ze[1].Z that are not structurally zero (centre column included)
+  int n, m, N, nv, g1;
 };
 
 struct StepArgs {
   int64_t S;                       // scenarios in this launch
   int64_t ld;                      // leading dimension of every SoA array (>= S)
+  int vec2;                        // 1: S, ld even and every array 16-byte aligned -> two scenarios per lane in the output phase
   const double* xbar0;             // parameters (n x S); aliases xbar/e in closed loop
   const double* e0;
   double* x;                       // closed loop only (NULL = solve only)
   double* xbar;
   double* e;
   const double* noise;
+  const double* x_restart;         // closed loop only: state an infeasible scenario restarts from (NULL: it keeps its state)
   const double* A_true;
   const double* B_true;
   double* cost;
@@ -66,18 +67,236 @@ struct StepArgs {
 // Shared-memory image of one CTA: the program (read-only after staging) and, per warp, the
 // exchange buffers between the solve phase and the output phase of a tile.
 template <class BK>
-struct WarpBuf {
-  double om[kMaxOm][BK::SPW];      // [1; v; p; centre of Ze[1]] per scenario of the warp's tile
+struct alignas(16) WarpBuf {
+  double pre[2][BK::PRE_ROWS][BK::SPO];  // cp.async double buffer: rows [xbar0 | e0 | x | noise] (n each) of this / the next output tile
+  double om[BK::KOM][BK::SPO];     // [1 | v | xbar0 | e0 | centre of Ze[1] | x+] per scenario of the warp's output tile
   double ysave[BK::NCL][32];       // duals at the previous residual check (certificate of infeasibility)
-  double cost[BK::SPW];
-  int status[BK::SPW];
-  int iters[BK::SPW];
+  double cost[BK::SPO];
+  double stacc[TZ_NSTATS][BK::SPO];   // closed-loop statistics of this warp's tiles, reduced once at the end of the kernel
+  int status[BK::SPO];
+  int iters[BK::SPO];
 };
 template <class BK>
-struct Smem {
+struct alignas(16) Smem {
+  double Aa[BK::NC][BK::NZ];       // alpha * A (alpha is a solver option, so this is built when the program is staged)
   QpProg<BK> pg;
   WarpBuf<BK> wb[BK::WPB];
 };
+
+// ---- W scenarios per lane (1: scalar accesses, 2: 16-byte accesses) ----------------------------
+template <int W> struct Vec;
+template <> struct Vec<1> { double a; };
+template <> struct Vec<2> { double a, b; };
+__device__ __forceinline__ Vec<1> vld(const double* p, Vec<1>*) { return Vec<1>{*p}; }
+__device__ __forceinline__ Vec<2> vld(const double* p, Vec<2>*) { const double2 t = *reinterpret_cast<const double2*>(p); return Vec<2>{t.x, t.y}; }
+__device__ __forceinline__ void vst(double* p, Vec<1> v) { *p = v.a; }
+__device__ __forceinline__ void vst(double* p, Vec<2> v) { *reinterpret_cast<double2*>(p) = make_double2(v.a, v.b); }
+#ifndef TZ_ZST
+#define TZ_ZST 1
+#endif
+#if TZ_ZST == 0
+__device__ __forceinline__ void vstcs(double* p, Vec<1> v) { *p = v.a; }
+__device__ __forceinline__ void vstcs(double* p, Vec<2> v) { *reinterpret_cast<double2*>(p) = make_double2(v.a, v.b); }
+#elif TZ_ZST == 1
+__device__ __forceinline__ void vstcs(double* p, Vec<1> v) { __stcs(p, v.a); }
+__device__ __forceinline__ void vstcs(double* p, Vec<2> v) { __stcs(reinterpret_cast<double2*>(p), make_double2(v.a, v.b)); }
+#else
+__device__ __forceinline__ void vstcs(double* p, Vec<1> v) { __stcg(p, v.a); }
+__device__ __forceinline__ void vstcs(double* p, Vec<2> v) { __stcg(reinterpret_cast<double2*>(p), make_double2(v.a, v.b)); }
+#endif
+__device__ __forceinline__ Vec<1> vfma(double c, Vec<1> x, Vec<1> acc) { return Vec<1>{fma(c, x.a, acc.a)}; }
+__device__ __forceinline__ Vec<2> vfma(double c, Vec<2> x, Vec<2> acc) { return Vec<2>{fma(c, x.a, acc.a), fma(c, x.b, acc.b)}; }
+__device__ __forceinline__ Vec<1> vmul(double c, Vec<1> x) { return Vec<1>{c * x.a}; }
+__device__ __forceinline__ Vec<2> vmul(double c, Vec<2> x) { return Vec<2>{c * x.a, c * x.b}; }
+__device__ __forceinline__ Vec<1> vsub(Vec<1> x, Vec<1> y) { return Vec<1>{x.a - y.a}; }
+__device__ __forceinline__ Vec<2> vsub(Vec<2> x, Vec<2> y) { return Vec<2>{x.a - y.a, x.b - y.b}; }
+__device__ __forceinline__ Vec<1> vzero(Vec<1>*) { return Vec<1>{0.0}; }
+__device__ __forceinline__ Vec<2> vzero(Vec<2>*) { return Vec<2>{0.0, 0.0}; }
+__device__ __forceinline__ Vec<1> vsel(const bool* g, Vec<1> x, double other) { return Vec<1>{g[0] ? x.a : other}; }
+__device__ __forceinline__ Vec<2> vsel(const bool* g, Vec<2> x, double other) { return Vec<2>{g[0] ? x.a : other, g[1] ? x.b : other}; }
+__device__ __forceinline__ double vget(Vec<1> x, int) { return x.a; }
+__device__ __forceinline__ double vget(Vec<2> x, int i) { return i == 0 ? x.a : x.b; }
+
+// ---- cp.async prefetch of the per-scenario inputs of an output tile (hides the DRAM latency of the only loads of the step)
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+template <class BK>
+__device__ __forceinline__ void prefetch_inputs(double (*dst)[BK::SPO], const StepArgs& a, int n, int64_t otile, int lane) {
+  constexpr int SPO = BK::SPO;
+  const double* src[4] = {a.xbar0, a.e0, a.x, a.noise};
+  const int64_t s0 = otile * SPO;
+  const int narr = a.x != nullptr ? 4 : 2;
+  if (a.vec2) {
+    constexpr int CPR = SPO / 2;                        // 16-byte chunks per row
+    const int total = narr * n * CPR;
+    for (int c = lane; c < total; c += 32) {
+      const int row = c / CPR, ch = c - row * CPR, arr = row / n, r = row - arr * n;
+      const int64_t s = s0 + 2 * ch;
+      if (src[arr] != nullptr && s < a.S) cp_async16(&dst[row][2 * ch], src[arr] + (int64_t)r * a.ld + s);
+    }
+  } else {
+    const int total = narr * n * SPO;
+    for (int c = lane; c < total; c += 32) {
+      const int row = c / SPO, ch = c - row * SPO, arr = row / n, r = row - arr * n;
+      const int64_t s = s0 + ch;
+      if (src[arr] != nullptr && s < a.S) cp_async8(&dst[row][ch], src[arr] + (int64_t)r * a.ld + s);
+    }
+  }
+  cp_async_commit();
+}
+
+// Output phase of one output tile (SPO >= 16 consecutive scenarios = TPO solve tiles): lane -> (W consecutive
+// scenarios, slice); one store instruction of the warp covers NSL entries x SPO scenarios = NSL runs of SPO*8 >= 128
+// contiguous bytes (full lines) of the scenario-fastest arrays.
+template <class BK, int W>
+__device__ __forceinline__ void output_phase(WarpBuf<BK>& wb, const double (*pre)[BK::SPO], const Aux& ax, const StepArgs& a,
+                                             const double* __restrict__ tabd, const int* __restrict__ tabi, int64_t tile, int lane) {
+  constexpr int SPW = BK::SPO, NW = BK::NW, NGRP = SPW / W, NSL = 32 / NGRP;
+  using V = Vec<W>;
+  V* const vt = nullptr;
+  const int pc = lane % NGRP, slice = lane / NGRP, sc0 = pc * W;
+  const int64_t so = tile * SPW + sc0;
+  const int64_t LD = a.ld;
+  const int n = ax.n, m = ax.m, nv = ax.nv;
+  const double* sXB = tabd + ax.o_XB;
+  int stt[W];
+  bool olive[W], ogood[W];
+  bool any_live = false, all_good = true;
+#pragma unroll
+  for (int t = 0; t < W; ++t) {
+    stt[t] = wb.status[sc0 + t];
+    olive[t] = stt[t] >= 0;
+    ogood[t] = stt[t] == TZ_STATUS_OK || stt[t] == TZ_STATUS_MAXITER;
+    any_live = any_live || olive[t];
+    all_good = all_good && ogood[t];
+  }
+  // (vector path: S is even, so the scenarios of a pair are live together)
+  auto om = [&](int j) { return vld(&wb.om[j][sc0], vt); };
+  if (any_live) {
+    // ---- Ze[1].Z at the optimum (examples/2.pulley_sim.py:96: Zek.Z.value), dense n x (1+g1): zero-fill, then
+    // overwrite the ~12 % entries that are not structurally zero (both writes merge in L2 before reaching HBM)
+    if (a.ze1) {
+      double* base = a.ze1 + so;
+      const int nent = n * (1 + ax.g1);
+      const int64_t stepb = (int64_t)NSL * LD;
+      double* ptr = base + (int64_t)slice * LD;
+      const V z0 = vzero(vt);
+      // (a down-counter: with the trip count as loop bound the compiler spilled it and re-loaded it from local memory in
+      // every iteration, behind the stores in the same LSU queue -- 20 % of all stall samples in profiles/r1_v6)
+#pragma unroll 4
+      for (int cnt = (nent - slice + NSL - 1) / NSL; cnt > 0; --cnt, ptr += stepb) vstcs(ptr, z0);
+      __syncwarp();
+      const double* coef = tabd + ax.o_coef;
+      const int* ent = tabi + ax.o_ent;
+      const int* idx = tabi + ax.o_idx;
+#pragma unroll 2
+      for (int i = slice; i < ax.n_nz; i += NSL) vstcs(base + (int64_t)ent[i] * LD, vmul(coef[i], om(idx[i])));
+    }
+    // ---- nominal trajectory xbar_0..xbar_N = XB om  (tzddpc/tzddpc.py:166-170)
+    if (a.xbar_traj) {
+      const int nrows = (ax.N + 1) * n;
+      for (int i = slice; i < nrows; i += NSL) {
+        const double* row = sXB + i * NW;
+        V acc = vzero(vt);
+#pragma unroll
+        for (int j = 0; j < NW; ++j) acc = vfma(row[j], om(j), acc);
+        vst(a.xbar_traj + (int64_t)i * LD + so, acc);
+      }
+    }
+    if (a.v)
+      for (int j = slice; j < nv; j += NSL) vst(a.v + (int64_t)j * LD + so, om(BK::OM_V + j));
+    if (slice == 0) {
+#pragma unroll
+      for (int t = 0; t < W; ++t) {
+        if (olive[t]) {
+          if (a.status) a.status[so + t] = stt[t];
+          if (a.iters) a.iters[so + t] = wb.iters[sc0 + t];
+          if (a.cost) a.cost[so + t] = wb.cost[sc0 + t];
+        }
+      }
+    }
+  }
+  // ---- closed-loop update (examples/2.pulley_sim.py:90-94): row i of the update by slice i
+  if (a.x != nullptr) {
+    const double* sK = tabd + ax.o_K;
+    const double* sA = tabd + ax.n_dbl;
+    const double* sB = sA + n * n;
+    if (any_live) {
+      V us[kMaxM];
+#pragma unroll
+      for (int j = 0; j < kMaxM; ++j) {
+        V acc = vzero(vt);
+        if (j < m) {
+          acc = om(BK::OM_V + j);                                              // v[0]
+          for (int i = 0; i < n; ++i) acc = vfma(sK[j * n + i], om(BK::OM_P + BK::NPAR / 2 + i), acc);
+          if (a.u_out && slice == 0) vst(a.u_out + (int64_t)j * LD + so, vsel(ogood, acc, NAN));
+        }
+        us[j] = acc;                                                           // u = K e + v[0]
+      }
+      for (int i = slice; i < n; i += NSL) {
+        V acc = a.noise ? vld(&pre[3 * n + i][sc0], vt) : vzero(vt);
+        for (int k = 0; k < n; ++k) acc = vfma(sA[i * n + k], vld(&pre[2 * n + k][sc0], vt), acc);
+#pragma unroll
+        for (int k = 0; k < kMaxM; ++k)
+          if (k < m) acc = vfma(sB[i * m + k], us[k], acc);
+        const double* row = sXB + (n + i) * NW;                                // xbar+ = xbar_traj[1]
+        V xb1 = vzero(vt);
+#pragma unroll
+        for (int j = 0; j < NW; ++j) xb1 = vfma(row[j], om(j), xb1);
+        V en = vsub(acc, xb1);                                                 // e+ = x+ - xbar+
+        if (!all_good) {
+          // a scenario whose step failed keeps its state, or -- the reference raises and the run ends
+          // (tzddpc/tzddpc.py:374-375) -- starts a new run from x_restart: x = xbar = x_restart, e = 0
+          const V xo = vld(&pre[2 * n + i][sc0], vt);
+          const V xbo = om(BK::OM_P + i), eo = om(BK::OM_P + BK::NPAR / 2 + i);
+          const V xr = a.x_restart ? vld(a.x_restart + (int64_t)i * LD + so, vt) : xo;
+          double xa[W], ba[W], ea[W];
+#pragma unroll
+          for (int t = 0; t < W; ++t) {
+            xa[t] = ogood[t] ? vget(acc, t) : vget(xr, t);
+            ba[t] = ogood[t] ? vget(xb1, t) : (a.x_restart ? vget(xr, t) : vget(xbo, t));
+            ea[t] = ogood[t] ? vget(en, t) : (a.x_restart ? 0.0 : vget(eo, t));
+          }
+          if constexpr (W == 1) { acc = V{xa[0]}; xb1 = V{ba[0]}; en = V{ea[0]}; }
+          else { acc = V{xa[0], xa[1]}; xb1 = V{ba[0], ba[1]}; en = V{ea[0], ea[1]}; }
+        }
+        vst(&wb.om[BK::OM_XP + i][sc0], acc);
+        vst(a.x + (int64_t)i * LD + so, acc);                                  // x+ = A x + B u + w
+        vst(a.xbar + (int64_t)i * LD + so, xb1);
+        vst(a.e + (int64_t)i * LD + so, en);
+      }
+    }
+    if (a.stats != nullptr) {       // per-scenario-slot partial sums in shared memory, reduced once at the end of the kernel
+      __syncwarp();
+      if (slice == 0) {
+#pragma unroll
+        for (int t = 0; t < W; ++t) {
+          if (olive[t]) {
+            const int c = sc0 + t;
+            double nrm2 = 0.0;
+            for (int i = 0; i < n; ++i) { const double xv = wb.om[BK::OM_XP + i][c]; nrm2 = fma(xv, xv, nrm2); }
+            if (ogood[t]) { wb.stacc[0][c] += sqrt(nrm2); wb.stacc[1][c] += nrm2; wb.stacc[2][c] += wb.cost[c]; }
+            if (stt[t] == TZ_STATUS_INFEASIBLE) wb.stacc[3][c] += 1.0;
+            if (stt[t] == TZ_STATUS_MAXITER) wb.stacc[4][c] += 1.0;
+            wb.stacc[5][c] += (double)wb.iters[c];
+            if (stt[t] == TZ_STATUS_NONFINITE) wb.stacc[6][c] += 1.0;
+            wb.stacc[7][c] += 1.0;
+          }
+        }
+      }
+    }
+  }
+}
 
 // Persistent kernel; every WARP loops on its own over tiles of SPW = 32/G scenarios, so there is
 // no CTA barrier after the program has been staged (a CTA barrier made fast warps wait for the
@@ -86,15 +305,27 @@ template <class BK>
 __global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel(const QpProg<BK>* __restrict__ gpg, const Aux ax,
                                                                 const SolverParams sp, const StepArgs a) {
   constexpr int NZ = BK::NZ, NCL = BK::NCL, N2 = BK::N2, NU = BK::NU, NPAR = BK::NPAR, NAG = BK::NAG, NCHL = BK::NCHL,
-                NCOL = BK::NCOL, TPB = BK::TPB, G = BK::G, SPW = BK::SPW;
+                NCOL = BK::NCOL, TPB = BK::TPB, G = BK::G, SPW = BK::SPW, NW = BK::NW, HP = BK::NPAR / 2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem<BK>& sm = *reinterpret_cast<Smem<BK>*>(smem_raw);
+  double* tabd = reinterpret_cast<double*>(smem_raw + sizeof(Smem<BK>));
   const int tid = threadIdx.x;
-  {  // stage the program once per CTA (persistent kernel: amortised over all tiles of this CTA)
+  const int n = ax.n, m = ax.m, nv = ax.nv;
+  int* tabi = reinterpret_cast<int*>(tabd + ax.n_dbl + n * n + n * m);
+  {  // stage the program and its tables once per CTA (persistent kernel: amortised over all tiles of this CTA)
     const double* src = reinterpret_cast<const double*>(gpg);
     double* dst = reinterpret_cast<double*>(&sm.pg);
     for (int i = tid; i < (int)(sizeof(QpProg<BK>) / sizeof(double)); i += TPB) dst[i] = src[i];
+    for (int i = tid; i < ax.n_dbl; i += TPB) tabd[i] = ax.tab[i];
+    if (a.x != nullptr) {
+      for (int i = tid; i < n * n; i += TPB) tabd[ax.n_dbl + i] = a.A_true[i];
+      for (int i = tid; i < n * m; i += TPB) tabd[ax.n_dbl + n * n + i] = a.B_true[i];
+    }
+    const int* gi = reinterpret_cast<const int*>(ax.tab + ax.n_dbl);
+    for (int i = tid; i < ax.n_int; i += TPB) tabi[i] = gi[i];
   }
+  __syncthreads();
+  for (int i = tid; i < BK::NC * NZ; i += TPB) (&sm.Aa[0][0])[i] = sp.alpha * (&sm.pg.A[0][0])[i];
   __syncthreads();
   const QpProg<BK>& pg = sm.pg;
   const int lane = tid & 31, wib = tid >> 5;
@@ -102,46 +333,78 @@ __global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel(const QpProg<BK
   const int g = lane % G;                 // lane within the scenario's group
   const int sl = lane / G;                // scenario within the warp's tile (solve-phase mapping)
   const int64_t LD = a.ld;
-  const int n = ax.n, m = ax.m, nv = ax.nv, nw = ax.nw;
   const bool explicit_qp = a.q_in != nullptr;
-  const int64_t ntiles = (a.S + SPW - 1) / SPW;
+  const int64_t ntiles = (a.S + BK::SPO - 1) / BK::SPO;
   const int64_t nwarps = (int64_t)gridDim.x * BK::WPB;
-  const double alpha = sp.alpha, inv_alpha = 1.0 / sp.alpha;
+  const double inv_alpha = 1.0 / sp.alpha;
+  const double* sCZ = tabd + ax.o_CZ;
+  for (int i = lane; i < TZ_NSTATS * BK::SPO; i += 32) (&wb.stacc[0][0])[i] = 0.0;
+  __syncwarp();
 
-  for (int64_t tile = (int64_t)blockIdx.x * BK::WPB + wib; tile < ntiles; tile += nwarps) {
-    const int64_t s = tile * SPW + sl;
+  int buf = 0;
+  const int64_t otile0 = (int64_t)blockIdx.x * BK::WPB + wib;
+  if (!explicit_qp && otile0 < ntiles) prefetch_inputs<BK>(wb.pre[0], a, n, otile0, lane);
+  for (int64_t otile = otile0; otile < ntiles; otile += nwarps, buf ^= 1) {
+    if (!explicit_qp) {        // inputs of the NEXT output tile stream in while this one is solved
+      if (otile + nwarps < ntiles) {
+        prefetch_inputs<BK>(wb.pre[buf ^ 1], a, n, otile + nwarps, lane);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncwarp();
+    }
+    const double (*pre)[BK::SPO] = wb.pre[buf];
+   #pragma unroll 1
+   for (int half = 0; half < BK::TPO; ++half) {
+    const int col = half * SPW + sl;        // column of this scenario in the warp's exchange buffers
+    const int64_t s = otile * BK::SPO + col;
     const bool live = s < a.S;
     double c0 = 0.0;
     bool param_ok = true, finite = true;
     LaneQp<BK> qp;
 
     if (!explicit_qp) {
-      // ---- parameters p = [xbar0; e0] (every lane of the group loads them: same sectors)
-      double w[NCOL];                        // w = [1; p; |p|; general atoms |Bt p + gam|]
+      // ---- parameters p = [xbar0 | e0] (every lane of the group loads them: same sectors)
+      double w[BK::NCOLP];                   // w = [1 | p | |p| | general atoms |Bt p + gam|]
       w[0] = 1.0;
+      w[BK::NCOLP - 1] = 0.0;
 #pragma unroll
-      for (int j = 0; j < NPAR; ++j) {
-        double val = 0.0;
-        if (live && j < 2 * n) val = (j < n) ? a.xbar0[(int64_t)j * LD + s] : a.e0[(int64_t)(j - n) * LD + s];
-        w[1 + j] = val;
-        w[1 + NPAR + j] = fabs(val);
-        finite = finite && (fabs(val) < 1e300);
-        if (g == 0 && j < 2 * n) wb.om[1 + nv + j][sl] = val;      // kept for the output phase
+      for (int j = 0; j < HP; ++j) {
+        double xv = 0.0, ev = 0.0;
+        if (live && j < n) { xv = pre[j][col]; ev = pre[n + j][col]; }
+        w[1 + j] = xv;
+        w[1 + HP + j] = ev;
+        w[1 + NPAR + j] = fabs(xv);
+        w[1 + NPAR + HP + j] = fabs(ev);
+        finite = finite && (fabs(xv) < 1e300) && (fabs(ev) < 1e300);
+        if (g == 0) { wb.om[BK::OM_P + j][col] = xv; wb.om[BK::OM_P + HP + j][col] = ev; }   // kept for the output phase
       }
 #pragma unroll
-      for (int i = 0; i < NAG; ++i) {
-        double acc = pg.gam[i];
+      for (int i = 0; i < NAG; ++i) w[1 + 2 * NPAR + i] = 0.0;
+      if (pg.nag > 0) {
 #pragma unroll
-        for (int j = 0; j < NPAR; ++j) acc = fma(pg.Bt[i][j], w[1 + j], acc);
-        w[1 + 2 * NPAR + i] = fabs(acc);
+        for (int i = 0; i < NAG; ++i) {
+          double acc = pg.gam[i];
+#pragma unroll
+          for (int j = 0; j < NPAR; ++j) acc = fma(pg.Bt[i][j], w[1 + j], acc);
+          w[1 + 2 * NPAR + i] = fabs(acc);
+        }
       }
       // ---- this lane's rows of the bounds: l = l0 + R w, u = u0 + R w (scaled), kinks
 #pragma unroll
       for (int k = 0; k < NCL; ++k) {
         const int i = k * G + g;
-        double r = 0.0;
+        // (16-byte shared loads, two accumulation chains per row)
+        const double2* Rr = reinterpret_cast<const double2*>(&pg.R[i][0]);
+        double r = 0.0, r1 = 0.0;
 #pragma unroll
-        for (int j = 0; j < NCOL; ++j) r = fma(pg.R[i][j], w[j], r);
+        for (int j = 0; j < BK::NCOLP / 2; ++j) {
+          const double2 c2 = Rr[j];
+          r = fma(c2.x, w[2 * j], r);
+          r1 = fma(c2.y, w[2 * j + 1], r1);
+        }
+        r += r1;
         if (k < N2) {
           qp.lo[k < N2 ? k : 0] = pg.l0[i] + r;
           qp.hi[k < N2 ? k : 0] = pg.u0[i] + r;
@@ -155,24 +418,32 @@ __global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel(const QpProg<BK
 #pragma unroll
       for (int j = 0; j < NZ; ++j) {
         double acc = pg.q0[j];
+        if (pg.has_qp) {
 #pragma unroll
-        for (int k = 0; k < NPAR; ++k) acc = fma(pg.Qp[j][k], w[1 + k], acc);
+          for (int k = 0; k < NPAR; ++k) acc = fma(pg.Qp[j][k], w[1 + k], acc);
+        }
         qp.q[j] = acc;
       }
-      // ---- parameter-only feasibility rows, split over the group
+      // ---- parameter-only feasibility rows, split over the group:  sum_j R_j w_j <= 1e-9 max(1, sum_j |R_j| |w_j|)
       int bad = 0;
 #pragma unroll
       for (int k = 0; k < NCHL; ++k) {
         const int i = k * G + g;
-        if (i < BK::NCHK) {
-          double r = 0.0, sc = 1.0;
+        if (i < pg.nchk) {
+          const double2* Rc = reinterpret_cast<const double2*>(&pg.Rchk[i % BK::NCHK][0]);
+          double r = 0.0, ra = 0.0;
 #pragma unroll
-          for (int j = 0; j < NCOL; ++j) {
-            const double t = pg.Rchk[i % BK::NCHK][j] * w[j];
-            r += t;
-            sc = fmax(sc, fabs(t));
+          for (int j2 = 0; j2 < BK::NCOLP / 2; ++j2) {
+            const double2 c2 = Rc[j2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int j = 2 * j2 + h;
+              const double c = h == 0 ? c2.x : c2.y;
+              r = fma(c, w[j], r);
+              ra = fma(fabs(c), (j >= 1 && j <= NPAR) ? w[j + NPAR] : w[j], ra);    // |w_j|: the |p| columns are already there
+            }
           }
-          bad |= (r > 1e-9 * sc) ? 1 : 0;
+          bad |= (r > 1e-9 * fmax(1.0, ra)) ? 1 : 0;
         }
       }
       param_ok = gor<G>(bad) == 0;
@@ -211,18 +482,16 @@ __global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel(const QpProg<BK
         }
       }
     }
-    // ---- this lane's rows of alpha*A and P (from shared memory; not kept live across the tile's other phases)
-#pragma unroll
-    for (int k = 0; k < NCL; ++k)
-#pragma unroll
-      for (int j = 0; j < NZ; ++j) qp.Aa[k][j] = alpha * pg.A[k * G + g][j];
+    qp.Aa.base = &sm.Aa[g][0];
     qp.P = pg.P;
     qp.wk = &pg.wabs[g];
+    qp.sinv = &pg.sing_inv[g];
+    qp.svar = &pg.sing_var[g];
 
-    // ---- ADMM (+ polish)
+    // ---- ADMM (+ certificate / polish)
     LaneState<BK> st;
     bool warm = false;
-    if (sp.warm && a.warm != nullptr && live) {
+    if (sp.warm == 1 && a.warm != nullptr && live) {
       // layout: [x (NZ) | y (NC, slot-indexed) | activity words (G) | valid flag] x LD
       warm = (a.warm[(int64_t)(NZ + BK::NC + G) * LD + s] == 1.0);
       if (warm) {
@@ -236,11 +505,46 @@ __global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel(const QpProg<BK
     }
     const bool solve_it = live && param_ok && finite;
     int iters = 0;
-    int status = admm_solve<BK>(qp, sp, solve_it, st, warm, &wb.ysave[0][lane], iters);
+    bool certified = false;
+    int status = TZ_STATUS_OK;
+    // ---- active-set hint (warm_start == 2): the optimal active set of the scenario's previous closed-loop step is
+    // tried first; when its KKT certificate holds the step is solved exactly without a single ADMM iteration
+    const bool use_hint = sp.warm == 2 && a.warm != nullptr;
+    bool hint_ok = false;
+    if (use_hint) {
+      unsigned long long hint = 0ull;
+      if (live) hint = (unsigned long long)__double_as_longlong(a.warm[(int64_t)g * LD + s]);
+      const bool valid = solve_it && gor<G>((hint & kCodeValid) ? 0 : 1) == 0;
+      if (__any_sync(0xffffffffu, valid)) {
+        double lam[NCL], xk[NZ], x0[NZ];
+#pragma unroll
+        for (int k = 0; k < NCL; ++k) lam[k] = 0.0;
+#pragma unroll
+        for (int j = 0; j < NZ; ++j) x0[j] = 0.0;
+        const unsigned long long code = hint & ~kCodeValid;
+        const bool ok = admm_certify<BK>(qp, inv_alpha, sp.polish > 0 ? sp.polish : 3, code, x0, lam, xk);
+        if (ok && valid) {
+#pragma unroll
+          for (int j = 0; j < NZ; ++j) st.x[j] = xk[j];
+#pragma unroll
+          for (int k = 0; k < NCL; ++k) st.w[k] = lam[k];
+          st.code = code;
+          hint_ok = true;
+        }
+      }
+    }
+    if (!__all_sync(0xffffffffu, hint_ok || !solve_it)) {
+      bool cert2 = false;
+      const int st2 = admm_solve<BK>(qp, sp, solve_it && !hint_ok, st, warm, &wb.ysave[0][lane], iters, cert2);
+      if (!hint_ok) { status = st2; certified = cert2; }
+    }
+    if (hint_ok) { certified = true; iters = 0; }
     if (live && !finite) status = TZ_STATUS_NONFINITE;
     else if (live && !param_ok) status = TZ_STATUS_INFEASIBLE;
     const bool good = live && (status == TZ_STATUS_OK || status == TZ_STATUS_MAXITER);
-    if (good && a.warm != nullptr) {
+    if (use_hint) {
+      if (live) a.warm[(int64_t)g * LD + s] = good ? __longlong_as_double((long long)(st.code | kCodeValid)) : 0.0;
+    } else if (good && a.warm != nullptr) {
       if (g == 0) {
 #pragma unroll
         for (int j = 0; j < NZ; ++j) a.warm[(int64_t)j * LD + s] = st.x[j];
@@ -250,7 +554,8 @@ __global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel(const QpProg<BK
       for (int k = 0; k < NCL; ++k) a.warm[(int64_t)(NZ + k * G + g) * LD + s] = st.w[k];
       a.warm[(int64_t)(NZ + BK::NC + g) * LD + s] = __longlong_as_double((long long)st.act);
     }
-    if (sp.polish) (void)admm_polish<BK>(qp, inv_alpha, st, good, sp.polish);
+    // residual exits are polished; certified exits already are an exact KKT point
+    if (sp.polish && __any_sync(0xffffffffu, good && !certified)) (void)admm_polish<BK>(qp, inv_alpha, st, good && !certified, sp.polish);
 
     if (explicit_qp) {
       if (live) {
@@ -299,118 +604,38 @@ __global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel(const QpProg<BK
     } else if (live && status == TZ_STATUS_INFEASIBLE) {
       cost = INFINITY;                      // cvxpy returns +inf for an infeasible Minimize (:374)
     }
-    // ---- hand om = [1; v; p; centre of Ze[1]], cost, status to the output phase (warp-private buffer)
+    // ---- hand om = [1 | v | p | centre of Ze[1]], cost, status to the output phase (warp-private buffer)
     if (g == 0) {
-      wb.om[0][sl] = 1.0;
+      wb.om[0][col] = 1.0;
 #pragma unroll
-      for (int j = 0; j < NZ; ++j)
-        if (j < nv) wb.om[1 + j][sl] = good ? pg.D[j] * st.x[j] : NAN;
-      wb.cost[sl] = cost;
-      wb.status[sl] = live ? status : -1;
-      wb.iters[sl] = iters;
+      for (int j = 0; j < NZ; ++j) wb.om[BK::OM_V + j][col] = (j < nv) ? (good ? pg.D[j] * st.x[j] : NAN) : 0.0;
+      wb.cost[col] = cost;
+      wb.status[col] = live ? status : -1;
+      wb.iters[col] = iters;
     }
     __syncwarp();
     for (int r = g; r < n; r += G) {        // centre of Ze[1]: rows split over the group
-      const double* row = ax.CZ + (size_t)r * nw;
+      const double* row = sCZ + r * NW;
       double acc = 0.0;
-      for (int j = 0; j < nw; ++j) acc = fma(__ldg(row + j), wb.om[j][sl], acc);
-      wb.om[nw + r][sl] = acc;
+#pragma unroll
+      for (int j = 0; j < NW; ++j) acc = fma(row[j], wb.om[j][col], acc);
+      wb.om[BK::OM_C + r][col] = acc;
     }
+   }     // solve tiles of this output tile
+    if (explicit_qp) continue;
     __syncwarp();
-
-    // =========== output phase: lane -> (scenario sc of the tile, slice); one store instruction covers
-    // G entries x SPW scenarios = G segments of SPW*8 contiguous bytes ===============================
-    {
-      const int sc = lane % SPW, slice = lane / SPW;
-      const int64_t so = tile * SPW + sc;
-      const int stt = wb.status[sc];
-      const bool olive = stt >= 0;
-      if (olive) {
-        // Ze[1].Z at the optimum (examples/2.pulley_sim.py:96: Zek.Z.value), dense n x (1+g1): zero-fill,
-        // then overwrite the few non-zero entries (both writes merge in L2 before reaching HBM)
-        if (a.ze1) {
-          double* base = a.ze1 + so;
-          const int nent = n * (1 + ax.g1);
-#pragma unroll 4
-          for (int en = slice; en < nent; en += G) __stcs(base + (int64_t)en * LD, 0.0);
-          __syncwarp();
-          for (int i = slice; i < ax.n_nz; i += G)
-            __stcs(base + (int64_t)__ldg(ax.nz_ent + i) * LD, __ldg(ax.nz_coef + i) * wb.om[__ldg(ax.nz_idx + i)][sc]);
-        }
-        // nominal trajectory xbar_0..xbar_N = XB om  (tzddpc/tzddpc.py:166-170)
-        if (a.xbar_traj) {
-          const int nrows = (ax.N + 1) * n;
-          for (int i = slice; i < nrows; i += G) {
-            const double* row = ax.XB + (size_t)i * nw;
-            double acc = 0.0;
-            for (int j = 0; j < nw; ++j) acc = fma(__ldg(row + j), wb.om[j][sc], acc);
-            a.xbar_traj[(int64_t)i * LD + so] = acc;
-          }
-        }
-        if (a.v)
-          for (int j = slice; j < nv; j += G) a.v[(int64_t)j * LD + so] = wb.om[1 + j][sc];
-        if (slice == 0) {
-          if (a.status) a.status[so] = stt;
-          if (a.iters) a.iters[so] = wb.iters[sc];
-          if (a.cost) a.cost[so] = wb.cost[sc];
-        }
-      }
-      // ---- closed-loop update (examples/2.pulley_sim.py:90-94): row i of the update by slice i mod G
-      if (a.x != nullptr) {
-        const bool ogood = olive && (stt == TZ_STATUS_OK || stt == TZ_STATUS_MAXITER);
-        double nrm2 = 0.0;
-        if (ogood) {
-          double us[kMaxM];
-#pragma unroll
-          for (int j = 0; j < kMaxM; ++j) {
-            double acc = 0.0;
-            if (j < m) {
-              acc = wb.om[1 + j][sc];                                   // v[0]
-              for (int i = 0; i < n; ++i) acc = fma(__ldg(ax.K + j * n + i), wb.om[1 + nv + n + i][sc], acc);
-              if (a.u_out && slice == 0) a.u_out[(int64_t)j * LD + so] = acc;
-            }
-            us[j] = acc;                                                // u = K e + v[0]
-          }
-          for (int i = slice; i < n; i += G) {
-            double acc = a.noise ? a.noise[(int64_t)i * LD + so] : 0.0;
-            for (int k = 0; k < n; ++k) acc = fma(__ldg(a.A_true + i * n + k), a.x[(int64_t)k * LD + so], acc);
-#pragma unroll
-            for (int k = 0; k < kMaxM; ++k)
-              if (k < m) acc = fma(__ldg(a.B_true + i * m + k), us[k], acc);
-            const double* row = ax.XB + (size_t)(n + i) * nw;           // xbar+ = xbar_traj[1]
-            double xb1 = 0.0;
-            for (int j = 0; j < nw; ++j) xb1 = fma(__ldg(row + j), wb.om[j][sc], xb1);
-            wb.om[nw + n + i][sc] = acc;                                // x+ staged: x is read by the other slices
-            a.xbar[(int64_t)i * LD + so] = xb1;
-            a.e[(int64_t)i * LD + so] = acc - xb1;                      // e+ = x+ - xbar+
-          }
-        }
-        __syncwarp();
-        if (ogood) {
-          for (int i = slice; i < n; i += G) a.x[(int64_t)i * LD + so] = wb.om[nw + n + i][sc];   // x+ = A x + B u + w
-          if (slice == 0)
-            for (int i = 0; i < n; ++i) nrm2 = fma(wb.om[nw + n + i][sc], wb.om[nw + n + i][sc], nrm2);
-        }
-        if (a.stats != nullptr) {
-          const bool cnt = slice == 0;      // one lane per scenario contributes
-          double stv[TZ_NSTATS];
-          stv[0] = (cnt && ogood) ? sqrt(nrm2) : 0.0;
-          stv[1] = (cnt && ogood) ? nrm2 : 0.0;
-          stv[2] = (cnt && ogood) ? wb.cost[sc] : 0.0;
-          stv[3] = (cnt && olive && stt == TZ_STATUS_INFEASIBLE) ? 1.0 : 0.0;
-          stv[4] = (cnt && olive && stt == TZ_STATUS_MAXITER) ? 1.0 : 0.0;
-          stv[5] = (cnt && olive) ? (double)wb.iters[sc] : 0.0;
-          stv[6] = (cnt && olive && stt == TZ_STATUS_NONFINITE) ? 1.0 : 0.0;
-          stv[7] = (cnt && olive) ? 1.0 : 0.0;
-#pragma unroll
-          for (int k = 0; k < TZ_NSTATS; ++k) {
-            const double v_ = warp_sum(stv[k]);
-            if (lane == 0 && v_ != 0.0) atomicAdd(a.stats + k, v_);
-          }
-        }
-      }
-    }
+    if (a.vec2) output_phase<BK, 2>(wb, pre, ax, a, tabd, tabi, otile, lane);
+    else output_phase<BK, 1>(wb, pre, ax, a, tabd, tabi, otile, lane);
     __syncwarp();     // wb is rewritten by the next tile
+  }
+  if (a.stats != nullptr && a.x != nullptr) {
+    __syncwarp();
+    if (lane < TZ_NSTATS) {
+      double v_ = 0.0;
+#pragma unroll
+      for (int c = 0; c < BK::SPO; ++c) v_ += wb.stacc[lane][c];
+      if (v_ != 0.0) atomicAdd(a.stats + lane, v_);
+    }
   }
 }
 
@@ -457,7 +682,7 @@ template <class BK>
 bool fits(const TzProgramDesc& d) {
   const RowClasses rc = classify(d, nullptr);
   return d.nz <= BK::NZ && rc.n2 <= BK::N2 * BK::G && rc.nu <= BK::NU * BK::G && rc.nl <= BK::NL * BK::G &&
-         d.npar <= BK::NPAR && general_atoms(d, nullptr) <= BK::NAG && d.nchk <= BK::NCHK;
+         2 * d.n <= BK::NPAR && general_atoms(d, nullptr) <= BK::NAG && d.nchk <= BK::NCHK;
 }
 
 template <class BK>
@@ -467,19 +692,28 @@ void pack(const TzProgramDesc& d, QpProg<BK>& g) {
   std::vector<int> cls(nc), amap(na);
   classify(d, &cls);
   const int nag = general_atoms(d, &amap);
+  // parameter k of the caller's p = [xbar0 (n); e0 (n)] -> slot of the padded p = [xbar0 (NPAR/2) | e0 (NPAR/2)]
+  const int nx = d.n;
+  auto pk = [&](int k) { return k < nx ? k : BK::NPAR / 2 + (k - nx); };
   // column j of the caller's [1 | p | alpha] layout -> column of the padded [1 | p | |p| | general] layout
   auto colmap = [&](int j) {
-    if (j <= npar) return j;
+    if (j == 0) return 0;
+    if (j <= npar) return 1 + pk(j - 1);
     const int am = amap[j - 1 - npar];
-    return am < 0 ? 1 + BK::NPAR + (-am - 1) : 1 + 2 * BK::NPAR + am;
+    return am < 0 ? 1 + BK::NPAR + pk(-am - 1) : 1 + 2 * BK::NPAR + am;
   };
   for (int a = 0; a < BK::NZ; ++a) g.D[a] = 1.0;
-  for (int i = 0; i < BK::NC; ++i) { g.l0[i] = -INFINITY; g.u0[i] = INFINITY; g.Einv[i] = 1.0; g.row_of_slot[i] = -1; }
+  for (int i = 0; i < BK::NC; ++i) {
+    g.l0[i] = -INFINITY; g.u0[i] = INFINITY; g.Einv[i] = 1.0; g.row_of_slot[i] = -1; g.sing_var[i] = -1; g.sing_inv[i] = 0.0;
+  }
   for (int a = 0; a < nz; ++a) {
     g.D[a] = d.D[a];
     g.q0[a] = d.c * d.D[a] * d.q0[a];
     for (int b = 0; b < nz; ++b) g.P[a][b] = d.c * d.D[a] * d.P[a * nz + b] * d.D[b];
-    for (int k = 0; k < npar; ++k) g.Qp[a][k] = d.c * d.D[a] * d.Qp[a * npar + k];
+    for (int k = 0; k < npar; ++k) {
+      g.Qp[a][pk(k)] = d.c * d.D[a] * d.Qp[a * npar + k];
+      if (d.Qp[a * npar + k] != 0.0) g.has_qp = 1;
+    }
   }
   int next[3] = {0, BK::N2 * BK::G, (BK::N2 + BK::NU) * BK::G};
   for (int i = 0; i < nc; ++i) {
@@ -487,7 +721,12 @@ void pack(const TzProgramDesc& d, QpProg<BK>& g) {
     const double E = d.E[i];
     g.row_of_slot[s] = i;
     g.Einv[s] = 1.0 / E;
-    for (int a = 0; a < nz; ++a) g.A[s][a] = E * d.A[i * nz + a] * d.D[a];
+    int nnz = 0, where = -1;
+    for (int a = 0; a < nz; ++a) {
+      g.A[s][a] = E * d.A[i * nz + a] * d.D[a];
+      if (g.A[s][a] != 0.0) { ++nnz; where = a; }
+    }
+    if (nnz == 1) { g.sing_var[s] = where; g.sing_inv[s] = 1.0 / g.A[s][where]; }     // a bound on one variable
     g.l0[s] = E * d.l0[i];
     g.u0[s] = E * d.u0[i];
     for (int j = 0; j < ncol; ++j) g.R[s][colmap(j)] += E * d.R[i * ncol + j];
@@ -499,13 +738,13 @@ void pack(const TzProgramDesc& d, QpProg<BK>& g) {
   for (int i = 0; i < na; ++i) {
     if (amap[i] < 0) continue;
     g.gam[amap[i]] = d.gam[i];
-    for (int k = 0; k < npar; ++k) g.Bt[amap[i]][k] = d.Bt[i * npar + k];
+    for (int k = 0; k < npar; ++k) g.Bt[amap[i]][pk(k)] = d.Bt[i * npar + k];
   }
   for (int i = 0; i < d.nchk; ++i)
     for (int j = 0; j < ncol; ++j) g.Rchk[i][colmap(j)] += d.Rchk[i * ncol + j];
   for (int j = 0; j < ncol; ++j) g.cc[colmap(j)] += d.cc[j];
   for (int a = 0; a < npar; ++a)
-    for (int b = 0; b < npar; ++b) g.CC2[a][b] = d.CC2[a * npar + b];
+    for (int b = 0; b < npar; ++b) g.CC2[pk(a)][pk(b)] = d.CC2[a * npar + b];
   g.cinv = 1.0 / d.c;
   g.nz = nz; g.nc = nc; g.npar = npar; g.nag = nag; g.nchk = d.nchk;
   g.has_cc2 = 0;
@@ -523,8 +762,12 @@ struct TzProgram {
   Aux aux{};
   int nz = 0, nc = 0, n = 0, m = 0, N = 0, nv = 0, g1 = 0, npar = 0;
   int NZ = 0, NC = 0, G = 0;
+  int NW = 0, OM_V = 0, OM_P = 0, OM_C = 0, HP = 0;     // om layout of the bucket (Bucket::OM_*)
+  size_t smem_tab = 0;                   // bytes of the run-time tables staged behind Smem<bucket>
   int num_sms = 148;
 };
+
+constexpr int kMaxTabBytes = 24 * 1024;
 
 template <class BK>
 static int create_bucket(const TzProgramDesc& d, TzProgram* p, int id) {
@@ -534,6 +777,7 @@ static int create_bucket(const TzProgramDesc& d, TzProgram* p, int id) {
   p->NZ = BK::NZ;
   p->NC = BK::NC;
   p->G = BK::G;
+  p->NW = BK::NW; p->OM_V = BK::OM_V; p->OM_P = BK::OM_P; p->OM_C = BK::OM_C; p->HP = BK::NPAR / 2;
   int dev = 0;
   TZ_CUDA(cudaGetDevice(&dev));
   TZ_CUDA(cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -564,53 +808,66 @@ extern "C" int tz_program_create(const TzProgramDesc* d, TzProgram** out) {
     return rc;
   }
   p->nz = d->nz; p->nc = d->nc; p->n = d->n; p->m = d->m; p->N = d->horizon; p->nv = d->nv; p->g1 = d->g1; p->npar = d->npar;
-  // ---- run-time sized tables: XB, centre map of Ze[1], K, and the Ze[1] entry lists
-  const int n = d->n, nw = 1 + d->nv + d->npar, ld1 = 1 + d->g1, nent = n * ld1;
-  std::vector<double> CZ((size_t)n * nw, 0.0), coef;
-  std::vector<int32_t> ent, idx, zero;
+  // ---- run-time sized tables: XB, centre map of Ze[1], K, and the non-zero entries of Ze[1].Z.  Columns / indices
+  // of the caller's w = [1; v (nv); xbar0 (n); e0 (n)] are remapped to the kernel's padded vector om (Bucket::OM_*).
+  const int n = d->n, nwc = 1 + d->nv + d->npar, ld1 = 1 + d->g1, nent = n * ld1, NW = p->NW;
+  auto omidx = [&](int j) {
+    if (j == 0) return 0;
+    if (j <= d->nv) return p->OM_V + (j - 1);
+    const int k = j - 1 - d->nv;
+    return k < n ? p->OM_P + k : p->OM_P + p->HP + (k - n);
+  };
+  const int nrows = (d->horizon + 1) * n;
+  std::vector<double> XB((size_t)nrows * NW, 0.0), CZ((size_t)n * NW, 0.0), coef;
+  std::vector<int32_t> ent, idx;
+  for (int i = 0; i < nrows; ++i)
+    for (int j = 0; j < nwc; ++j) XB[(size_t)i * NW + omidx(j)] = d->XB[(size_t)i * nwc + j];
   for (int e = 0; e < nent; ++e) {
     const int t0 = d->ze1_ptr[e], t1 = d->ze1_ptr[e + 1];
     for (int t = t0; t < t1; ++t)
-      if (d->ze1_idx[t] < 0 || d->ze1_idx[t] >= nw) { delete p; return fail(TZ_EINVAL, "ze1_idx[%d] out of range", t); }
+      if (d->ze1_idx[t] < 0 || d->ze1_idx[t] >= nwc) { delete p; return fail(TZ_EINVAL, "ze1_idx[%d] out of range", t); }
     const int r = e / ld1, j = e % ld1;
-    if (j == 0) {                        // centre column: its (possibly many) terms become om[nw + r]
-      for (int t = t0; t < t1; ++t) CZ[(size_t)r * nw + d->ze1_idx[t]] += d->ze1_val[t];
-      ent.push_back(e); idx.push_back(nw + r); coef.push_back(1.0);
-    } else if (t1 - t0 == 0) {
-      zero.push_back(e);
+    if (j == 0) {                        // centre column: its (possibly many) terms become om[OM_C + r]
+      for (int t = t0; t < t1; ++t) CZ[(size_t)r * NW + omidx(d->ze1_idx[t])] += d->ze1_val[t];
+      ent.push_back(e); idx.push_back(p->OM_C + r); coef.push_back(1.0);
     } else if (t1 - t0 == 1) {
-      ent.push_back(e); idx.push_back(d->ze1_idx[t0]); coef.push_back(d->ze1_val[t0]);
-    } else {
+      ent.push_back(e); idx.push_back(omidx(d->ze1_idx[t0])); coef.push_back(d->ze1_val[t0]);
+    } else if (t1 - t0 > 1) {
       delete p;
       return fail(TZ_EINVAL, "generator entry %d of Ze[1] has %d terms: only single-term generator entries are supported "
                   "(boxed M_K / M_Delta)", e, t1 - t0);
     }
   }
-  const size_t nXB = (size_t)(d->horizon + 1) * n * nw, nCZ = CZ.size(), nK = (size_t)d->m * n, nco = coef.size();
-  const size_t ndbl = nXB + nCZ + nK + nco, nint = ent.size() + idx.size() + zero.size();
+  const size_t nXB = XB.size(), nCZ = CZ.size(), nK = (size_t)d->m * n, nco = coef.size();
+  const size_t ndbl = nXB + nCZ + nK + nco, nint = ent.size() + idx.size();
+  const size_t smem_tab = (ndbl + (size_t)n * n + (size_t)n * d->m) * sizeof(double) + nint * sizeof(int32_t);
+  if (smem_tab > kMaxTabBytes) {
+    delete p;
+    return fail(TZ_ERANGE, "program tables need %zu bytes of shared memory (limit %d)", smem_tab, kMaxTabBytes);
+  }
   std::vector<unsigned char> host(ndbl * sizeof(double) + nint * sizeof(int32_t) + 16);
   double* hd = reinterpret_cast<double*>(host.data());
-  std::memcpy(hd, d->XB, nXB * sizeof(double));
+  std::memcpy(hd, XB.data(), nXB * sizeof(double));
   std::memcpy(hd + nXB, CZ.data(), nCZ * sizeof(double));
   std::memcpy(hd + nXB + nCZ, d->K, nK * sizeof(double));
   if (nco) std::memcpy(hd + nXB + nCZ + nK, coef.data(), nco * sizeof(double));
   int32_t* hi = reinterpret_cast<int32_t*>(hd + ndbl);
   if (!ent.empty()) std::memcpy(hi, ent.data(), ent.size() * sizeof(int32_t));
   if (!idx.empty()) std::memcpy(hi + ent.size(), idx.data(), idx.size() * sizeof(int32_t));
-  if (!zero.empty()) std::memcpy(hi + ent.size() + idx.size(), zero.data(), zero.size() * sizeof(int32_t));
   cudaError_t err = cudaMalloc(&p->aux_dev, host.size());
   if (err == cudaSuccess) err = cudaMemcpy(p->aux_dev, host.data(), host.size(), cudaMemcpyHostToDevice);
   if (err != cudaSuccess) {
     tz_program_destroy(p);
     return fail(TZ_ECUDA, "aux upload: %s", cudaGetErrorString(err));
   }
-  double* dd = reinterpret_cast<double*>(p->aux_dev);
-  int32_t* di = reinterpret_cast<int32_t*>(dd + ndbl);
   Aux& ax = p->aux;
-  ax.XB = dd; ax.CZ = dd + nXB; ax.K = dd + nXB + nCZ; ax.nz_coef = dd + nXB + nCZ + nK;
-  ax.nz_ent = di; ax.nz_idx = di + ent.size(); ax.zero_ent = di + ent.size() + idx.size();
-  ax.n_nz = (int)ent.size(); ax.n_zero = (int)zero.size();
-  ax.n = n; ax.m = d->m; ax.N = d->horizon; ax.nv = d->nv; ax.g1 = d->g1; ax.nw = nw;
+  ax.tab = reinterpret_cast<const double*>(p->aux_dev);
+  ax.n_dbl = (int)ndbl; ax.n_int = (int)nint;
+  ax.o_XB = 0; ax.o_CZ = (int)nXB; ax.o_K = (int)(nXB + nCZ); ax.o_coef = (int)(nXB + nCZ + nK);
+  ax.o_ent = 0; ax.o_idx = (int)ent.size();
+  ax.n_nz = (int)ent.size();
+  ax.n = n; ax.m = d->m; ax.N = d->horizon; ax.nv = d->nv; ax.g1 = d->g1;
+  p->smem_tab = (smem_tab + 15) & ~(size_t)15;
   *out = p;
   return TZ_OK;
 }
@@ -637,6 +894,7 @@ extern "C" void tz_solver_opts_default(TzSolverOpts* o) {
   if (!o) return;
   o->rho = 0.1; o->rho_active = 100.0; o->rho_inactive = 0.1; o->sigma = 1e-6; o->alpha = 1.6;
   o->eps_abs = 1e-6; o->eps_rel = 1e-6; o->max_iter = 4000; o->check_every = 8; o->polish = 3; o->warm_start = 0;
+  o->cert_first = 3;
 }
 
 static SolverParams to_params(const TzSolverOpts* o) {
@@ -644,19 +902,20 @@ static SolverParams to_params(const TzSolverOpts* o) {
   tz_solver_opts_default(&d);
   if (o) d = *o;
   return SolverParams{d.rho, d.rho_active, d.rho_inactive, d.sigma, d.alpha, d.eps_abs, d.eps_rel,
-                      d.max_iter, d.check_every, d.polish, d.warm_start};
+                      d.max_iter, d.check_every, d.polish, d.warm_start, d.cert_first};
 }
 
 template <class BK>
 static int launch_bucket(const TzProgram* p, const SolverParams& sp, const StepArgs& a, cudaStream_t st) {
-  const size_t smem = sizeof(Smem<BK>);
+  const size_t smem = sizeof(Smem<BK>) + p->smem_tab;
   static bool configured = false;     // benign race: the attribute is idempotent
   if (!configured) {
-    TZ_CUDA(cudaFuncSetAttribute(step_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TZ_CUDA(cudaFuncSetAttribute(step_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(sizeof(Smem<BK>) + kMaxTabBytes)));
     configured = true;
   }
   // persistent grid: one wave of CTAs (MINB per SM); every warp loops over tiles of SPW scenarios
-  const int64_t ntiles = (a.S + BK::SPW - 1) / BK::SPW;
+  const int64_t ntiles = (a.S + BK::SPO - 1) / BK::SPO;
   const int64_t need = (ntiles + BK::WPB - 1) / BK::WPB;
   const int64_t wave = (int64_t)p->num_sms * BK::MINB;
   const unsigned grid = (unsigned)(need < wave ? need : wave);
@@ -665,10 +924,18 @@ static int launch_bucket(const TzProgram* p, const SolverParams& sp, const StepA
   return TZ_OK;
 }
 
-static int launch(const TzProgram* p, const TzSolverOpts* o, const StepArgs& a, void* stream) {
+static int launch(const TzProgram* p, const TzSolverOpts* o, const StepArgs& a_in, void* stream) {
   TZ_REQUIRE(p != nullptr, "null program");
-  TZ_REQUIRE(a.S >= 0, "negative batch");
-  if (a.S == 0) return TZ_OK;
+  TZ_REQUIRE(a_in.S >= 0, "negative batch");
+  if (a_in.S == 0) return TZ_OK;
+  StepArgs a = a_in;
+  {  // two scenarios per lane in the output phase need 16-byte aligned rows: S, ld even and aligned base pointers
+    const void* ptrs[] = {a.x, a.xbar, a.e, a.noise, a.x_restart, a.cost, a.v, a.xbar_traj, a.ze1, a.u_out};
+    bool ok = (a.S % 2 == 0) && (a.ld % 2 == 0);
+    for (const void* q : ptrs) ok = ok && ((reinterpret_cast<uintptr_t>(q) & 15u) == 0);
+    ok = ok && ((reinterpret_cast<uintptr_t>(a.status) & 7u) == 0) && ((reinterpret_cast<uintptr_t>(a.iters) & 7u) == 0);
+    a.vec2 = ok ? 1 : 0;
+  }
   const SolverParams sp = to_params(o);
   TZ_REQUIRE(sp.max_iter >= 1 && sp.rho > 0 && sp.rho_act > 0 && sp.rho_inact > 0 && sp.alpha > 0 && sp.alpha < 2,
              "bad solver options");
@@ -694,12 +961,13 @@ extern "C" int tz_solve(const TzProgram* prog, const TzSolverOpts* opts, int64_t
 }
 
 extern "C" int tz_closed_loop_step(const TzProgram* prog, const TzSolverOpts* opts, int64_t S, double* x, double* xbar,
-                                   double* e, const double* noise, const double* A_true, const double* B_true,
+                                   double* e, const double* noise, const double* x_restart, const double* A_true,
+                                   const double* B_true,
                                    double* cost, double* v, double* xbar_traj, double* ze1, double* u_out,
                                    int32_t* status, int32_t* iters, double* warm, double* stats, void* stream) {
   TZ_REQUIRE(S == 0 || (x && xbar && e && A_true && B_true && status), "x, xbar, e, A_true, B_true, status are required");
   StepArgs a{};
-  a.S = S; a.ld = S; a.xbar0 = xbar; a.e0 = e; a.x = x; a.xbar = xbar; a.e = e; a.noise = noise; a.A_true = A_true; a.B_true = B_true;
+  a.S = S; a.ld = S; a.xbar0 = xbar; a.e0 = e; a.x = x; a.xbar = xbar; a.e = e; a.noise = noise; a.x_restart = x_restart; a.A_true = A_true; a.B_true = B_true;
   a.cost = cost; a.v = v; a.xbar_traj = xbar_traj; a.ze1 = ze1; a.u_out = u_out; a.status = status; a.iters = iters;
   a.warm = warm; a.stats = stats;
   return launch(prog, opts, a, stream);
@@ -756,7 +1024,8 @@ extern "C" int tz_closed_loop_step_host(const TzProgram* prog, const TzSolverOpt
   cudaError_t err = cudaMemcpyAsync(dA, A_true_host, n * n * sizeof(double), cudaMemcpyHostToDevice, streams[0]);
   if (err == cudaSuccess) err = cudaMemcpyAsync(dB, B_true_host, n * m * sizeof(double), cudaMemcpyHostToDevice, streams[0]);
   if (err == cudaSuccess) err = cudaStreamSynchronize(streams[0]);
-  const int64_t per = (S + nchunks - 1) / nchunks;
+  int64_t per = (S + nchunks - 1) / nchunks;
+  per = (per + 15) & ~(int64_t)15;          // whole tiles, 16-byte aligned chunk starts
   // The device arrays are SoA with leading dimension S; a chunk [s0, s1) of a d x S array is d strided
   // segments, moved with one 2-D copy per array.
   auto h2d = [&](double* dev, const double* host, int64_t rows, int64_t s0, int64_t cnt, cudaStream_t st) {

@@ -28,17 +28,20 @@ class SolverOptions:
     max_iter: int = 4000
     check_every: int = 8
     polish: int = 3          # iterations of the active-set polish, 0 = off
-    warm_start: bool = False
+    warm_start: int = 0      # 0 cold, 1 reuse (x, y) of the previous call, 2 active-set hint of the previous call
+    cert_first: int = 3      # first ADMM iteration at which the active-set KKT certificate is tried, 0 = off
 
     def pack(self) -> List[float]:
         return [self.rho, self.rho_active, self.rho_inactive, self.sigma, self.alpha, self.eps_abs, self.eps_rel,
-                float(self.max_iter), float(self.check_every), float(int(self.polish)), float(self.warm_start)]
+                float(self.max_iter), float(self.check_every), float(int(self.polish)), float(self.warm_start),
+                float(int(self.cert_first))]
 
 
 def _opts(o: List[float]) -> _abi.TzSolverOpts:
     s = _abi.TzSolverOpts()
     s.rho, s.rho_active, s.rho_inactive, s.sigma, s.alpha, s.eps_abs, s.eps_rel = o[:7]
     s.max_iter, s.check_every, s.polish, s.warm_start = int(o[7]), int(o[8]), int(o[9]), int(o[10])
+    s.cert_first = int(o[11]) if len(o) > 11 else 3
     return s
 
 
@@ -80,8 +83,8 @@ def solve(prog: int, dims: List[int], xbar0: Tensor, e0: Tensor, warm: Optional[
 @torch.library.custom_op("tzddpc::closed_loop_step",
                          mutates_args=("x", "xbar", "e", "cost", "v", "traj", "ze1", "u", "status", "iters", "warm", "stats"),
                          device_types="cuda")
-def closed_loop_step(prog: int, x: Tensor, xbar: Tensor, e: Tensor, noise: Tensor, A_true: Tensor, B_true: Tensor,
-                     status: Tensor, cost: Optional[Tensor], v: Optional[Tensor], traj: Optional[Tensor],
+def closed_loop_step(prog: int, x: Tensor, xbar: Tensor, e: Tensor, noise: Tensor, x_restart: Optional[Tensor],
+                     A_true: Tensor, B_true: Tensor, status: Tensor, cost: Optional[Tensor], v: Optional[Tensor], traj: Optional[Tensor],
                      ze1: Optional[Tensor], u: Optional[Tensor], iters: Optional[Tensor], warm: Optional[Tensor],
                      stats: Optional[Tensor], opts: List[float]) -> None:
     # (no default values: torch strips trailing defaulted arguments, which breaks mutated Optional[Tensor] args)
@@ -91,7 +94,7 @@ def closed_loop_step(prog: int, x: Tensor, xbar: Tensor, e: Tensor, noise: Tenso
     o = _opts(opts)
     with torch.cuda.device(x.device):
         rc = _abi.lib().tz_closed_loop_step(C.c_void_p(prog), C.byref(o), S, _ptr(x), _ptr(xbar), _ptr(e), _ptr(noise),
-                                            _ptr(A_true), _ptr(B_true), _ptr(cost), _ptr(v), _ptr(traj), _ptr(ze1),
+                                            _ptr(x_restart), _ptr(A_true), _ptr(B_true), _ptr(cost), _ptr(v), _ptr(traj), _ptr(ze1),
                                             _ptr(u), _ptr(status), _ptr(iters), _ptr(warm), _ptr(stats), _stream(x))
     _abi.check(rc, "tz_closed_loop_step")
 

@@ -274,9 +274,11 @@ class TZDDPC(object):
 
     # ---- batched closed loop (examples/2.pulley_sim.py:62-103, one scenario per column) --------
     def simulate(self, A_true: np.ndarray, B_true: np.ndarray, x0: np.ndarray, noise, keep_tubes: bool = False,
-                 options: Optional[SolverOptions] = None):
+                 options: Optional[SolverOptions] = None, restart: bool = False):
         """Run the closed loop for S scenarios in lock step.
         x0: (S, n); noise: (steps, S, n) array or CUDA tensor (steps, n, S).
+        restart: an infeasible scenario (the reference raises and the run ends, tzddpc/tzddpc.py:374-375) starts a
+        new run from its x0 instead of keeping its state.
         Returns dict with x (steps+1, S, n), xbar, e, u, v0, cost (steps, S), status (steps, S), stats (steps, 8)."""
         assert self._program is not None, "call build_problem first"
         n, m = self.dim_x, self.dim_u
@@ -305,9 +307,10 @@ class TZDDPC(object):
         tubes = torch.empty((steps, self._dims[3], S), **f64) if keep_tubes else None
         warm = torch.zeros((self._program.warm_rows, S), **f64) if o.warm_start else None
         xs[0], xbars[0], es[0] = x, xbar, e
+        xr = x.clone() if restart else None
         h = self._program.handle.value
         for t in range(steps):
-            ops.closed_loop_step(h, x, xbar, e, w[t].contiguous(), At, Bt, stat[t], costs[t], vs[t], None,
+            ops.closed_loop_step(h, x, xbar, e, w[t].contiguous(), xr, At, Bt, stat[t], costs[t], vs[t], None,
                                  tubes[t] if keep_tubes else None, us[t], iters[t], warm, stats[t], o.pack())
             xs[t + 1], xbars[t + 1], es[t + 1] = x, xbar, e
         out = {"x": xs.permute(0, 2, 1).cpu().numpy(), "xbar": xbars.permute(0, 2, 1).cpu().numpy(),
