@@ -151,42 +151,56 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md): NVML polled from a thread every ~2 ms
+    (the timed region of the default run lasts tens of milliseconds, too short for `nvidia-smi -lms`)."""
 
-    def __init__(self, uuid):
-        self.rows, self.proc = [], None
+    def __init__(self, device_index):
+        self.rows, self.ok, self._stop = [], False, False
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", uuid], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = device_index
+            if vis:
+                ent = vis.split(",")[device_index].strip()
+                if ent.startswith("GPU-"):
+                    self.h = pynvml.nvmlDeviceGetHandleByUUID(ent)
+                    idx = None
+                else:
+                    idx = int(ent)
+            if idx is not None:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+            self.th = threading.Thread(target=self._poll, daemon=True)
             self.th.start()
-        except Exception:
-            self.proc = None
+        except Exception as e:      # noqa: BLE001
+            self.err = repr(e)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+    def _poll(self):
+        nv = self.nv
+        while not self._stop:
+            try:
+                self.rows.append((time.perf_counter(), nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
+                                  nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)))
+            except Exception:       # noqa: BLE001
+                pass
+            time.sleep(0.002)
 
     def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except Exception:
-                continue
-            for name, val in zip(names, r[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "?")]}
+        self._stop = True
+        self.th.join(timeout=1.0)
+        nv = self.nv
+        rows = [r for r in self.rows if t0 <= r[0] <= t1] or self.rows[-3:]
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        reasons = sorted(k for k, bit in names.items() if any(r[2] & bit for r in rows))
+        sm = [r[1] for r in rows]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(self.max_sm), "reasons": reasons,
+                "samples": len(sm)}
 
 
 def run_gpu(args):
@@ -220,7 +234,8 @@ def run_gpu(args):
     prog = ctl._program
     g1 = prog.compiled.g1
     nent, nt, nv = n * (1 + g1), (N + 1) * n, prog.compiled.nv
-    opts = tz.SolverOptions(warm_start=int(args.warm_start), check_every=args.check_every, eps_abs=args.eps, eps_rel=args.eps)
+    opts = tz.SolverOptions(warm_start=int(args.warm_start), check_every=args.check_every, eps_abs=args.eps, eps_rel=args.eps,
+                            polish=args.polish)
     po = opts.pack()
 
     f64 = dict(dtype=torch.float64, device=dev)
@@ -264,7 +279,7 @@ def run_gpu(args):
     for t in range(W_steps):
         step(t)
     barrier()
-    sampler = ClockSampler("GPU-" + str(torch.cuda.get_device_properties(dev).uuid)) if rank == 0 else None
+    sampler = ClockSampler(local) if rank == 0 else None
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(K_steps + 1)]
     t_wall0 = time.perf_counter()
     ev[0].record()
@@ -370,6 +385,7 @@ def main():
     ap.add_argument("--warm-start", type=int, default=2, help="0 cold, 1 previous (x, y), 2 active-set hint (default)")
     ap.add_argument("--check-every", type=int, default=8)
     ap.add_argument("--eps", type=float, default=1e-6)
+    ap.add_argument("--polish", type=int, default=3, help="augmented-Lagrangian iterations of the certificate / polish")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--e2e-chunks", type=int, default=4)
     ap.add_argument("--cpu-steps", type=int, default=1500)

@@ -192,6 +192,22 @@ int tz_reach_step(int64_t S, int32_t n, int32_t p, int32_t N, int32_t g, int32_t
 int tz_girard_reduce(int64_t S, int32_t n, int32_t g, double order, int32_t metric,
                      const double* Z, int32_t gout_cap, double* Zout, int32_t* gout, void* stream);
 
+/* Tube rollout with in-loop order reduction (BASELINE.json configs[4]; tzddpc/tzddpc.py:175-186,205 evaluated
+ * numerically + Zonotope.reduce of examples/1.double_integrator_sim.py:170 after every step):
+ *   Z_{k+1} = reduce( M_K (x) Z_k  (+)  M_Delta (x) <[xbar_k; v_k], 0>  (+)  W ,  order ),   k = 0 .. steps-1
+ * one CTA per scenario, the zonotope stays in shared memory for all steps.
+ *   CK: n x n centre of M_K, GK: NK x n x n, GD: ND x n x (n+m) generators of M_Delta (zero centre); shared by all
+ *   scenarios, or per scenario (S x ...) when per_scenario_model != 0.
+ *   Z0: S x n x (1+g0);  XU: S x steps x (n+m) the nominal [xbar_k; v_k];  W: n x (1+gW) or NULL.
+ *   Zfinal: S x n x (1+gcap), gfinal[s] generators of the final zonotope (negative: gcap too small, truncated);
+ *   hull_lo, hull_hi: S x steps x n interval hull of Z_{k+1} (tzddpc/tzddpc.py:191-197).
+ * gcap >= max(g0, floor(n (order-1)) + n).  Column order of the pre-reduction block as pyzonotope's product:
+ *   [C_K G | G^K_1 c, G^K_1 G | ... | G^D_1 z .. | G_W]; reduction as tz_girard_reduce. */
+int tz_tube_rollout(int64_t S, int32_t n, int32_t m, int32_t NK, int32_t ND, int32_t gW, int32_t g0, int32_t steps,
+                    double order, int32_t metric, const double* CK, const double* GK, const double* GD,
+                    int32_t per_scenario_model, const double* Z0, const double* XU, const double* W, int32_t gcap,
+                    double* Zfinal, int32_t* gfinal, double* hull_lo, double* hull_hi, void* stream);
+
 /* Data-driven model  M_Sigma = (X1 - M_w) pinv([X0; U0])  (tzddpc/tzddpc.py:81-83) followed by
  * tzddpc/tzddpc.py:119-128 (MdataK = Mdata [I;K], Mdelta, order-1 reduction), batched over S datasets:
  *   X: S x T x n, U: S x T x m (as Data.x / Data.u), WZ: n x (1+gW) shared, K: S x m x n or NULL

@@ -40,8 +40,8 @@ _lib = None
 # every symbol include/tzddpc.h declares (tests/test_abi.py checks the library exports all of them)
 EXPORTS = ["tz_version", "tz_last_error", "tz_device_cc", "tz_program_create", "tz_program_destroy", "tz_program_bucket", "tz_program_warm_rows",
            "tz_solver_opts_default", "tz_solve", "tz_closed_loop_step", "tz_closed_loop_step_host_scratch_bytes",
-           "tz_closed_loop_step_host", "tz_interval_hull", "tz_reach_step", "tz_girard_reduce", "tz_identify",
-           "tz_qp_solve"]
+           "tz_closed_loop_step_host", "tz_interval_hull", "tz_reach_step", "tz_girard_reduce", "tz_tube_rollout",
+           "tz_identify", "tz_qp_solve"]
 
 
 def lib() -> C.CDLL:
@@ -82,6 +82,8 @@ def lib() -> C.CDLL:
     L.tz_reach_step.argtypes = [i64, i32, i32, i32, i32, i32, vp, vp, i32, vp, vp, vp, vp]
     L.tz_girard_reduce.restype = C.c_int
     L.tz_girard_reduce.argtypes = [i64, i32, i32, dbl, i32, vp, i32, vp, vp, vp]
+    L.tz_tube_rollout.restype = C.c_int
+    L.tz_tube_rollout.argtypes = [i64] + [i32] * 7 + [dbl, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp]
     L.tz_identify.restype = C.c_int
     L.tz_identify.argtypes = [i64, i32, i32, i32, i32] + [vp] * 10
     L.tz_qp_solve.restype = C.c_int

@@ -298,13 +298,9 @@ __device__ __forceinline__ bool admm_certify(const LaneQp<BK>& qp, double inv_al
                                              const double (&x0)[BK::NZ], double (&lam)[BK::NCL], double (&xk)[BK::NZ]) {
   constexpr int NZ = BK::NZ, NCL = BK::NCL, N2 = BK::N2, G = BK::G;
   const double delta = 1e-9, mu = 1e6, alpha = 1.0 / inv_alpha;
-  double L[NZ][NZ], qt[NZ];
+  double L[NZ][NZ], qt[NZ], tgt[NCL];
+  uint32_t am = 0u;                      // active rows (on a bound / on the kink / equality)
   auto cof = [&](int k) { return (unsigned)(code >> (3 * k)) & 7u; };
-  auto target = [&](int k, unsigned c) {          // alpha * (the bound the row sits on)
-    double b = (c == 2u) ? qp.upper(k) : qp.lower(k);
-    if (k < N2 && c == 3u) b = qp.kink[k < N2 ? k : 0];
-    return b * alpha;
-  };
 #pragma unroll
   for (int a = 0; a < NZ; ++a) {
     qt[a] = 0.0;
@@ -312,16 +308,23 @@ __device__ __forceinline__ bool admm_certify(const LaneQp<BK>& qp, double inv_al
 #pragma unroll
     for (int b = 0; b <= a; ++b) L[a][b] = 0.0;
   }
+  // decode the code once: active mask, alpha * (the bound the row sits on), subgradients of the |.| rows off their kink
 #pragma unroll
   for (int k = 0; k < NCL; ++k) {
     const unsigned c = cof(k);
     const bool ia = (c >= 1u && c <= 3u) || c == 6u;
-    if (k < N2 && (c == 4u || c == 5u)) {           // away from the kink the |.| cost is linear: its multiplier is the subgradient
-      const double wgt = qp.wk[(k < N2 ? k : 0) * G];
-      const double sg = (c == 4u ? wgt : -wgt) * inv_alpha;
+    double b = (c == 2u) ? qp.upper(k) : qp.lower(k);
+    if (k < N2) {
+      if (c == 3u) b = qp.kink[k < N2 ? k : 0];
+      if (c == 4u || c == 5u) {
+        const double wgt = qp.wk[(k < N2 ? k : 0) * G];
+        const double sg = (c == 4u ? wgt : -wgt) * inv_alpha;
 #pragma unroll
-      for (int a = 0; a < NZ; ++a) qt[a] = fma(sg, qp.Aa[k][a], qt[a]);
+        for (int a = 0; a < NZ; ++a) qt[a] = fma(sg, qp.Aa[k][a], qt[a]);
+      }
     }
+    tgt[k] = ia ? b * alpha : 0.0;
+    am |= ia ? (1u << k) : 0u;
     const double m_ = ia ? mu : 0.0;
     lam[k] = ia ? lam[k] : 0.0;
 #pragma unroll
@@ -345,9 +348,7 @@ __device__ __forceinline__ bool admm_certify(const LaneQp<BK>& qp, double inv_al
     for (int a = 0; a < NZ; ++a) rhs[a] = 0.0;
 #pragma unroll
     for (int k = 0; k < NCL; ++k) {
-      const unsigned c = cof(k);
-      const bool ia = (c >= 1u && c <= 3u) || c == 6u;
-      const double t = ia ? fma(mu, target(k, c), -lam[k]) : 0.0;
+      const double t = ((am >> k) & 1u) ? fma(mu, tgt[k], -lam[k]) : 0.0;
 #pragma unroll
       for (int a = 0; a < NZ; ++a) rhs[a] = fma(qp.Aa[k][a], t, rhs[a]);
     }
@@ -358,12 +359,10 @@ __device__ __forceinline__ bool admm_certify(const LaneQp<BK>& qp, double inv_al
     for (int a = 0; a < NZ; ++a) xk[a] = rhs[a];
 #pragma unroll
     for (int k = 0; k < NCL; ++k) {
-      const unsigned c = cof(k);
-      const bool ia = (c >= 1u && c <= 3u) || c == 6u;
       double ax = 0.0;
 #pragma unroll
       for (int a = 0; a < NZ; ++a) ax = fma(qp.Aa[k][a], xk[a], ax);
-      lam[k] = ia ? fma(mu, ax - target(k, c), lam[k]) : lam[k];
+      lam[k] = ((am >> k) & 1u) ? fma(mu, ax - tgt[k], lam[k]) : lam[k];
     }
   }
   // ---- KKT certificate
@@ -380,15 +379,15 @@ __device__ __forceinline__ bool admm_certify(const LaneQp<BK>& qp, double inv_al
   }
   scale = gmax<G>(scale);
   lscale = gmax<G>(lscale);
-  const double ptol = 1e-9 * scale, ltol = 1e-9 * lscale;
+  const double ptol = 1e-9 * scale, ltol = 1e-9 * lscale, etol = 1e-8 * scale;
   int bad = 0;
 #pragma unroll
   for (int k = 0; k < NCL; ++k) {
     const double ax = axs[k];
     const unsigned c = cof(k);
     bad |= (qp.lower(k) - ax > ptol) || (ax - qp.upper(k) > ptol);                 // primal feasibility
-    if ((c >= 1u && c <= 3u) || c == 6u) {
-      bad |= fabs(ax - target(k, c) * inv_alpha) > 1e-8 * scale;                  // active rows on their bound
+    if ((am >> k) & 1u) {
+      bad |= fabs(ax - tgt[k] * inv_alpha) > etol;                                // active rows on their bound
       bad |= (c == 2u) && (lam[k] < -ltol);                                       // multiplier signs
       bad |= (c == 1u) && (lam[k] > ltol);
       if (k < N2) bad |= (c == 3u) && (fabs(lam[k]) * alpha > qp.wk[(k < N2 ? k : 0) * G] * (1.0 + 1e-9));

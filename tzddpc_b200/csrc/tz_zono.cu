@@ -115,31 +115,19 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_tot, int& t
   return base + inc - v;
 }
 
-__global__ void __launch_bounds__(kGirardThreads) girard_kernel(int n, int g, double order, int metric,
-                                                                const double* __restrict__ Z, int gout_cap,
-                                                                double* __restrict__ Zout, int32_t* __restrict__ gout) {
-  extern __shared__ unsigned char smraw[];
-  double* G = reinterpret_cast<double*>(smraw);                              // n x g
-  unsigned long long* key = reinterpret_cast<unsigned long long*>(G + (size_t)n * g);   // g
-  unsigned char* flag = reinterpret_cast<unsigned char*>(key + g);           // g: 0 zero, 1 keep, 2 reduce
+// Girard reduction of the generator block G (n x g, shared memory, row-major) of one zonotope by one CTA.
+// Writes the reduced generators to out[r * ldo + j] (global or shared), zero-pads up to gout_cap, returns the
+// number of generators written (negative: gout_cap too small).  key / flag: g-element scratch in shared memory.
+__device__ int girard_block(int n, int g, double order, int metric, const double* __restrict__ G,
+                            unsigned long long* __restrict__ key, unsigned char* __restrict__ flag, double* __restrict__ out,
+                            int64_t ldo, int gout_cap) {
   __shared__ int hist[256];
   __shared__ int warp_tot[kGirardThreads / 32];
   __shared__ unsigned long long sel_prefix;
   __shared__ int sel_remaining;
   __shared__ double dbox[kGirardMaxDim];
   __shared__ double red[kGirardThreads / 32];
-
-  const int64_t s = blockIdx.x;
   const int tid = threadIdx.x;
-  const int ldz = 1 + g, ldo = 1 + gout_cap;
-  const double* Zs = Z + s * (int64_t)n * ldz;
-  double* Os = Zout + s * (int64_t)n * ldo;
-
-  for (int i = tid; i < n * g; i += kGirardThreads) {
-    const int r = i / g, j = i - r * g;
-    G[i] = __ldcs(Zs + (int64_t)r * ldz + 1 + j);
-  }
-  __syncthreads();
   // metric (rows accumulated r = 0..n-1, exactly as oracle/zono.py:_girard_metric) and zero filter
   int nnz_local = 0;
   for (int j = tid; j < g; j += kGirardThreads) {
@@ -219,8 +207,7 @@ __global__ void __launch_bounds__(kGirardThreads) girard_kernel(int n, int g, do
       __syncthreads();
     }
   }
-  // ---- output: centre, kept columns in original order, then diag(d), zero padding
-  for (int r = tid; r < n; r += kGirardThreads) Os[(int64_t)r * ldo] = Zs[(int64_t)r * ldz];
+  // ---- output: kept columns in original order, then diag(d), zero padding
   int out_base = 0;
   for (int j0 = 0; j0 < g; j0 += kGirardThreads) {
     const int j = j0 + tid;
@@ -228,14 +215,14 @@ __global__ void __launch_bounds__(kGirardThreads) girard_kernel(int n, int g, do
     int tot;
     const int pos = out_base + block_exclusive_scan(keep, warp_tot, tot);
     if (keep && pos < gout_cap)
-      for (int r = 0; r < n; ++r) Os[(int64_t)r * ldo + 1 + pos] = G[(size_t)r * g + j];
+      for (int r = 0; r < n; ++r) out[(int64_t)r * ldo + pos] = G[(size_t)r * g + j];
     out_base += tot;
   }
   int written = out_base;
   if (do_reduce) {
     for (int i = tid; i < n * n; i += kGirardThreads) {
       const int r = i / n, c = i - r * n;
-      if (written + c < gout_cap) Os[(int64_t)r * ldo + 1 + written + c] = (r == c) ? dbox[r] : 0.0;
+      if (written + c < gout_cap) out[(int64_t)r * ldo + written + c] = (r == c) ? dbox[r] : 0.0;
     }
     written += n;
   }
@@ -243,9 +230,133 @@ __global__ void __launch_bounds__(kGirardThreads) girard_kernel(int n, int g, do
   const int wpos = written < 0 ? gout_cap : written;
   for (int i = tid; i < n * (gout_cap - wpos); i += kGirardThreads) {
     const int r = i / (gout_cap - wpos), c = i - r * (gout_cap - wpos);
-    Os[(int64_t)r * ldo + 1 + wpos + c] = 0.0;
+    out[(int64_t)r * ldo + wpos + c] = 0.0;
   }
+  __syncthreads();
+  return written;
+}
+
+__global__ void __launch_bounds__(kGirardThreads) girard_kernel(int n, int g, double order, int metric,
+                                                                const double* __restrict__ Z, int gout_cap,
+                                                                double* __restrict__ Zout, int32_t* __restrict__ gout) {
+  extern __shared__ unsigned char smraw[];
+  double* G = reinterpret_cast<double*>(smraw);                              // n x g
+  unsigned long long* key = reinterpret_cast<unsigned long long*>(G + (size_t)n * g);   // g
+  unsigned char* flag = reinterpret_cast<unsigned char*>(key + g);           // g: 0 zero, 1 keep, 2 reduce
+  const int64_t s = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int ldz = 1 + g, ldo = 1 + gout_cap;
+  const double* Zs = Z + s * (int64_t)n * ldz;
+  double* Os = Zout + s * (int64_t)n * ldo;
+  for (int i = tid; i < n * g; i += kGirardThreads) {
+    const int r = i / g, j = i - r * g;
+    G[i] = __ldcs(Zs + (int64_t)r * ldz + 1 + j);
+  }
+  for (int r = tid; r < n; r += kGirardThreads) Os[(int64_t)r * ldo] = Zs[(int64_t)r * ldz];
+  __syncthreads();
+  const int written = girard_block(n, g, order, metric, G, key, flag, Os + 1, ldo, gout_cap);
   if (tid == 0) gout[s] = written;
+}
+
+// ---------------------------------------------------------------------------------------
+// Tube rollout: `steps` reach-set steps of one scenario by one CTA, the zonotope never leaving shared memory:
+//   Z_{k+1} = reduce( M_K (x) Z_k  (+)  M_Delta (x) <z_k, 0>  (+)  W ,  order )          z_k = [xbar_k; v_k]
+// i.e. tzddpc/tzddpc.py:175-186,205 evaluated numerically with the Girard reduction of
+// examples/1.double_integrator_sim.py:170 applied after every step (BASELINE.json configs[4]: long horizons need
+// it, the un-reduced generator count grows like (N_K + 1)^k).  Per step the pre-reduction block
+//   [C_K G | G^K_1 c, G^K_1 G | ... | G^D_1 z .. G^D_ND z | G_W]   (n x ((N_K+1) g + N_K + N_D + g_W), pyzonotope order)
+// is built in shared memory, reduced in place (girard_block) and its interval hull (tzddpc/tzddpc.py:191-197)
+// written out: HBM traffic per scenario-step is the hull (2n doubles) + z_k, not the 100 KB generator block.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kGirardThreads) tube_rollout_kernel(
+    int n, int m, int NK, int ND, int gW, int g0, int steps, double order, int metric, int gcap, int gpre_cap,
+    const double* __restrict__ CK, const double* __restrict__ GK, const double* __restrict__ GD, int per_scenario,
+    const double* __restrict__ Z0, const double* __restrict__ XU, const double* __restrict__ W,
+    double* __restrict__ Zfinal, int32_t* __restrict__ gfinal, double* __restrict__ hull_lo, double* __restrict__ hull_hi) {
+  extern __shared__ unsigned char smraw[];
+  const int p = n + m, tid = threadIdx.x;
+  const int64_t s = blockIdx.x;
+  double* Zc = reinterpret_cast<double*>(smraw);                 // n x (1 + gcap): current zonotope [c, G]
+  double* Gp = Zc + (size_t)n * (1 + gcap);                      // n x gpre_cap: pre-reduction generator block
+  double* MK = Gp + (size_t)n * gpre_cap;                        // (NK + 1) x n x n : C_K, G^K_i
+  double* MD = MK + (size_t)(NK + 1) * n * n;                    // ND x n x p
+  double* zk = MD + (size_t)ND * n * p;                          // p
+  double* cnew = zk + p;                                         // n
+  unsigned long long* key = reinterpret_cast<unsigned long long*>(cnew + n + ((n + p) & 1));
+  unsigned char* flag = reinterpret_cast<unsigned char*>(key + gpre_cap);
+  __shared__ int g_cur, overflow;
+  const double* CKs = CK + (per_scenario ? s * (int64_t)n * n : 0);
+  const double* GKs = GK + (per_scenario ? s * (int64_t)NK * n * n : 0);
+  const double* GDs = GD + (per_scenario ? s * (int64_t)ND * n * p : 0);
+  for (int i = tid; i < n * n; i += kGirardThreads) MK[i] = CKs[i];
+  for (int i = tid; i < NK * n * n; i += kGirardThreads) MK[n * n + i] = GKs[i];
+  for (int i = tid; i < ND * n * p; i += kGirardThreads) MD[i] = GDs[i];
+  const int ldc = 1 + gcap;
+  for (int i = tid; i < n * (1 + g0); i += kGirardThreads) {
+    const int r = i / (1 + g0), j = i - r * (1 + g0);
+    Zc[r * ldc + j] = Z0[s * (int64_t)n * (1 + g0) + i];
+  }
+  if (tid == 0) { g_cur = g0; overflow = 0; }
+  __syncthreads();
+  for (int k = 0; k < steps; ++k) {
+    const int g = g_cur;
+    const int gpre = (NK + 1) * g + NK + ND + gW;
+    if (tid < p) zk[tid] = XU[(s * (int64_t)steps + k) * p + tid];
+    __syncthreads();
+    // ---- centre: C_K c + c_W   (M_Delta has a zero centre, tzddpc/tzddpc.py:122-123)
+    if (tid < n) {
+      double acc = W ? W[(int64_t)tid * (1 + gW)] : 0.0;
+      for (int q = 0; q < n; ++q) acc = fma(MK[tid * n + q], Zc[q * ldc], acc);
+      cnew[tid] = acc;
+    }
+    // ---- generator block, pyzonotope column order
+    for (int col = tid; col < gpre; col += kGirardThreads) {
+      const double* M;
+      const double* v;        // the vector multiplied: a column of Zc (stride ldc) or z_k (stride 1)
+      int vstride, len;
+      if (col < g) { M = MK; v = Zc + 1 + col; vstride = ldc; len = n; }
+      else if (col < g + NK * (1 + g)) {
+        const int t = col - g, b = t / (1 + g), j = t - b * (1 + g);
+        M = MK + (size_t)(1 + b) * n * n; v = Zc + j; vstride = ldc; len = n;
+      } else if (col < g + NK * (1 + g) + ND) {
+        const int b = col - g - NK * (1 + g);
+        M = MD + (size_t)b * n * p; v = zk; vstride = 1; len = p;
+      } else {
+        M = nullptr; v = W + 1 + (col - g - NK * (1 + g) - ND); vstride = 1 + gW; len = 0;
+      }
+      for (int r = 0; r < n; ++r) {
+        double acc;
+        if (M == nullptr) acc = v[(int64_t)r * vstride];
+        else {
+          acc = 0.0;
+          for (int q = 0; q < len; ++q) acc = fma(M[r * len + q], v[(int64_t)q * vstride], acc);
+        }
+        Gp[(size_t)r * gpre + col] = acc;
+      }
+    }
+    __syncthreads();
+    if (tid < n) Zc[tid * ldc] = cnew[tid];
+    const int written = girard_block(n, gpre, order, metric, Gp, key, flag, Zc + 1, ldc, gcap);
+    if (tid == 0) { g_cur = written < 0 ? gcap : written; if (written < 0) overflow = 1; }
+    __syncthreads();
+    // ---- interval hull of Z_{k+1}: warp r handles row r
+    {
+      const int gg = g_cur, lane = tid & 31;
+      for (int r = tid >> 5; r < n; r += kGirardThreads / 32) {
+        double acc = 0.0;
+        for (int j = 1 + lane; j <= gg; j += 32) acc += fabs(Zc[r * ldc + j]);
+        acc = warp_sum(acc);
+        if (lane == 0) {
+          const double c = Zc[r * ldc];
+          hull_lo[(s * (int64_t)steps + k) * n + r] = c - acc;
+          hull_hi[(s * (int64_t)steps + k) * n + r] = c + acc;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < n * ldc; i += kGirardThreads) Zfinal[s * (int64_t)n * ldc + i] = Zc[i];
+  if (tid == 0) gfinal[s] = overflow ? -g_cur : g_cur;       // negative: gcap was too small at some step (truncated)
 }
 
 // ---------------------------------------------------------------------------------------
@@ -435,10 +546,10 @@ extern "C" int tz_reach_step(int64_t S, int32_t n, int32_t p, int32_t N, int32_t
   TZ_REQUIRE(smem <= 200 * 1024, "matrix zonotope too large for shared memory");
   cudaStream_t st = (cudaStream_t)stream;
   if (n <= 8) {
-    if (smem > 48 * 1024) TZ_CUDA(cudaFuncSetAttribute(reach_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem + 8192 > 48 * 1024) TZ_CUDA(cudaFuncSetAttribute(reach_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     reach_kernel<8><<<(unsigned)S, 256, smem, st>>>(n, p, N, g, gW, C, Gm, per_scenario_model, Z, gW ? W : nullptr, Zout);
   } else {
-    if (smem > 48 * 1024) TZ_CUDA(cudaFuncSetAttribute(reach_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem + 8192 > 48 * 1024) TZ_CUDA(cudaFuncSetAttribute(reach_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     reach_kernel<16><<<(unsigned)S, 256, smem, st>>>(n, p, N, g, gW, C, Gm, per_scenario_model, Z, gW ? W : nullptr, Zout);
   }
   TZ_CUDA(cudaGetLastError());
@@ -453,8 +564,37 @@ extern "C" int tz_girard_reduce(int64_t S, int32_t n, int32_t g, double order, i
   TZ_REQUIRE(Z && Zout && gout, "null pointer");
   const size_t smem = (size_t)n * g * sizeof(double) + (size_t)g * sizeof(unsigned long long) + (size_t)g + 16;
   TZ_REQUIRE(smem <= 220 * 1024, "zonotope (n=%d, g=%d) does not fit in shared memory", n, g);
-  if (smem > 48 * 1024) TZ_CUDA(cudaFuncSetAttribute(girard_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem + 8192 > 48 * 1024) TZ_CUDA(cudaFuncSetAttribute(girard_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   girard_kernel<<<(unsigned)S, kGirardThreads, smem, (cudaStream_t)stream>>>(n, g, order, metric, Z, gout_cap, Zout, gout);
+  TZ_CUDA(cudaGetLastError());
+  return TZ_OK;
+}
+
+extern "C" int tz_tube_rollout(int64_t S, int32_t n, int32_t m, int32_t NK, int32_t ND, int32_t gW, int32_t g0, int32_t steps,
+                               double order, int32_t metric, const double* CK, const double* GK, const double* GD,
+                               int32_t per_scenario_model, const double* Z0, const double* XU, const double* W, int32_t gcap,
+                               double* Zfinal, int32_t* gfinal, double* hull_lo, double* hull_hi, void* stream) {
+  TZ_REQUIRE(S >= 0 && n >= 1 && n <= 16 && m >= 1 && NK >= 0 && ND >= 0 && gW >= 0 && g0 >= 0 && steps >= 0 && order >= 1.0,
+             "bad shape (n <= 16, order >= 1)");
+  TZ_REQUIRE(metric >= 0 && metric <= 2, "metric must be 0 (l1-linf), 1 (l1) or 2 (l2)");
+  if (S == 0) return TZ_OK;
+  TZ_REQUIRE(CK && Z0 && XU && Zfinal && gfinal && hull_lo && hull_hi && (NK == 0 || GK) && (ND == 0 || GD) && (gW == 0 || W),
+             "null pointer");
+  // generators after a reduction: floor(n (order - 1)) kept + n boxed; before the first one there may be g0
+  const int gred = (int)floor((double)n * (order - 1.0)) + n;
+  const int gmax = g0 > gred ? g0 : gred;
+  TZ_REQUIRE(gcap >= gmax, "gcap must be at least max(g0, floor(n (order - 1)) + n) = %d", gmax);
+  const int64_t gpre_cap = (int64_t)(NK + 1) * gmax + NK + ND + gW;
+  const int p = n + m;
+  const size_t smem = ((size_t)n * (1 + gcap) + (size_t)n * gpre_cap + (size_t)(NK + 1) * n * n + (size_t)ND * n * p + p + n + 2) *
+                          sizeof(double) + (size_t)gpre_cap * sizeof(unsigned long long) + (size_t)gpre_cap + 16;
+  TZ_REQUIRE(smem <= 220 * 1024, "tube step (n=%d, %lld generators before reduction) needs %zu bytes of shared memory",
+             n, (long long)gpre_cap, smem);
+  if (smem + 8192 > 48 * 1024)
+    TZ_CUDA(cudaFuncSetAttribute(tube_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tube_rollout_kernel<<<(unsigned)S, kGirardThreads, smem, (cudaStream_t)stream>>>(
+      n, m, NK, ND, gW, g0, steps, order, metric, gcap, (int)gpre_cap, CK, GK, GD, per_scenario_model, Z0, XU, gW ? W : nullptr,
+      Zfinal, gfinal, hull_lo, hull_hi);
   TZ_CUDA(cudaGetLastError());
   return TZ_OK;
 }
@@ -468,7 +608,7 @@ extern "C" int tz_identify(int64_t S, int32_t T, int32_t n, int32_t m, int32_t g
   TZ_REQUIRE(!dK || K, "dK needs K");
   const size_t smem = (size_t)(T - 1) * (2 * n + m) * sizeof(double);
   TZ_REQUIRE(smem <= 200 * 1024, "dataset too long for shared memory (T=%d)", T);
-  if (smem > 48 * 1024) TZ_CUDA(cudaFuncSetAttribute(identify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem + 8192 > 48 * 1024) TZ_CUDA(cudaFuncSetAttribute(identify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   identify_kernel<<<(unsigned)S, kIdThreads, smem, (cudaStream_t)stream>>>(T, n, m, gW, X, U, WZ, K, AB, dAB, dK, Pinv, status);
   TZ_CUDA(cudaGetLastError());
   return TZ_OK;

@@ -147,6 +147,34 @@ def girard_reduce(Z: Tensor, order: float, metric: int, gout_cap: int) -> Tuple[
     return out, gout
 
 
+@torch.library.custom_op("tzddpc::tube_rollout", mutates_args=(), device_types="cuda")
+def tube_rollout(CK: Tensor, GK: Tensor, GD: Tensor, Z0: Tensor, XU: Tensor, W: Optional[Tensor], order: float, metric: int,
+                 gcap: int) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """Z_{k+1} = reduce(M_K x Z_k + M_Delta x <[xbar_k; v_k], 0> + W, order) for k < steps, zonotope resident in shared
+    memory (tzddpc/tzddpc.py:175-186,205 + Zonotope.reduce).  CK: (n, n) or (S, n, n); GK: (NK, n, n) or (S, NK, n, n);
+    GD: (ND, n, n+m) or (S, ND, n, n+m); Z0: (S, n, 1+g0); XU: (S, steps, n+m); W: (n, 1+gW).
+    Returns Zfinal (S, n, 1+gcap), gfinal (S), hull_lo, hull_hi (S, steps, n)."""
+    _chk(CK), _chk(GK), _chk(GD), _chk(Z0), _chk(XU)
+    per = CK.dim() == 3
+    S, n, ld0 = Z0.shape
+    steps, p = XU.shape[1], XU.shape[2]
+    NK, ND = GK.shape[-3], GD.shape[-3]
+    gW = 0 if W is None else W.shape[1] - 1
+    if W is not None:
+        _chk(W)
+    dev = Z0.device
+    Zf = torch.empty((S, n, 1 + gcap), dtype=torch.float64, device=dev)
+    gf = torch.empty(S, dtype=torch.int32, device=dev)
+    lo = torch.empty((S, steps, n), dtype=torch.float64, device=dev)
+    hi = torch.empty_like(lo)
+    with torch.cuda.device(dev):
+        rc = _abi.lib().tz_tube_rollout(S, n, p - n, NK, ND, gW, ld0 - 1, steps, float(order), int(metric), _ptr(CK), _ptr(GK),
+                                        _ptr(GD), int(per), _ptr(Z0), _ptr(XU), _ptr(W), int(gcap), _ptr(Zf), _ptr(gf),
+                                        _ptr(lo), _ptr(hi), _stream(Z0))
+    _abi.check(rc, "tz_tube_rollout")
+    return Zf, gf, lo, hi
+
+
 @torch.library.custom_op("tzddpc::identify", mutates_args=(), device_types="cuda")
 def identify(X: Tensor, U: Tensor, WZ: Tensor, K: Optional[Tensor], want_pinv: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
     """X: (S, T, n), U: (S, T, m), WZ: (n, 1+gW), K: (S, m, n).  Returns AB (S,n,n+m), dAB, dK (S,n,n), Pinv, status.
