@@ -268,7 +268,8 @@ def run_gpu(args):
 
     def step(t):
         r = t % ring
-        ops.closed_loop_step(h, x, xbar, e, noise[t % nring], xrestart, At, Bt, status[r], cost[r], vbuf[r], traj[r], ze1[r], None,
+        ops.closed_loop_step(h, x, xbar, e, noise[t % nring], xrestart, At, Bt, status[r], cost[r], vbuf[r],
+                             None if args.ablate >= 2 else traj[r], None if args.ablate >= 1 else ze1[r], None,
                              iters[r], warm, stats[t], po)
 
     def barrier():
@@ -391,6 +392,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=1500)
     ap.add_argument("--cpu-cores", type=int, default=0, help="processes of the CPU baseline (0 = all host cores)")
     ap.add_argument("--dump-steps", default="", help="write per-step kernel ms and solver statistics to this .npz (diagnostics)")
+    ap.add_argument("--ablate", type=int, default=0, help="diagnostics only: 1 = do not write Ze[1].Z, 2 = nor the trajectory")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

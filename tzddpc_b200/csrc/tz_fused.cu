@@ -155,12 +155,36 @@ __device__ __forceinline__ void prefetch_inputs(double (*dst)[BK::SPO], const St
   cp_async_commit();
 }
 
+// Zero-fill of the dense Ze[1].Z block of one output tile (88 % of its entries are structural zeros, but the reference
+// returns the matrix dense, examples/2.pulley_sim.py:96).  It depends on nothing the solve computes, so half of the
+// warps issue it BEFORE solving their tile and the other half after: the stores of one half drain while the other half
+// computes (all warps in lock step would alternate between an idle DRAM and a saturated one: profiles/r1_v8).
+template <class BK, int W>
+__device__ __forceinline__ void zero_fill(const Aux& ax, const StepArgs& a, int64_t tile, int lane) {
+  constexpr int SPW = BK::SPO, NGRP = SPW / W, NSL = 32 / NGRP;
+  using V = Vec<W>;
+  V* const vt = nullptr;
+  const int pc = lane % NGRP, slice = lane / NGRP;
+  const int64_t so = tile * SPW + pc * W;
+  if (so >= a.S) return;
+  const int64_t LD = a.ld;
+  const int nent = ax.n * (1 + ax.g1);
+  const int64_t stepb = (int64_t)NSL * LD;
+  double* ptr = a.ze1 + so + (int64_t)slice * LD;
+  const V z0 = vzero(vt);
+  // (a down-counter: with the trip count as loop bound the compiler spilled it and re-loaded it from local memory in
+  // every iteration, behind the stores in the same LSU queue -- 20 % of all stall samples in profiles/r1_v6)
+#pragma unroll 4
+  for (int cnt = (nent - slice + NSL - 1) / NSL; cnt > 0; --cnt, ptr += stepb) vstcs(ptr, z0);
+}
+
 // Output phase of one output tile (SPO >= 16 consecutive scenarios = TPO solve tiles): lane -> (W consecutive
 // scenarios, slice); one store instruction of the warp covers NSL entries x SPO scenarios = NSL runs of SPO*8 >= 128
 // contiguous bytes (full lines) of the scenario-fastest arrays.
 template <class BK, int W>
 __device__ __forceinline__ void output_phase(WarpBuf<BK>& wb, const double (*pre)[BK::SPO], const Aux& ax, const StepArgs& a,
-                                             const double* __restrict__ tabd, const int* __restrict__ tabi, int64_t tile, int lane) {
+                                             const double* __restrict__ tabd, const int* __restrict__ tabi, int64_t tile, int lane,
+                                             bool zero_done) {
   constexpr int SPW = BK::SPO, NW = BK::NW, NGRP = SPW / W, NSL = 32 / NGRP;
   using V = Vec<W>;
   V* const vt = nullptr;
@@ -187,14 +211,7 @@ __device__ __forceinline__ void output_phase(WarpBuf<BK>& wb, const double (*pre
     // overwrite the ~12 % entries that are not structurally zero (both writes merge in L2 before reaching HBM)
     if (a.ze1) {
       double* base = a.ze1 + so;
-      const int nent = n * (1 + ax.g1);
-      const int64_t stepb = (int64_t)NSL * LD;
-      double* ptr = base + (int64_t)slice * LD;
-      const V z0 = vzero(vt);
-      // (a down-counter: with the trip count as loop bound the compiler spilled it and re-loaded it from local memory in
-      // every iteration, behind the stores in the same LSU queue -- 20 % of all stall samples in profiles/r1_v6)
-#pragma unroll 4
-      for (int cnt = (nent - slice + NSL - 1) / NSL; cnt > 0; --cnt, ptr += stepb) vstcs(ptr, z0);
+      if (!zero_done) zero_fill<BK, W>(ax, a, tile, lane);
       __syncwarp();
       const double* coef = tabd + ax.o_coef;
       const int* ent = tabi + ax.o_ent;
@@ -355,6 +372,11 @@ __global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel(const QpProg<BK
       __syncwarp();
     }
     const double (*pre)[BK::SPO] = wb.pre[buf];
+    const bool zero_first = !explicit_qp && a.ze1 != nullptr && ((blockIdx.x * BK::WPB + wib) & 1);
+    if (zero_first) {
+      if (a.vec2) zero_fill<BK, 2>(ax, a, otile, lane);
+      else zero_fill<BK, 1>(ax, a, otile, lane);
+    }
    #pragma unroll 1
    for (int half = 0; half < BK::TPO; ++half) {
     const int col = half * SPW + sl;        // column of this scenario in the warp's exchange buffers
@@ -624,8 +646,8 @@ __global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel(const QpProg<BK
    }     // solve tiles of this output tile
     if (explicit_qp) continue;
     __syncwarp();
-    if (a.vec2) output_phase<BK, 2>(wb, pre, ax, a, tabd, tabi, otile, lane);
-    else output_phase<BK, 1>(wb, pre, ax, a, tabd, tabi, otile, lane);
+    if (a.vec2) output_phase<BK, 2>(wb, pre, ax, a, tabd, tabi, otile, lane, zero_first);
+    else output_phase<BK, 1>(wb, pre, ax, a, tabd, tabi, otile, lane, zero_first);
     __syncwarp();     // wb is rewritten by the next tile
   }
   if (a.stats != nullptr && a.x != nullptr) {
