@@ -53,7 +53,7 @@ struct Bucket {
   static constexpr int HP = NPAR / 2;
   static constexpr int OM_V = 1, OM_P = 1 + NZ, NW = 1 + NZ + NPAR;
   static constexpr int OM_C = NW, OM_XP = NW + HP, KOM = NW + 2 * HP;
-  static constexpr int PRE_ROWS = 4 * HP;             // prefetched input rows of an output tile: [xbar0 | e0 | x | noise]
+  static constexpr int PRE_ROWS = 4 * HP + G;         // prefetched input rows of an output tile: [xbar0 | e0 | x | noise | hint words]
   static constexpr int NCOLP = (NCOL + 1) & ~1;       // row pitch of R / Rchk (even: 16-byte aligned rows)
   static_assert(NCL <= 32 && (G & (G - 1)) == 0 && G <= 32 && N2 >= 1 && NAG >= 1, "bad bucket");
 };

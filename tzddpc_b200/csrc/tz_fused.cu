@@ -131,11 +131,27 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 template <class BK>
-__device__ __forceinline__ void prefetch_inputs(double (*dst)[BK::SPO], const StepArgs& a, int n, int64_t otile, int lane) {
+__device__ __forceinline__ void prefetch_inputs(double (*dst)[BK::SPO], const StepArgs& a, const double* hint, int n,
+                                                int64_t otile, int lane) {
   constexpr int SPO = BK::SPO;
   const double* src[4] = {a.xbar0, a.e0, a.x, a.noise};
   const int64_t s0 = otile * SPO;
   const int narr = a.x != nullptr ? 4 : 2;
+  if (hint != nullptr) {                                 // active-set hint words: G rows behind the 4n input rows
+    if (a.vec2) {
+      for (int c = lane; c < BK::G * (SPO / 2); c += 32) {
+        const int row = c / (SPO / 2), ch = c - row * (SPO / 2);
+        const int64_t s = s0 + 2 * ch;
+        if (s < a.S) cp_async16(&dst[4 * n + row][2 * ch], hint + (int64_t)row * a.ld + s);
+      }
+    } else {
+      for (int c = lane; c < BK::G * SPO; c += 32) {
+        const int row = c / SPO, ch = c - row * SPO;
+        const int64_t s = s0 + ch;
+        if (s < a.S) cp_async8(&dst[4 * n + row][ch], hint + (int64_t)row * a.ld + s);
+      }
+    }
+  }
   if (a.vec2) {
     constexpr int CPR = SPO / 2;                        // 16-byte chunks per row
     const int total = narr * n * CPR;
@@ -216,7 +232,7 @@ __device__ __forceinline__ void output_phase(WarpBuf<BK>& wb, const double (*pre
       const double* coef = tabd + ax.o_coef;
       const int* ent = tabi + ax.o_ent;
       const int* idx = tabi + ax.o_idx;
-#pragma unroll 2
+#pragma unroll 4
       for (int i = slice; i < ax.n_nz; i += NSL) vstcs(base + (int64_t)ent[i] * LD, vmul(coef[i], om(idx[i])));
     }
     // ---- nominal trajectory xbar_0..xbar_N = XB om  (tzddpc/tzddpc.py:166-170)
@@ -360,11 +376,12 @@ __global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel(const QpProg<BK
 
   int buf = 0;
   const int64_t otile0 = (int64_t)blockIdx.x * BK::WPB + wib;
-  if (!explicit_qp && otile0 < ntiles) prefetch_inputs<BK>(wb.pre[0], a, n, otile0, lane);
+  const double* hintp = (sp.warm == 2 && !explicit_qp) ? a.warm : nullptr;
+  if (!explicit_qp && otile0 < ntiles) prefetch_inputs<BK>(wb.pre[0], a, hintp, n, otile0, lane);
   for (int64_t otile = otile0; otile < ntiles; otile += nwarps, buf ^= 1) {
     if (!explicit_qp) {        // inputs of the NEXT output tile stream in while this one is solved
       if (otile + nwarps < ntiles) {
-        prefetch_inputs<BK>(wb.pre[buf ^ 1], a, n, otile + nwarps, lane);
+        prefetch_inputs<BK>(wb.pre[buf ^ 1], a, hintp, n, otile + nwarps, lane);
         cp_async_wait<1>();
       } else {
         cp_async_wait<0>();
@@ -535,7 +552,7 @@ __global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel(const QpProg<BK
     bool hint_ok = false;
     if (use_hint) {
       unsigned long long hint = 0ull;
-      if (live) hint = (unsigned long long)__double_as_longlong(a.warm[(int64_t)g * LD + s]);
+      if (live) hint = (unsigned long long)__double_as_longlong(pre[4 * n + g][col]);
       const bool valid = solve_it && gor<G>((hint & kCodeValid) ? 0 : 1) == 0;
       if (__any_sync(0xffffffffu, valid)) {
         double lam[NCL], xk[NZ], x0[NZ];

@@ -115,26 +115,32 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_tot, int& t
   return base + inc - v;
 }
 
-// Girard reduction of the generator block G (n x g, shared memory, row-major) of one zonotope by one CTA.
+// Girard reduction of the generator block G (n x g, row pitch ldg; shared memory, or global memory that stays in L2
+// between the metric pass and the box / compaction passes) of one zonotope by one CTA.
 // Writes the reduced generators to out[r * ldo + j] (global or shared), zero-pads up to gout_cap, returns the
 // number of generators written (negative: gout_cap too small).  key / flag: g-element scratch in shared memory.
-__device__ int girard_block(int n, int g, double order, int metric, const double* __restrict__ G,
+//   metric per column -> MSB-first radix select of the n_red-th smallest key (stops as soon as a digit bucket is
+//   consumed whole) -> ties by lowest index -> box of the selected columns -> stable compaction of the kept ones.
+// Every thread owns a CONTIGUOUS range of columns, so that ranks (ties, output positions) need one block scan each.
+__device__ int girard_block(int n, int g, double order, int metric, const double* __restrict__ G, int64_t ldg,
                             unsigned long long* __restrict__ key, unsigned char* __restrict__ flag, double* __restrict__ out,
                             int64_t ldo, int gout_cap) {
   __shared__ int hist[256];
   __shared__ int warp_tot[kGirardThreads / 32];
   __shared__ unsigned long long sel_prefix;
-  __shared__ int sel_remaining;
+  __shared__ int sel_remaining, sel_done;
   __shared__ double dbox[kGirardMaxDim];
-  __shared__ double red[kGirardThreads / 32];
-  const int tid = threadIdx.x;
+  __shared__ double red[kGirardThreads / 32][8];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int per = (g + kGirardThreads - 1) / kGirardThreads;       // columns per thread (contiguous range)
+  const int j0 = min(tid * per, g), j1 = min(j0 + per, g);
   // metric (rows accumulated r = 0..n-1, exactly as oracle/zono.py:_girard_metric) and zero filter
   int nnz_local = 0;
   for (int j = tid; j < g; j += kGirardThreads) {
     double sum = 0.0, mx = 0.0;
     bool nzc = false;
     for (int r = 0; r < n; ++r) {
-      const double a = fabs(G[(size_t)r * g + j]);
+      const double a = fabs(G[(int64_t)r * ldg + j]);
       nzc = nzc || (a != 0.0);
       if (metric == 2) sum = __dadd_rn(sum, __dmul_rn(a, a));      // no FMA contraction: selection must match the oracle bit for bit
       else sum += a;
@@ -154,71 +160,108 @@ __device__ int girard_block(int n, int g, double order, int metric, const double
     if (n_unred < 0) n_unred = 0;
     n_red = gnz - n_unred;
     // ---- radix select (MSB first, 8 bits per pass) of the n_red-th smallest key among non-zero columns
-    if (tid == 0) { sel_prefix = 0ull; sel_remaining = n_red; }
+    if (tid == 0) { sel_prefix = 0ull; sel_remaining = n_red; sel_done = 0; }
     __syncthreads();
-    for (int pass = 7; pass >= 0; --pass) {
-      for (int i = tid; i < 256; i += kGirardThreads) hist[i] = 0;
+    int pass = 7;
+    for (; pass >= 0; --pass) {
+      hist[tid] = 0;                                           // kGirardThreads == 256 bins
       __syncthreads();
       const unsigned long long prefix = sel_prefix;
       const unsigned long long himask = (pass == 7) ? 0ull : (~0ull << ((pass + 1) * 8));
       for (int j = tid; j < g; j += kGirardThreads)
         if (flag[j] && ((key[j] & himask) == prefix)) atomicAdd(&hist[(int)((key[j] >> (pass * 8)) & 0xffull)], 1);
       __syncthreads();
-      if (tid == 0) {
-        int rem = sel_remaining, d = 0;
-        for (; d < 256; ++d) {
-          if (hist[d] >= rem) break;
-          rem -= hist[d];
+      if (wid == 0) {        // warp 0 finds the digit: lane l owns bins 8l .. 8l+7
+        int loc[8], tot = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { loc[i] = hist[lane * 8 + i]; tot += loc[i]; }
+        int inc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += t;
         }
-        sel_prefix = prefix | ((unsigned long long)d << (pass * 8));
-        sel_remaining = rem;
+        const int rem = sel_remaining;
+        const int before = inc - tot;                          // keys in lower bins of other lanes
+        const bool mine = before < rem && rem <= inc;          // the rem-th smallest lies in one of my bins
+        if (mine) {
+          int acc = before, d = 0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (acc + loc[i] >= rem) { d = i; break; }
+            acc += loc[i];
+          }
+          const int cnt = loc[d];
+          const unsigned long long digit = (unsigned long long)(lane * 8 + d);
+          if (acc + cnt == rem) {
+            // the bucket is consumed whole: every key with this prefix and digit is reduced, no need to refine
+            const unsigned long long low = pass == 0 ? 0ull : ((1ull << (pass * 8)) - 1ull);
+            sel_prefix = prefix | (digit << (pass * 8)) | low;
+            sel_remaining = 0;                                 // no ties at the threshold are left out
+            sel_done = 1;
+          } else {
+            sel_prefix = prefix | (digit << (pass * 8));
+            sel_remaining = rem - acc;
+          }
+        }
       }
       __syncthreads();
+      if (sel_done) break;
     }
-    // keys < thr are reduced; among keys == thr the first `sel_remaining` (lowest index) are reduced
+    // keys < thr are reduced; among keys == thr the first `ties_needed` (lowest index) are reduced.
+    // (early stop: thr is the largest key of the consumed bucket's range and all keys <= thr are reduced)
     const unsigned long long thr = sel_prefix;
+    const bool whole = sel_done != 0;
     const int ties_needed = sel_remaining;
-    // stable rank among the ties: chunked scan in index order
-    int tie_base = 0;
-    for (int j0 = 0; j0 < g; j0 += kGirardThreads) {
-      const int j = j0 + tid;
-      const int is_tie = (j < g && flag[j] && key[j] == thr) ? 1 : 0;
-      int tot;
-      const int rank = tie_base + block_exclusive_scan(is_tie, warp_tot, tot);
-      if (j < g && flag[j]) {
-        if (key[j] < thr || (is_tie && rank < ties_needed)) flag[j] = 2;
-      }
-      tie_base += tot;
+    int my_ties = 0;
+    if (!whole)
+      for (int j = j0; j < j1; ++j) my_ties += (flag[j] && key[j] == thr) ? 1 : 0;
+    int tot;
+    int rank = whole ? 0 : block_exclusive_scan(my_ties, warp_tot, tot);
+    for (int j = j0; j < j1; ++j) {
+      if (!flag[j]) continue;
+      if (whole) { if (key[j] <= thr) flag[j] = 2; }
+      else if (key[j] < thr) flag[j] = 2;
+      else if (key[j] == thr) { if (rank < ties_needed) flag[j] = 2; ++rank; }
     }
     __syncthreads();
-    // ---- box of the reduced columns: fixed-order block reduction per row (deterministic)
-    for (int r = 0; r < n; ++r) {
-      double acc = 0.0;
+    // ---- box of the reduced columns: 8 rows per sweep, fixed-order block reduction (deterministic)
+    for (int r0 = 0; r0 < n; r0 += 8) {
+      double acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.0;
       for (int j = tid; j < g; j += kGirardThreads)
-        if (flag[j] == 2) acc += fabs(G[(size_t)r * g + j]);
-      acc = warp_sum(acc);
-      if ((tid & 31) == 0) red[tid >> 5] = acc;
+        if (flag[j] == 2) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (r0 + i < n) acc[i] += fabs(G[(int64_t)(r0 + i) * ldg + j]);
+        }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const double v = warp_sum(acc[i]);
+        if (lane == 0) red[wid][i] = v;
+      }
       __syncthreads();
-      if (tid == 0) {
+      if (tid < 8 && r0 + tid < n) {
         double t = 0.0;
-        for (int w = 0; w < kGirardThreads / 32; ++w) t += red[w];
-        dbox[r] = t;
+        for (int w = 0; w < kGirardThreads / 32; ++w) t += red[w][tid];
+        dbox[r0 + tid] = t;
       }
       __syncthreads();
     }
   }
   // ---- output: kept columns in original order, then diag(d), zero padding
-  int out_base = 0;
-  for (int j0 = 0; j0 < g; j0 += kGirardThreads) {
-    const int j = j0 + tid;
-    const int keep = (j < g && flag[j] == 1) ? 1 : 0;
-    int tot;
-    const int pos = out_base + block_exclusive_scan(keep, warp_tot, tot);
-    if (keep && pos < gout_cap)
-      for (int r = 0; r < n; ++r) out[(int64_t)r * ldo + pos] = G[(size_t)r * g + j];
-    out_base += tot;
+  int my_keep = 0;
+  for (int j = j0; j < j1; ++j) my_keep += flag[j] == 1 ? 1 : 0;
+  int kept;
+  int pos = block_exclusive_scan(my_keep, warp_tot, kept);
+  for (int j = j0; j < j1; ++j) {
+    if (flag[j] != 1) continue;
+    if (pos < gout_cap)
+      for (int r = 0; r < n; ++r) out[(int64_t)r * ldo + pos] = G[(int64_t)r * ldg + j];
+    ++pos;
   }
-  int written = out_base;
+  int written = kept;
   if (do_reduce) {
     for (int i = tid; i < n * n; i += kGirardThreads) {
       const int r = i / n, c = i - r * n;
@@ -236,25 +279,21 @@ __device__ int girard_block(int n, int g, double order, int metric, const double
   return written;
 }
 
+// Stand-alone reduction: only the keys and flags live in shared memory (9 bytes per generator), so several CTAs share an
+// SM; the generator block is read from HBM once (metric pass) and a second time from L2 (box and compaction).
 __global__ void __launch_bounds__(kGirardThreads) girard_kernel(int n, int g, double order, int metric,
                                                                 const double* __restrict__ Z, int gout_cap,
                                                                 double* __restrict__ Zout, int32_t* __restrict__ gout) {
   extern __shared__ unsigned char smraw[];
-  double* G = reinterpret_cast<double*>(smraw);                              // n x g
-  unsigned long long* key = reinterpret_cast<unsigned long long*>(G + (size_t)n * g);   // g
+  unsigned long long* key = reinterpret_cast<unsigned long long*>(smraw);    // g
   unsigned char* flag = reinterpret_cast<unsigned char*>(key + g);           // g: 0 zero, 1 keep, 2 reduce
   const int64_t s = blockIdx.x;
   const int tid = threadIdx.x;
   const int ldz = 1 + g, ldo = 1 + gout_cap;
   const double* Zs = Z + s * (int64_t)n * ldz;
   double* Os = Zout + s * (int64_t)n * ldo;
-  for (int i = tid; i < n * g; i += kGirardThreads) {
-    const int r = i / g, j = i - r * g;
-    G[i] = __ldcs(Zs + (int64_t)r * ldz + 1 + j);
-  }
   for (int r = tid; r < n; r += kGirardThreads) Os[(int64_t)r * ldo] = Zs[(int64_t)r * ldz];
-  __syncthreads();
-  const int written = girard_block(n, g, order, metric, G, key, flag, Os + 1, ldo, gout_cap);
+  const int written = girard_block(n, g, order, metric, Zs + 1, ldz, key, flag, Os + 1, ldo, gout_cap);
   if (tid == 0) gout[s] = written;
 }
 
@@ -336,7 +375,7 @@ __global__ void __launch_bounds__(kGirardThreads) tube_rollout_kernel(
     }
     __syncthreads();
     if (tid < n) Zc[tid * ldc] = cnew[tid];
-    const int written = girard_block(n, gpre, order, metric, Gp, key, flag, Zc + 1, ldc, gcap);
+    const int written = girard_block(n, gpre, order, metric, Gp, gpre, key, flag, Zc + 1, ldc, gcap);
     if (tid == 0) { g_cur = written < 0 ? gcap : written; if (written < 0) overflow = 1; }
     __syncthreads();
     // ---- interval hull of Z_{k+1}: warp r handles row r
@@ -562,8 +601,8 @@ extern "C" int tz_girard_reduce(int64_t S, int32_t n, int32_t g, double order, i
   TZ_REQUIRE(metric >= 0 && metric <= 2, "metric must be 0 (l1-linf), 1 (l1) or 2 (l2)");
   if (S == 0) return TZ_OK;
   TZ_REQUIRE(Z && Zout && gout, "null pointer");
-  const size_t smem = (size_t)n * g * sizeof(double) + (size_t)g * sizeof(unsigned long long) + (size_t)g + 16;
-  TZ_REQUIRE(smem <= 220 * 1024, "zonotope (n=%d, g=%d) does not fit in shared memory", n, g);
+  const size_t smem = (size_t)g * sizeof(unsigned long long) + (size_t)g + 16;
+  TZ_REQUIRE(smem <= 200 * 1024, "too many generators (g=%d) for the shared-memory key table", g);
   if (smem + 8192 > 48 * 1024) TZ_CUDA(cudaFuncSetAttribute(girard_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   girard_kernel<<<(unsigned)S, kGirardThreads, smem, (cudaStream_t)stream>>>(n, g, order, metric, Z, gout_cap, Zout, gout);
   TZ_CUDA(cudaGetLastError());
