@@ -13,678 +13,14 @@
 //   examples/2.pulley_sim.py:90-96 (nominal/plant/error update, Zek.Z.value)
 // Algorithmic HBM bytes per scenario-step:
 //   8*[6n + N*m + (N+1)n + 1 + n(1+g1)] + 4.
-#include <cmath>
-#include <new>
-#include <vector>
-
-#include "tz_admm.cuh"
+#include "tz_step.cuh"
 
 namespace tz {
 
-// Run-time sized tables of a program, one device blob staged into shared memory by every CTA:
-//   doubles: XB ((N+1)n x NW) | CZ (n x NW) | K (m x n) | nz_coef (n_nz)      [+ A_true, B_true appended in smem]
-//   int32  : nz_ent (n_nz) | nz_idx (n_nz)
-// XB / CZ columns and nz_idx address the per-scenario vector om (layout in Bucket: OM_*).
-struct Aux {
-  const double* tab;
-  int n_dbl, n_int;                // sizes of the two parts
-  int o_XB, o_CZ, o_K, o_coef;     // offsets (doubles)
-  int o_ent, o_idx;                // offsets (int32, from the start of the int part)
-  int n_nz;                        // entries of Ze[1].Z that are not structurally zero (centre column included)
-  int n, m, N, nv, g1;
-};
-
-struct StepArgs {
-  int64_t S;                       // scenarios in this launch
-  int64_t ld;                      // leading dimension of every SoA array (>= S)
-  int vec2;                        // 1: S, ld even and every array 16-byte aligned -> two scenarios per lane in the output phase
-  const double* xbar0;             // parameters (n x S); aliases xbar/e in closed loop
-  const double* e0;
-  double* x;                       // closed loop only (NULL = solve only)
-  double* xbar;
-  double* e;
-  const double* noise;
-  const double* x_restart;         // closed loop only: state an infeasible scenario restarts from (NULL: it keeps its state)
-  const double* A_true;
-  const double* B_true;
-  double* cost;
-  double* v;
-  double* xbar_traj;
-  double* ze1;
-  double* u_out;
-  int32_t* status;
-  int32_t* iters;
-  double* warm;
-  double* stats;
-  // explicit-instance mode (tz_qp_solve): q, l, u given, z / y returned
-  const double* q_in;
-  const double* l_in;
-  const double* u_in;
-  double* z_out;
-  double* y_out;
-};
-
-// Shared-memory image of one CTA: the program (read-only after staging) and, per warp, the
-// exchange buffers between the solve phase and the output phase of a tile.
-template <class BK>
-struct alignas(16) WarpBuf {
-  double pre[2][BK::PRE_ROWS][BK::SPO];  // cp.async double buffer: rows [xbar0 | e0 | x | noise] (n each) of this / the next output tile
-  double om[BK::KOM][BK::SPO];     // [1 | v | xbar0 | e0 | centre of Ze[1] | x+] per scenario of the warp's output tile
-  double ysave[BK::NCL][32];       // duals at the previous residual check (certificate of infeasibility)
-  double cost[BK::SPO];
-  double stacc[TZ_NSTATS][BK::SPO];   // closed-loop statistics of this warp's tiles, reduced once at the end of the kernel
-  int status[BK::SPO];
-  int iters[BK::SPO];
-};
-template <class BK>
-struct alignas(16) Smem {
-  double Aa[BK::NC][BK::NZ];       // alpha * A (alpha is a solver option, so this is built when the program is staged)
-  QpProg<BK> pg;
-  WarpBuf<BK> wb[BK::WPB];
-};
-
-// ---- W scenarios per lane (1: scalar accesses, 2: 16-byte accesses) ----------------------------
-template <int W> struct Vec;
-template <> struct Vec<1> { double a; };
-template <> struct Vec<2> { double a, b; };
-__device__ __forceinline__ Vec<1> vld(const double* p, Vec<1>*) { return Vec<1>{*p}; }
-__device__ __forceinline__ Vec<2> vld(const double* p, Vec<2>*) { const double2 t = *reinterpret_cast<const double2*>(p); return Vec<2>{t.x, t.y}; }
-__device__ __forceinline__ void vst(double* p, Vec<1> v) { *p = v.a; }
-__device__ __forceinline__ void vst(double* p, Vec<2> v) { *reinterpret_cast<double2*>(p) = make_double2(v.a, v.b); }
-#ifndef TZ_ZST
-#define TZ_ZST 1
-#endif
-#if TZ_ZST == 0
-__device__ __forceinline__ void vstcs(double* p, Vec<1> v) { *p = v.a; }
-__device__ __forceinline__ void vstcs(double* p, Vec<2> v) { *reinterpret_cast<double2*>(p) = make_double2(v.a, v.b); }
-#elif TZ_ZST == 1
-__device__ __forceinline__ void vstcs(double* p, Vec<1> v) { __stcs(p, v.a); }
-__device__ __forceinline__ void vstcs(double* p, Vec<2> v) { __stcs(reinterpret_cast<double2*>(p), make_double2(v.a, v.b)); }
-#else
-__device__ __forceinline__ void vstcs(double* p, Vec<1> v) { __stcg(p, v.a); }
-__device__ __forceinline__ void vstcs(double* p, Vec<2> v) { __stcg(reinterpret_cast<double2*>(p), make_double2(v.a, v.b)); }
-#endif
-__device__ __forceinline__ Vec<1> vfma(double c, Vec<1> x, Vec<1> acc) { return Vec<1>{fma(c, x.a, acc.a)}; }
-__device__ __forceinline__ Vec<2> vfma(double c, Vec<2> x, Vec<2> acc) { return Vec<2>{fma(c, x.a, acc.a), fma(c, x.b, acc.b)}; }
-__device__ __forceinline__ Vec<1> vmul(double c, Vec<1> x) { return Vec<1>{c * x.a}; }
-__device__ __forceinline__ Vec<2> vmul(double c, Vec<2> x) { return Vec<2>{c * x.a, c * x.b}; }
-__device__ __forceinline__ Vec<1> vsub(Vec<1> x, Vec<1> y) { return Vec<1>{x.a - y.a}; }
-__device__ __forceinline__ Vec<2> vsub(Vec<2> x, Vec<2> y) { return Vec<2>{x.a - y.a, x.b - y.b}; }
-__device__ __forceinline__ Vec<1> vzero(Vec<1>*) { return Vec<1>{0.0}; }
-__device__ __forceinline__ Vec<2> vzero(Vec<2>*) { return Vec<2>{0.0, 0.0}; }
-__device__ __forceinline__ Vec<1> vsel(const bool* g, Vec<1> x, double other) { return Vec<1>{g[0] ? x.a : other}; }
-__device__ __forceinline__ Vec<2> vsel(const bool* g, Vec<2> x, double other) { return Vec<2>{g[0] ? x.a : other, g[1] ? x.b : other}; }
-__device__ __forceinline__ double vget(Vec<1> x, int) { return x.a; }
-__device__ __forceinline__ double vget(Vec<2> x, int i) { return i == 0 ? x.a : x.b; }
-
-// ---- cp.async prefetch of the per-scenario inputs of an output tile (hides the DRAM latency of the only loads of the step)
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-
-template <class BK>
-__device__ __forceinline__ void prefetch_inputs(double (*dst)[BK::SPO], const StepArgs& a, const double* hint, int n,
-                                                int64_t otile, int lane) {
-  constexpr int SPO = BK::SPO;
-  const double* src[4] = {a.xbar0, a.e0, a.x, a.noise};
-  const int64_t s0 = otile * SPO;
-  const int narr = a.x != nullptr ? 4 : 2;
-  if (hint != nullptr) {                                 // active-set hint words: G rows behind the 4n input rows
-    if (a.vec2) {
-      for (int c = lane; c < BK::G * (SPO / 2); c += 32) {
-        const int row = c / (SPO / 2), ch = c - row * (SPO / 2);
-        const int64_t s = s0 + 2 * ch;
-        if (s < a.S) cp_async16(&dst[4 * n + row][2 * ch], hint + (int64_t)row * a.ld + s);
-      }
-    } else {
-      for (int c = lane; c < BK::G * SPO; c += 32) {
-        const int row = c / SPO, ch = c - row * SPO;
-        const int64_t s = s0 + ch;
-        if (s < a.S) cp_async8(&dst[4 * n + row][ch], hint + (int64_t)row * a.ld + s);
-      }
-    }
-  }
-  if (a.vec2) {
-    constexpr int CPR = SPO / 2;                        // 16-byte chunks per row
-    const int total = narr * n * CPR;
-    for (int c = lane; c < total; c += 32) {
-      const int row = c / CPR, ch = c - row * CPR, arr = row / n, r = row - arr * n;
-      const int64_t s = s0 + 2 * ch;
-      if (src[arr] != nullptr && s < a.S) cp_async16(&dst[row][2 * ch], src[arr] + (int64_t)r * a.ld + s);
-    }
-  } else {
-    const int total = narr * n * SPO;
-    for (int c = lane; c < total; c += 32) {
-      const int row = c / SPO, ch = c - row * SPO, arr = row / n, r = row - arr * n;
-      const int64_t s = s0 + ch;
-      if (src[arr] != nullptr && s < a.S) cp_async8(&dst[row][ch], src[arr] + (int64_t)r * a.ld + s);
-    }
-  }
-  cp_async_commit();
-}
-
-// Zero-fill of the dense Ze[1].Z block of one output tile (88 % of its entries are structural zeros, but the reference
-// returns the matrix dense, examples/2.pulley_sim.py:96).  It depends on nothing the solve computes, so half of the
-// warps issue it BEFORE solving their tile and the other half after: the stores of one half drain while the other half
-// computes (all warps in lock step would alternate between an idle DRAM and a saturated one: profiles/r1_v8).
-template <class BK, int W>
-__device__ __forceinline__ void zero_fill(const Aux& ax, const StepArgs& a, int64_t tile, int lane) {
-  constexpr int SPW = BK::SPO, NGRP = SPW / W, NSL = 32 / NGRP;
-  using V = Vec<W>;
-  V* const vt = nullptr;
-  const int pc = lane % NGRP, slice = lane / NGRP;
-  const int64_t so = tile * SPW + pc * W;
-  if (so >= a.S) return;
-  const int64_t LD = a.ld;
-  const int nent = ax.n * (1 + ax.g1);
-  const int64_t stepb = (int64_t)NSL * LD;
-  double* ptr = a.ze1 + so + (int64_t)slice * LD;
-  const V z0 = vzero(vt);
-  // (a down-counter: with the trip count as loop bound the compiler spilled it and re-loaded it from local memory in
-  // every iteration, behind the stores in the same LSU queue -- 20 % of all stall samples in profiles/r1_v6)
-#pragma unroll 4
-  for (int cnt = (nent - slice + NSL - 1) / NSL; cnt > 0; --cnt, ptr += stepb) vstcs(ptr, z0);
-}
-
-// Output phase of one output tile (SPO >= 16 consecutive scenarios = TPO solve tiles): lane -> (W consecutive
-// scenarios, slice); one store instruction of the warp covers NSL entries x SPO scenarios = NSL runs of SPO*8 >= 128
-// contiguous bytes (full lines) of the scenario-fastest arrays.
-template <class BK, int W>
-__device__ __forceinline__ void output_phase(WarpBuf<BK>& wb, const double (*pre)[BK::SPO], const Aux& ax, const StepArgs& a,
-                                             const double* __restrict__ tabd, const int* __restrict__ tabi, int64_t tile, int lane,
-                                             bool zero_done) {
-  constexpr int SPW = BK::SPO, NW = BK::NW, NGRP = SPW / W, NSL = 32 / NGRP;
-  using V = Vec<W>;
-  V* const vt = nullptr;
-  const int pc = lane % NGRP, slice = lane / NGRP, sc0 = pc * W;
-  const int64_t so = tile * SPW + sc0;
-  const int64_t LD = a.ld;
-  const int n = ax.n, m = ax.m, nv = ax.nv;
-  const double* sXB = tabd + ax.o_XB;
-  int stt[W];
-  bool olive[W], ogood[W];
-  bool any_live = false, all_good = true;
-#pragma unroll
-  for (int t = 0; t < W; ++t) {
-    stt[t] = wb.status[sc0 + t];
-    olive[t] = stt[t] >= 0;
-    ogood[t] = stt[t] == TZ_STATUS_OK || stt[t] == TZ_STATUS_MAXITER;
-    any_live = any_live || olive[t];
-    all_good = all_good && ogood[t];
-  }
-  // (vector path: S is even, so the scenarios of a pair are live together)
-  auto om = [&](int j) { return vld(&wb.om[j][sc0], vt); };
-  if (any_live) {
-    // ---- Ze[1].Z at the optimum (examples/2.pulley_sim.py:96: Zek.Z.value), dense n x (1+g1): zero-fill, then
-    // overwrite the ~12 % entries that are not structurally zero (both writes merge in L2 before reaching HBM)
-    if (a.ze1) {
-      double* base = a.ze1 + so;
-      if (!zero_done) zero_fill<BK, W>(ax, a, tile, lane);
-      __syncwarp();
-      const double* coef = tabd + ax.o_coef;
-      const int* ent = tabi + ax.o_ent;
-      const int* idx = tabi + ax.o_idx;
-#pragma unroll 4
-      for (int i = slice; i < ax.n_nz; i += NSL) vstcs(base + (int64_t)ent[i] * LD, vmul(coef[i], om(idx[i])));
-    }
-    // ---- nominal trajectory xbar_0..xbar_N = XB om  (tzddpc/tzddpc.py:166-170)
-    if (a.xbar_traj) {
-      const int nrows = (ax.N + 1) * n;
-      for (int i = slice; i < nrows; i += NSL) {
-        const double* row = sXB + i * NW;
-        V acc = vzero(vt);
-#pragma unroll
-        for (int j = 0; j < NW; ++j) acc = vfma(row[j], om(j), acc);
-        vst(a.xbar_traj + (int64_t)i * LD + so, acc);
-      }
-    }
-    if (a.v)
-      for (int j = slice; j < nv; j += NSL) vst(a.v + (int64_t)j * LD + so, om(BK::OM_V + j));
-    if (slice == 0) {
-#pragma unroll
-      for (int t = 0; t < W; ++t) {
-        if (olive[t]) {
-          if (a.status) a.status[so + t] = stt[t];
-          if (a.iters) a.iters[so + t] = wb.iters[sc0 + t];
-          if (a.cost) a.cost[so + t] = wb.cost[sc0 + t];
-        }
-      }
-    }
-  }
-  // ---- closed-loop update (examples/2.pulley_sim.py:90-94): row i of the update by slice i
-  if (a.x != nullptr) {
-    const double* sK = tabd + ax.o_K;
-    const double* sA = tabd + ax.n_dbl;
-    const double* sB = sA + n * n;
-    if (any_live) {
-      V us[kMaxM];
-#pragma unroll
-      for (int j = 0; j < kMaxM; ++j) {
-        V acc = vzero(vt);
-        if (j < m) {
-          acc = om(BK::OM_V + j);                                              // v[0]
-          for (int i = 0; i < n; ++i) acc = vfma(sK[j * n + i], om(BK::OM_P + BK::NPAR / 2 + i), acc);
-          if (a.u_out && slice == 0) vst(a.u_out + (int64_t)j * LD + so, vsel(ogood, acc, NAN));
-        }
-        us[j] = acc;                                                           // u = K e + v[0]
-      }
-      for (int i = slice; i < n; i += NSL) {
-        V acc = a.noise ? vld(&pre[3 * n + i][sc0], vt) : vzero(vt);
-        for (int k = 0; k < n; ++k) acc = vfma(sA[i * n + k], vld(&pre[2 * n + k][sc0], vt), acc);
-#pragma unroll
-        for (int k = 0; k < kMaxM; ++k)
-          if (k < m) acc = vfma(sB[i * m + k], us[k], acc);
-        const double* row = sXB + (n + i) * NW;                                // xbar+ = xbar_traj[1]
-        V xb1 = vzero(vt);
-#pragma unroll
-        for (int j = 0; j < NW; ++j) xb1 = vfma(row[j], om(j), xb1);
-        V en = vsub(acc, xb1);                                                 // e+ = x+ - xbar+
-        if (!all_good) {
-          // a scenario whose step failed keeps its state, or -- the reference raises and the run ends
-          // (tzddpc/tzddpc.py:374-375) -- starts a new run from x_restart: x = xbar = x_restart, e = 0
-          const V xo = vld(&pre[2 * n + i][sc0], vt);
-          const V xbo = om(BK::OM_P + i), eo = om(BK::OM_P + BK::NPAR / 2 + i);
-          const V xr = a.x_restart ? vld(a.x_restart + (int64_t)i * LD + so, vt) : xo;
-          double xa[W], ba[W], ea[W];
-#pragma unroll
-          for (int t = 0; t < W; ++t) {
-            xa[t] = ogood[t] ? vget(acc, t) : vget(xr, t);
-            ba[t] = ogood[t] ? vget(xb1, t) : (a.x_restart ? vget(xr, t) : vget(xbo, t));
-            ea[t] = ogood[t] ? vget(en, t) : (a.x_restart ? 0.0 : vget(eo, t));
-          }
-          if constexpr (W == 1) { acc = V{xa[0]}; xb1 = V{ba[0]}; en = V{ea[0]}; }
-          else { acc = V{xa[0], xa[1]}; xb1 = V{ba[0], ba[1]}; en = V{ea[0], ea[1]}; }
-        }
-        vst(&wb.om[BK::OM_XP + i][sc0], acc);
-        vst(a.x + (int64_t)i * LD + so, acc);                                  // x+ = A x + B u + w
-        vst(a.xbar + (int64_t)i * LD + so, xb1);
-        vst(a.e + (int64_t)i * LD + so, en);
-      }
-    }
-    if (a.stats != nullptr) {       // per-scenario-slot partial sums in shared memory, reduced once at the end of the kernel
-      __syncwarp();
-      if (slice == 0) {
-#pragma unroll
-        for (int t = 0; t < W; ++t) {
-          if (olive[t]) {
-            const int c = sc0 + t;
-            double nrm2 = 0.0;
-            for (int i = 0; i < n; ++i) { const double xv = wb.om[BK::OM_XP + i][c]; nrm2 = fma(xv, xv, nrm2); }
-            if (ogood[t]) { wb.stacc[0][c] += sqrt(nrm2); wb.stacc[1][c] += nrm2; wb.stacc[2][c] += wb.cost[c]; }
-            if (stt[t] == TZ_STATUS_INFEASIBLE) wb.stacc[3][c] += 1.0;
-            if (stt[t] == TZ_STATUS_MAXITER) wb.stacc[4][c] += 1.0;
-            wb.stacc[5][c] += (double)wb.iters[c];
-            if (stt[t] == TZ_STATUS_NONFINITE) wb.stacc[6][c] += 1.0;
-            wb.stacc[7][c] += 1.0;
-          }
-        }
-      }
-    }
-  }
-}
-
-// Persistent kernel; every WARP loops on its own over tiles of SPW = 32/G scenarios, so there is
-// no CTA barrier after the program has been staged (a CTA barrier made fast warps wait for the
-// slowest ADMM solve of the CTA: 8 % of the samples in profiles/r1_v2_*).
-template <class BK>
-__global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel(const QpProg<BK>* __restrict__ gpg, const Aux ax,
-                                                                const SolverParams sp, const StepArgs a) {
-  constexpr int NZ = BK::NZ, NCL = BK::NCL, N2 = BK::N2, NU = BK::NU, NPAR = BK::NPAR, NAG = BK::NAG, NCHL = BK::NCHL,
-                NCOL = BK::NCOL, TPB = BK::TPB, G = BK::G, SPW = BK::SPW, NW = BK::NW, HP = BK::NPAR / 2;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem<BK>& sm = *reinterpret_cast<Smem<BK>*>(smem_raw);
-  double* tabd = reinterpret_cast<double*>(smem_raw + sizeof(Smem<BK>));
-  const int tid = threadIdx.x;
-  const int n = ax.n, m = ax.m, nv = ax.nv;
-  int* tabi = reinterpret_cast<int*>(tabd + ax.n_dbl + n * n + n * m);
-  {  // stage the program and its tables once per CTA (persistent kernel: amortised over all tiles of this CTA)
-    const double* src = reinterpret_cast<const double*>(gpg);
-    double* dst = reinterpret_cast<double*>(&sm.pg);
-    for (int i = tid; i < (int)(sizeof(QpProg<BK>) / sizeof(double)); i += TPB) dst[i] = src[i];
-    for (int i = tid; i < ax.n_dbl; i += TPB) tabd[i] = ax.tab[i];
-    if (a.x != nullptr) {
-      for (int i = tid; i < n * n; i += TPB) tabd[ax.n_dbl + i] = a.A_true[i];
-      for (int i = tid; i < n * m; i += TPB) tabd[ax.n_dbl + n * n + i] = a.B_true[i];
-    }
-    const int* gi = reinterpret_cast<const int*>(ax.tab + ax.n_dbl);
-    for (int i = tid; i < ax.n_int; i += TPB) tabi[i] = gi[i];
-  }
-  __syncthreads();
-  for (int i = tid; i < BK::NC * NZ; i += TPB) (&sm.Aa[0][0])[i] = sp.alpha * (&sm.pg.A[0][0])[i];
-  __syncthreads();
-  const QpProg<BK>& pg = sm.pg;
-  const int lane = tid & 31, wib = tid >> 5;
-  WarpBuf<BK>& wb = sm.wb[wib];
-  const int g = lane % G;                 // lane within the scenario's group
-  const int sl = lane / G;                // scenario within the warp's tile (solve-phase mapping)
-  const int64_t LD = a.ld;
-  const bool explicit_qp = a.q_in != nullptr;
-  const int64_t ntiles = (a.S + BK::SPO - 1) / BK::SPO;
-  const int64_t nwarps = (int64_t)gridDim.x * BK::WPB;
-  const double inv_alpha = 1.0 / sp.alpha;
-  const double* sCZ = tabd + ax.o_CZ;
-  for (int i = lane; i < TZ_NSTATS * BK::SPO; i += 32) (&wb.stacc[0][0])[i] = 0.0;
-  __syncwarp();
-
-  int buf = 0;
-  const int64_t otile0 = (int64_t)blockIdx.x * BK::WPB + wib;
-  const double* hintp = (sp.warm == 2 && !explicit_qp) ? a.warm : nullptr;
-  if (!explicit_qp && otile0 < ntiles) prefetch_inputs<BK>(wb.pre[0], a, hintp, n, otile0, lane);
-  for (int64_t otile = otile0; otile < ntiles; otile += nwarps, buf ^= 1) {
-    if (!explicit_qp) {        // inputs of the NEXT output tile stream in while this one is solved
-      if (otile + nwarps < ntiles) {
-        prefetch_inputs<BK>(wb.pre[buf ^ 1], a, hintp, n, otile + nwarps, lane);
-        cp_async_wait<1>();
-      } else {
-        cp_async_wait<0>();
-      }
-      __syncwarp();
-    }
-    const double (*pre)[BK::SPO] = wb.pre[buf];
-    const bool zero_first = !explicit_qp && a.ze1 != nullptr && ((blockIdx.x * BK::WPB + wib) & 1);
-    if (zero_first) {
-      if (a.vec2) zero_fill<BK, 2>(ax, a, otile, lane);
-      else zero_fill<BK, 1>(ax, a, otile, lane);
-    }
-   #pragma unroll 1
-   for (int half = 0; half < BK::TPO; ++half) {
-    const int col = half * SPW + sl;        // column of this scenario in the warp's exchange buffers
-    const int64_t s = otile * BK::SPO + col;
-    const bool live = s < a.S;
-    double c0 = 0.0;
-    bool param_ok = true, finite = true;
-    LaneQp<BK> qp;
-
-    if (!explicit_qp) {
-      // ---- parameters p = [xbar0 | e0] (every lane of the group loads them: same sectors)
-      double w[BK::NCOLP];                   // w = [1 | p | |p| | general atoms |Bt p + gam|]
-      w[0] = 1.0;
-      w[BK::NCOLP - 1] = 0.0;
-#pragma unroll
-      for (int j = 0; j < HP; ++j) {
-        double xv = 0.0, ev = 0.0;
-        if (live && j < n) { xv = pre[j][col]; ev = pre[n + j][col]; }
-        w[1 + j] = xv;
-        w[1 + HP + j] = ev;
-        w[1 + NPAR + j] = fabs(xv);
-        w[1 + NPAR + HP + j] = fabs(ev);
-        finite = finite && (fabs(xv) < 1e300) && (fabs(ev) < 1e300);
-        if (g == 0) { wb.om[BK::OM_P + j][col] = xv; wb.om[BK::OM_P + HP + j][col] = ev; }   // kept for the output phase
-      }
-#pragma unroll
-      for (int i = 0; i < NAG; ++i) w[1 + 2 * NPAR + i] = 0.0;
-      if (pg.nag > 0) {
-#pragma unroll
-        for (int i = 0; i < NAG; ++i) {
-          double acc = pg.gam[i];
-#pragma unroll
-          for (int j = 0; j < NPAR; ++j) acc = fma(pg.Bt[i][j], w[1 + j], acc);
-          w[1 + 2 * NPAR + i] = fabs(acc);
-        }
-      }
-      // ---- this lane's rows of the bounds: l = l0 + R w, u = u0 + R w (scaled), kinks
-#pragma unroll
-      for (int k = 0; k < NCL; ++k) {
-        const int i = k * G + g;
-        // (16-byte shared loads, two accumulation chains per row)
-        const double2* Rr = reinterpret_cast<const double2*>(&pg.R[i][0]);
-        double r = 0.0, r1 = 0.0;
-#pragma unroll
-        for (int j = 0; j < BK::NCOLP / 2; ++j) {
-          const double2 c2 = Rr[j];
-          r = fma(c2.x, w[2 * j], r);
-          r1 = fma(c2.y, w[2 * j + 1], r1);
-        }
-        r += r1;
-        if (k < N2) {
-          qp.lo[k < N2 ? k : 0] = pg.l0[i] + r;
-          qp.hi[k < N2 ? k : 0] = pg.u0[i] + r;
-          qp.kink[k < N2 ? k : 0] = pg.kink0[i % BK::NK] + r;
-        } else if (k < N2 + NU) {
-          qp.hi[k < N2 + NU ? k : 0] = pg.u0[i] + r;
-        } else {
-          qp.lo[k - NU] = pg.l0[i] + r;
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < NZ; ++j) {
-        double acc = pg.q0[j];
-        if (pg.has_qp) {
-#pragma unroll
-          for (int k = 0; k < NPAR; ++k) acc = fma(pg.Qp[j][k], w[1 + k], acc);
-        }
-        qp.q[j] = acc;
-      }
-      // ---- parameter-only feasibility rows, split over the group:  sum_j R_j w_j <= 1e-9 max(1, sum_j |R_j| |w_j|)
-      int bad = 0;
-#pragma unroll
-      for (int k = 0; k < NCHL; ++k) {
-        const int i = k * G + g;
-        if (i < pg.nchk) {
-          const double2* Rc = reinterpret_cast<const double2*>(&pg.Rchk[i % BK::NCHK][0]);
-          double r = 0.0, ra = 0.0;
-#pragma unroll
-          for (int j2 = 0; j2 < BK::NCOLP / 2; ++j2) {
-            const double2 c2 = Rc[j2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int j = 2 * j2 + h;
-              const double c = h == 0 ? c2.x : c2.y;
-              r = fma(c, w[j], r);
-              ra = fma(fabs(c), (j >= 1 && j <= NPAR) ? w[j + NPAR] : w[j], ra);    // |w_j|: the |p| columns are already there
-            }
-          }
-          bad |= (r > 1e-9 * fmax(1.0, ra)) ? 1 : 0;
-        }
-      }
-      param_ok = gor<G>(bad) == 0;
-      // ---- cost constant c0(p)
-#pragma unroll
-      for (int j = 0; j < NCOL; ++j) c0 = fma(pg.cc[j], w[j], c0);
-      if (pg.has_cc2) {
-#pragma unroll
-        for (int i = 0; i < NPAR; ++i) {
-          double acc = 0.0;
-#pragma unroll
-          for (int j = 0; j < NPAR; ++j) acc = fma(pg.CC2[i][j], w[1 + j], acc);
-          c0 = fma(acc, w[1 + i], c0);
-        }
-      }
-    } else {
-      // explicit instance: scale the caller's q, l, u  (qbar = c D q, lbar = E l)
-#pragma unroll
-      for (int j = 0; j < NZ; ++j)
-        qp.q[j] = (live && j < pg.nz) ? a.q_in[(int64_t)j * LD + s] * pg.D[j] / pg.cinv : 0.0;
-#pragma unroll
-      for (int k = 0; k < NCL; ++k) {
-        const int i = k * G + g;
-        const int row = pg.row_of_slot[i];
-        const bool rr = live && row >= 0;
-        const double lv = rr ? a.l_in[(int64_t)row * LD + s] / pg.Einv[i] : -INFINITY;
-        const double uv = rr ? a.u_in[(int64_t)row * LD + s] / pg.Einv[i] : INFINITY;
-        if (k < N2) {
-          qp.lo[k < N2 ? k : 0] = lv;
-          qp.hi[k < N2 ? k : 0] = uv;
-          qp.kink[k < N2 ? k : 0] = 0.0;
-        } else if (k < N2 + NU) {
-          qp.hi[k < N2 + NU ? k : 0] = uv;
-        } else {
-          qp.lo[k - NU] = lv;
-        }
-      }
-    }
-    qp.Aa.base = &sm.Aa[g][0];
-    qp.P = pg.P;
-    qp.wk = &pg.wabs[g];
-    qp.sinv = &pg.sing_inv[g];
-    qp.svar = &pg.sing_var[g];
-
-    // ---- ADMM (+ certificate / polish)
-    LaneState<BK> st;
-    bool warm = false;
-    if (sp.warm == 1 && a.warm != nullptr && live) {
-      // layout: [x (NZ) | y (NC, slot-indexed) | activity words (G) | valid flag] x LD
-      warm = (a.warm[(int64_t)(NZ + BK::NC + G) * LD + s] == 1.0);
-      if (warm) {
-#pragma unroll
-        for (int j = 0; j < NZ; ++j) st.x[j] = a.warm[(int64_t)j * LD + s];
-#pragma unroll
-        for (int k = 0; k < NCL; ++k) st.w[k] = a.warm[(int64_t)(NZ + k * G + g) * LD + s];
-        st.act = (uint32_t)__double_as_longlong(a.warm[(int64_t)(NZ + BK::NC + g) * LD + s]);
-        st.switched = true;
-      }
-    }
-    const bool solve_it = live && param_ok && finite;
-    int iters = 0;
-    bool certified = false;
-    int status = TZ_STATUS_OK;
-    // ---- active-set hint (warm_start == 2): the optimal active set of the scenario's previous closed-loop step is
-    // tried first; when its KKT certificate holds the step is solved exactly without a single ADMM iteration
-    const bool use_hint = sp.warm == 2 && a.warm != nullptr;
-    bool hint_ok = false;
-    if (use_hint) {
-      unsigned long long hint = 0ull;
-      if (live) hint = (unsigned long long)__double_as_longlong(pre[4 * n + g][col]);
-      const bool valid = solve_it && gor<G>((hint & kCodeValid) ? 0 : 1) == 0;
-      if (__any_sync(0xffffffffu, valid)) {
-        double lam[NCL], xk[NZ], x0[NZ];
-#pragma unroll
-        for (int k = 0; k < NCL; ++k) lam[k] = 0.0;
-#pragma unroll
-        for (int j = 0; j < NZ; ++j) x0[j] = 0.0;
-        const unsigned long long code = hint & ~kCodeValid;
-        const bool ok = admm_certify<BK>(qp, inv_alpha, sp.polish > 0 ? sp.polish : 3, code, x0, lam, xk);
-        if (ok && valid) {
-#pragma unroll
-          for (int j = 0; j < NZ; ++j) st.x[j] = xk[j];
-#pragma unroll
-          for (int k = 0; k < NCL; ++k) st.w[k] = lam[k];
-          st.code = code;
-          hint_ok = true;
-        }
-      }
-    }
-    if (!__all_sync(0xffffffffu, hint_ok || !solve_it)) {
-      bool cert2 = false;
-      const int st2 = admm_solve<BK>(qp, sp, solve_it && !hint_ok, st, warm, &wb.ysave[0][lane], iters, cert2);
-      if (!hint_ok) { status = st2; certified = cert2; }
-    }
-    if (hint_ok) { certified = true; iters = 0; }
-    if (live && !finite) status = TZ_STATUS_NONFINITE;
-    else if (live && !param_ok) status = TZ_STATUS_INFEASIBLE;
-    const bool good = live && (status == TZ_STATUS_OK || status == TZ_STATUS_MAXITER);
-    if (use_hint) {
-      if (live) a.warm[(int64_t)g * LD + s] = good ? __longlong_as_double((long long)(st.code | kCodeValid)) : 0.0;
-    } else if (good && a.warm != nullptr) {
-      if (g == 0) {
-#pragma unroll
-        for (int j = 0; j < NZ; ++j) a.warm[(int64_t)j * LD + s] = st.x[j];
-        a.warm[(int64_t)(NZ + BK::NC + G) * LD + s] = 1.0;
-      }
-#pragma unroll
-      for (int k = 0; k < NCL; ++k) a.warm[(int64_t)(NZ + k * G + g) * LD + s] = st.w[k];
-      a.warm[(int64_t)(NZ + BK::NC + g) * LD + s] = __longlong_as_double((long long)st.act);
-    }
-    // residual exits are polished; certified exits already are an exact KKT point
-    if (sp.polish && __any_sync(0xffffffffu, good && !certified)) (void)admm_polish<BK>(qp, inv_alpha, st, good && !certified, sp.polish);
-
-    if (explicit_qp) {
-      if (live) {
-        if (g == 0) {
-          a.status[s] = status;
-          if (a.iters) a.iters[s] = iters;
-          if (a.z_out) {
-#pragma unroll
-            for (int j = 0; j < NZ; ++j)
-              if (j < pg.nz) a.z_out[(int64_t)j * LD + s] = good ? pg.D[j] * st.x[j] : NAN;
-          }
-        }
-        if (a.y_out) {
-#pragma unroll
-          for (int k = 0; k < NCL; ++k) {
-            const int i = k * G + g;
-            const int row = pg.row_of_slot[i];
-            if (row >= 0) a.y_out[(int64_t)row * LD + s] = good ? st.w[k] * pg.cinv / pg.Einv[i] : NAN;
-          }
-        }
-      }
-      continue;
-    }
-
-    // ---- objective value (reference `result`, tzddpc/tzddpc.py:367,377; constant terms included, quirk Q7)
-    double kcost = 0.0;
-#pragma unroll
-    for (int k = 0; k < N2; ++k) {
-      double axv = 0.0;
-#pragma unroll
-      for (int j = 0; j < NZ; ++j) axv = fma(qp.Aa[k][j], st.x[j], axv);
-      kcost = fma(qp.wk[k * G], fabs(axv * inv_alpha - qp.kink[k]), kcost);
-    }
-    kcost = gsum<G>(kcost);
-    double cost = NAN;
-    if (good) {
-      double acc = kcost;
-#pragma unroll
-      for (int j = 0; j < NZ; ++j) {
-        double px = 0.0;
-#pragma unroll
-        for (int b = 0; b < NZ; ++b) px = fma(qp.P[j][b], st.x[b], px);
-        acc = fma(0.5 * px + qp.q[j], st.x[j], acc);
-      }
-      cost = fma(acc, pg.cinv, c0);
-    } else if (live && status == TZ_STATUS_INFEASIBLE) {
-      cost = INFINITY;                      // cvxpy returns +inf for an infeasible Minimize (:374)
-    }
-    // ---- hand om = [1 | v | p | centre of Ze[1]], cost, status to the output phase (warp-private buffer)
-    if (g == 0) {
-      wb.om[0][col] = 1.0;
-#pragma unroll
-      for (int j = 0; j < NZ; ++j) wb.om[BK::OM_V + j][col] = (j < nv) ? (good ? pg.D[j] * st.x[j] : NAN) : 0.0;
-      wb.cost[col] = cost;
-      wb.status[col] = live ? status : -1;
-      wb.iters[col] = iters;
-    }
-    __syncwarp();
-    for (int r = g; r < n; r += G) {        // centre of Ze[1]: rows split over the group
-      const double* row = sCZ + r * NW;
-      double acc = 0.0;
-#pragma unroll
-      for (int j = 0; j < NW; ++j) acc = fma(row[j], wb.om[j][col], acc);
-      wb.om[BK::OM_C + r][col] = acc;
-    }
-   }     // solve tiles of this output tile
-    if (explicit_qp) continue;
-    __syncwarp();
-    if (a.vec2) output_phase<BK, 2>(wb, pre, ax, a, tabd, tabi, otile, lane, zero_first);
-    else output_phase<BK, 1>(wb, pre, ax, a, tabd, tabi, otile, lane, zero_first);
-    __syncwarp();     // wb is rewritten by the next tile
-  }
-  if (a.stats != nullptr && a.x != nullptr) {
-    __syncwarp();
-    if (lane < TZ_NSTATS) {
-      double v_ = 0.0;
-#pragma unroll
-      for (int c = 0; c < BK::SPO; ++c) v_ += wb.stacc[lane][c];
-      if (v_ != 0.0) atomicAdd(a.stats + lane, v_);
-    }
-  }
-}
-
-// ---- compiled buckets: <NZ, N2, NU, NL, G, NPAR, NAG, NCHK, MINB> -------------------------------
-#ifndef TZ_B0_MINB
-#define TZ_B0_MINB 3
-#endif
-using B0 = Bucket<2, 1, 3, 3, 4, 10, 2, 12, TZ_B0_MINB>;      // N = 2, m = 1, n <= 5: the three shipped examples (28 row slots)
-using B1 = Bucket<4, 2, 4, 4, 8, 16, 8, 16, 3>;      // generic small   (80 row slots)
-using B2 = Bucket<8, 3, 5, 5, 8, 16, 24, 16, 2>;     // generic medium  (104 row slots, N = 3..4)
+// the larger buckets are compiled in tz_bucket1.cu / tz_bucket2.cu / tz_bucket3.cu
+extern template int launch_bucket<B1>(const TzProgram*, const SolverParams&, const StepArgs&, cudaStream_t);
+extern template int launch_bucket<B2>(const TzProgram*, const SolverParams&, const StepArgs&, cudaStream_t);
+extern template int launch_bucket<B3>(const TzProgram*, const SolverParams&, const StepArgs&, cudaStream_t);
 
 struct RowClasses { int n2 = 0, nu = 0, nl = 0; };
 
@@ -794,20 +130,6 @@ void pack(const TzProgramDesc& d, QpProg<BK>& g) {
 
 using namespace tz;
 
-struct TzProgram {
-  int bucket = -1;
-  void* packed_dev = nullptr;            // device image of QpProg<bucket>, staged into shared memory by every CTA
-  void* aux_dev = nullptr;               // one allocation holding the run-time sized tables
-  Aux aux{};
-  int nz = 0, nc = 0, n = 0, m = 0, N = 0, nv = 0, g1 = 0, npar = 0;
-  int NZ = 0, NC = 0, G = 0;
-  int NW = 0, OM_V = 0, OM_P = 0, OM_C = 0, HP = 0;     // om layout of the bucket (Bucket::OM_*)
-  size_t smem_tab = 0;                   // bytes of the run-time tables staged behind Smem<bucket>
-  int num_sms = 148;
-};
-
-constexpr int kMaxTabBytes = 24 * 1024;
-
 template <class BK>
 static int create_bucket(const TzProgramDesc& d, TzProgram* p, int id) {
   p->bucket = id;
@@ -835,7 +157,7 @@ extern "C" int tz_program_create(const TzProgramDesc* d, TzProgram** out) {
   int rc = TZ_ERANGE;
 #define TZ_TRY(BK, ID) \
   if (rc == TZ_ERANGE && fits<BK>(*d)) rc = create_bucket<BK>(*d, p, ID);
-  TZ_TRY(B0, 0) TZ_TRY(B1, 1) TZ_TRY(B2, 2)
+  TZ_TRY(B0, 0) TZ_TRY(B1, 1) TZ_TRY(B2, 2) TZ_TRY(B3, 3)
 #undef TZ_TRY
   if (rc != TZ_OK) {
     delete p;
@@ -944,25 +266,6 @@ static SolverParams to_params(const TzSolverOpts* o) {
                       d.max_iter, d.check_every, d.polish, d.warm_start, d.cert_first};
 }
 
-template <class BK>
-static int launch_bucket(const TzProgram* p, const SolverParams& sp, const StepArgs& a, cudaStream_t st) {
-  const size_t smem = sizeof(Smem<BK>) + p->smem_tab;
-  static bool configured = false;     // benign race: the attribute is idempotent
-  if (!configured) {
-    TZ_CUDA(cudaFuncSetAttribute(step_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(sizeof(Smem<BK>) + kMaxTabBytes)));
-    configured = true;
-  }
-  // persistent grid: one wave of CTAs (MINB per SM); every warp loops over tiles of SPW scenarios
-  const int64_t ntiles = (a.S + BK::SPO - 1) / BK::SPO;
-  const int64_t need = (ntiles + BK::WPB - 1) / BK::WPB;
-  const int64_t wave = (int64_t)p->num_sms * BK::MINB;
-  const unsigned grid = (unsigned)(need < wave ? need : wave);
-  step_kernel<BK><<<grid, BK::TPB, smem, st>>>(reinterpret_cast<const QpProg<BK>*>(p->packed_dev), p->aux, sp, a);
-  TZ_CUDA(cudaGetLastError());
-  return TZ_OK;
-}
-
 static int launch(const TzProgram* p, const TzSolverOpts* o, const StepArgs& a_in, void* stream) {
   TZ_REQUIRE(p != nullptr, "null program");
   TZ_REQUIRE(a_in.S >= 0, "negative batch");
@@ -981,10 +284,9 @@ static int launch(const TzProgram* p, const TzSolverOpts* o, const StepArgs& a_i
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (p->bucket) {
     case 0: return launch_bucket<B0>(p, sp, a, st);
-#ifndef TZ_DEV_ONLY_B0
     case 1: return launch_bucket<B1>(p, sp, a, st);
     case 2: return launch_bucket<B2>(p, sp, a, st);
-#endif
+    case 3: return launch_bucket<B3>(p, sp, a, st);
   }
   return fail(TZ_EINVAL, "corrupt program handle");
 }
