@@ -178,14 +178,19 @@ class ClockSampler:
         except Exception as e:      # noqa: BLE001
             self.err = repr(e)
 
-    def _poll(self):
+    def sample(self):
+        if not self.ok:
+            return
         nv = self.nv
+        try:
+            self.rows.append((time.perf_counter(), nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
+                              nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)))
+        except Exception:       # noqa: BLE001
+            pass
+
+    def _poll(self):
         while not self._stop:
-            try:
-                self.rows.append((time.perf_counter(), nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
-                                  nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)))
-            except Exception:       # noqa: BLE001
-                pass
+            self.sample()
             time.sleep(0.002)
 
     def stop(self, t0, t1):
@@ -201,6 +206,77 @@ class ClockSampler:
         sm = [r[1] for r in rows]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(self.max_sm), "reasons": reasons,
                 "samples": len(sm)}
+
+
+def batch1_latency(tz, ops, torch, dev, steps_per_graph=12, replays=100):
+    from tzddpc_b200 import _abi, configs
+    cfg = configs.double_integrator()
+    rng = np.random.default_rng(cfg.seed)
+    u_data, x_data = configs.generate_dataset(cfg, rng)
+    ctl = tz.TZDDPC(tz.Data(u_data, x_data), device=dev)
+    ctl.verbose = False
+    Z = tz.Zonotope
+    zon = tz.SystemZonotopes(Z(*cfg.X0), Z(*cfg.U), Z(*cfg.X), Z(*cfg.W))
+    ctl.build_zonotopes(zon)
+    n, m = cfg.n, cfg.m
+    K = configs.lqr_gain(ctl.Mdata.center[:, :n], ctl.Mdata.center[:, n:])
+    ctl.build_zonotopes_theta(zon, K=K)
+    ctl.build_problem(cfg.horizon, tz.StageCost(**cfg.cost), tz.BoxConstraint())
+    prog = ctl._program
+    g1, nv, N = prog.compiled.g1, prog.compiled.nv, cfg.horizon
+    f64 = dict(dtype=torch.float64, device=dev)
+    S = 1
+    x0 = torch.tensor(cfg.X0[0], **f64)[:, None].contiguous()
+    x, xbar, e = x0.clone(), x0.clone(), torch.zeros((n, S), **f64)
+    GW = torch.tensor(cfg.W[1], **f64)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(cfg.seed)
+    beta = torch.sign(torch.rand((steps_per_graph, GW.shape[1], S), generator=gen, **f64) - 0.5)
+    noise = torch.einsum("rg,tgs->trs", GW, beta).contiguous()       # a random vertex of W per step (examples/1.double_integrator_sim.py:85)
+    At, Bt = torch.tensor(cfg.A, **f64), torch.tensor(cfg.B, **f64)
+    status = torch.zeros((steps_per_graph, S), dtype=torch.int32, device=dev)
+    cost = torch.empty((steps_per_graph, S), **f64)
+    v = torch.empty((steps_per_graph, nv, S), **f64)
+    traj = torch.empty((steps_per_graph, (N + 1) * n, S), **f64)
+    ze1 = torch.empty((steps_per_graph, n * (1 + g1), S), **f64)
+    warm = torch.zeros((prog.warm_rows, S), **f64)
+    po = tz.SolverOptions(warm_start=2).pack()
+    h = prog.handle.value
+
+    def run():
+        x.copy_(x0); xbar.copy_(x0); e.zero_(); warm.zero_()      # every replay is the example's 12-step run from X0
+        for t in range(steps_per_graph):
+            ops.closed_loop_step(h, x, xbar, e, noise[t], x0, At, Bt, status[t], cost[t], v[t], traj[t], ze1[t], None, None, warm,
+                                 None, po)
+
+    side = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(side):
+        run()                                   # warm-up on the capture stream
+    torch.cuda.synchronize(dev)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        run()
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize(dev)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(replays):
+        graph.replay()
+    b.record()
+    torch.cuda.synchronize(dev)
+    us = 1e3 * a.elapsed_time(b) / (replays * steps_per_graph)
+    # the same through plain launches of the torch op (host in the loop)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(4):
+        run()
+    torch.cuda.synchronize(dev)
+    us_eager = 1e6 * (time.perf_counter() - t0) / (4 * steps_per_graph)
+    return {"us_per_step": us, "us_per_step_eager_launches": us_eager, "scenarios": 1,
+            "workload": "double_integrator: n=2 m=1 T=100 horizon=2 (examples/1.double_integrator_sim.py), closed loop",
+            "how": f"CUDA graph of the example's {steps_per_graph} closed-loop steps from X0, {replays} replays, CUDA events", "status_ok": bool((status == 0).all().item()),
+            "kernel_bucket": prog.bucket}
 
 
 def run_gpu(args):
@@ -287,6 +363,10 @@ def run_gpu(args):
     for k in range(K_steps):
         step(W_steps + k)
         ev[k + 1].record()
+    if sampler is not None:          # the launches are asynchronous: sample the clocks while the GPU works through them
+        while not ev[-1].query():
+            sampler.sample()
+            time.sleep(0.0005)
     barrier()
     t_wall1 = time.perf_counter()
     elapsed_ms = ev[0].elapsed_time(ev[-1])
@@ -360,6 +440,14 @@ def run_gpu(args):
                        "ms_per_step": 1e3 * dt / Ke, "api": "tz_closed_loop_step_host (pinned host buffers)",
                        "status_ok_frac": float((hstat == 0).double().mean().item())}
 
+    # ---- batch-1 latency (BASELINE.json metric: "us/step at batch 1"): examples/1.double_integrator_sim.py as shipped, one
+    # scenario, the closed loop captured in a CUDA graph (50 fused steps per replay) so that no host work sits between steps
+    if rank == 0 and world == 1 and not args.no_batch1:
+        try:
+            line["batch1"] = batch1_latency(tz, ops, torch, dev)
+        except Exception as exc:      # noqa: BLE001  (diagnostic leg: never fail the headline line)
+            line["batch1"] = {"error": repr(exc)[:200]}
+
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only): the oracle port, one process per core
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = len(os.sched_getaffinity(0)) if args.cpu_cores <= 0 else args.cpu_cores
@@ -393,6 +481,7 @@ def main():
     ap.add_argument("--cpu-cores", type=int, default=0, help="processes of the CPU baseline (0 = all host cores)")
     ap.add_argument("--dump-steps", default="", help="write per-step kernel ms and solver statistics to this .npz (diagnostics)")
     ap.add_argument("--ablate", type=int, default=0, help="diagnostics only: 1 = do not write Ze[1].Z, 2 = nor the trajectory")
+    ap.add_argument("--no-batch1", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

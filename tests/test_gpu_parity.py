@@ -142,3 +142,22 @@ def test_restart_after_an_infeasible_step():
         np.testing.assert_array_equal(out["e"][k + 1, s], 0.0)
         r2 = o.closed_loop(cfg.A, cfg.B, x0[s], noise[k + 1:k + 11, s])
         np.testing.assert_allclose(out["x"][k + 1:k + 12, s], r2["x"], rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("S", [1, 3, 4, 7, 21])
+def test_partial_warps_in_every_solver_mode(pair, S):
+    """Batches that do not fill a warp tile (dead lanes) in all three warm-start modes, with restart: regression test for a
+    short-circuited warp collective in the hint path that only showed with fewer than 8 scenarios."""
+    import tzddpc_b200 as tz
+    cfg, o, t = pair
+    steps = min(cfg.steps, 14)
+    noise = np.repeat(common.noise_for(cfg, steps, 1, np.random.default_rng(0)), S, axis=1)
+    x0 = np.tile(np.asarray(cfg.X0[0], dtype=np.float64), (S, 1))
+    r = o.closed_loop(cfg.A, cfg.B, x0[0], noise[:, 0])
+    ok = r["status"] == 0
+    last = int(np.argmin(ok)) if not ok.all() else steps
+    for mode in (0, 1, 2):
+        out = t.simulate(cfg.A, cfg.B, x0, noise, options=tz.SolverOptions(warm_start=mode), restart=True)
+        for s in (0, S - 1):
+            assert (out["status"][:last, s] == 0).all(), (mode, out["status"][:, s])
+            np.testing.assert_allclose(out["x"][:last + 1, s], r["x"][:last + 1], rtol=1e-6, atol=1e-6)

@@ -211,19 +211,22 @@ __device__ __forceinline__ void output_phase(WarpBuf<BK>& wb, const double (*pre
   }
   // (vector path: S is even, so the scenarios of a pair are live together)
   auto om = [&](int j) { return vld(&wb.om[j][sc0], vt); };
-  if (any_live) {
-    // ---- Ze[1].Z at the optimum (examples/2.pulley_sim.py:96: Zek.Z.value), dense n x (1+g1): zero-fill, then
-    // overwrite the ~12 % entries that are not structurally zero (both writes merge in L2 before reaching HBM)
-    if (a.ze1) {
+  // ---- Ze[1].Z at the optimum (examples/2.pulley_sim.py:96: Zek.Z.value), dense n x (1+g1): zero-fill, then overwrite
+  // the ~12 % entries that are not structurally zero (both writes merge in L2 before reaching HBM).  The warp barrier
+  // between the two sits outside every lane-dependent branch (tiles at the end of a batch have dead lanes).
+  if (a.ze1) {
+    if (any_live && !zero_done) zero_fill<BK, W>(ax, a, tile, lane);
+    __syncwarp();
+    if (any_live) {
       double* base = a.ze1 + so;
-      if (!zero_done) zero_fill<BK, W>(ax, a, tile, lane);
-      __syncwarp();
       const double* coef = tabd + ax.o_coef;
       const int* ent = tabi + ax.o_ent;
       const int* idx = tabi + ax.o_idx;
 #pragma unroll 4
       for (int i = slice; i < ax.n_nz; i += NSL) vstcs(base + (int64_t)ent[i] * LD, vmul(coef[i], om(idx[i])));
     }
+  }
+  if (any_live) {
     // ---- nominal trajectory xbar_0..xbar_N = XB om  (tzddpc/tzddpc.py:166-170)
     if (a.xbar_traj) {
       const int nrows = (ax.N + 1) * n;
@@ -543,7 +546,9 @@ __global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel(const QpProg<BK
     if (use_hint) {
       unsigned long long hint = 0ull;
       if (live) hint = (unsigned long long)__double_as_longlong(pre[4 * n + g][col]);
-      const bool valid = solve_it && gor<G>((hint & kCodeValid) ? 0 : 1) == 0;
+      // (the group reduction is a warp-wide shuffle: every lane must execute it, so no short-circuit on solve_it)
+      const int invalid = gor<G>((hint & kCodeValid) ? 0 : 1);
+      const bool valid = solve_it && invalid == 0;
       if (__any_sync(0xffffffffu, valid)) {
         double lam[NCL], xk[NZ], x0[NZ];
 #pragma unroll
