@@ -127,3 +127,34 @@ def test_closed_loop_properties_full_size(big):
     # every scenario saw the same x0 and the loop is deterministic: scenario 0 against the oracle
     ro = o.closed_loop(cfg.A, cfg.B, x0[0], noise[:, 0])
     np.testing.assert_allclose(out["x"][:, 0], ro["x"], rtol=1e-6, atol=1e-6)
+
+
+def test_bench_configuration_hint_mode_equals_cold(cuda_lib):
+    """What bench.py times: 65,536 scenarios of the 5-dim example in closed loop with the active-set hint and restart of
+    infeasible scenarios, through the wave in which the example runs into its constraints (steps ~45-66).  The hint only
+    changes the work: states, inputs and statuses equal those of the cold solver, step by step."""
+    import tzddpc_b200 as tz
+    cfg = configs.fivedim()
+    u, x = common.dataset(cfg)
+    o, K = common.make_oracle(cfg, u, x)
+    t = common.make_product(cfg, u, x, K)
+    S, steps = 65536, 72
+    rng = np.random.default_rng(8)
+    noise = common.noise_for(cfg, steps, S, rng)
+    x0 = np.tile(np.asarray(cfg.X0[0], dtype=np.float64), (S, 1))
+    cold = t.simulate(cfg.A, cfg.B, x0, noise, restart=True)
+    hot = t.simulate(cfg.A, cfg.B, x0, noise, restart=True, options=tz.SolverOptions(warm_start=2))
+    assert np.array_equal(cold["status"], hot["status"])
+    assert set(np.unique(cold["status"])) <= {0, 2}
+    assert (cold["status"] == 2).sum() > S // 2                      # the wave is inside the window
+    np.testing.assert_allclose(hot["x"], cold["x"], rtol=1e-7, atol=1e-7)
+    np.testing.assert_allclose(hot["u"], cold["u"], rtol=1e-7, atol=1e-7, equal_nan=True)
+    assert hot["iters"].mean() < 0.2 * cold["iters"].mean()
+    # restarted scenarios are back at x0 right after their infeasible step
+    k, s = np.argwhere(cold["status"] == 2)[0]
+    np.testing.assert_array_equal(hot["x"][k + 1, s], x0[s])
+    # scenario 0 against the oracle up to its own infeasible step
+    r = o.closed_loop(cfg.A, cfg.B, x0[0], noise[:, 0])
+    last = int(np.argmax(r["status"] == 2)) if (r["status"] == 2).any() else steps
+    np.testing.assert_allclose(hot["x"][:last + 1, 0], r["x"][:last + 1], rtol=1e-6, atol=1e-6)
+    assert hot["status"][last, 0] == 2 if last < steps else True
