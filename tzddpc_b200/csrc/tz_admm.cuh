@@ -410,7 +410,7 @@ __device__ __forceinline__ bool admm_certify(const LaneQp<BK>& qp, double inv_al
 template <class BK>
 __device__ int admm_solve(const LaneQp<BK>& qp, const SolverParams& sp, bool live, LaneState<BK>& st, bool warm,
                           double* __restrict__ ysave /* lane-private shared scratch, element k at [k * 32] */,
-                          int& iters_out, bool& certified) {
+                          int& iters_out, bool& certified, bool presolved_in = false) {
   constexpr int NZ = BK::NZ, NCL = BK::NCL, N2 = BK::N2, G = BK::G;
   const double alpha = sp.alpha, sigma = sp.sigma, oma = 1.0 - sp.alpha, inv_alpha = 1.0 / sp.alpha;
   const double rq_base = sp.rho * inv_alpha, rq_act = sp.rho * sp.rho_act * inv_alpha,
@@ -465,7 +465,7 @@ __device__ int admm_solve(const LaneQp<BK>& qp, const SolverParams& sp, bool liv
   int next_upd = 2, gap = 2;
   int next_cert = sp.cert_first > 0 ? sp.cert_first : sp.max_iter + 1, cert_gap = 2;     // tests at cert_first + {0, 2, 5, 10, 18, ...}
   certified = false;
-  bool presolved = false;
+  bool presolved = presolved_in;
   const int check_every = sp.check_every > 0 ? sp.check_every : 1;
   int until_check = check_every;
   bool have_prev = false;             // ysave holds the duals of the previous check

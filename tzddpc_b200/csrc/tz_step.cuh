@@ -568,8 +568,16 @@ __global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel(const QpProg<BK
       }
     }
     if (!__all_sync(0xffffffffu, hint_ok || !solve_it)) {
+      // no (valid) hint: is the program infeasible outright?  (singleton presolve, exact; saves the ADMM iterations and
+      // the failed certificate an infeasible scenario would otherwise need before the same test inside admm_solve)
+      const bool inf = singleton_infeasible<BK>(qp);
+      const bool run = solve_it && !hint_ok && !inf;
       bool cert2 = false;
-      const int st2 = admm_solve<BK>(qp, sp, solve_it && !hint_ok, st, warm, &wb.ysave[0][lane], iters, cert2);
+      int st2 = TZ_STATUS_INFEASIBLE;
+      if (__any_sync(0xffffffffu, run)) {
+        const int st3 = admm_solve<BK>(qp, sp, run, st, warm, &wb.ysave[0][lane], iters, cert2, true);
+        if (run) st2 = st3;
+      }
       if (!hint_ok) { status = st2; certified = cert2; }
     }
     if (hint_ok) { certified = true; iters = 0; }
