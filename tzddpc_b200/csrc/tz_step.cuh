@@ -686,9 +686,9 @@ __global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel(const QpProg<BK
 #define TZ_B0_MINB 3
 #endif
 using B0 = Bucket<2, 1, 3, 3, 4, 10, 2, 12, TZ_B0_MINB>;      // N = 2, m = 1, n <= 5: the three shipped examples (28 row slots)
-using B1 = Bucket<4, 2, 4, 4, 8, 16, 8, 16, 3>;      // generic small   (80 row slots)
-using B2 = Bucket<8, 3, 5, 5, 8, 16, 24, 16, 2>;     // generic medium  (104 row slots, N = 3..4)
-using B3 = Bucket<12, 1, 4, 4, 8, 16, 24, 16, 1>;    // large           (72 row slots, nz <= 12: N = 5 of the complexity sweep)
+using B1 = Bucket<4, 2, 4, 4, 8, 16, 8, 32, 3>;      // generic small   (80 row slots)
+using B2 = Bucket<8, 3, 5, 5, 8, 16, 24, 32, 2>;     // generic medium  (104 row slots, N = 3..4)
+using B3 = Bucket<12, 1, 4, 4, 8, 16, 24, 32, 1>;    // large           (72 row slots, nz <= 12: N = 5 of the complexity sweep)
 
 }  // namespace tz
 
