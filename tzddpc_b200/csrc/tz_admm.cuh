@@ -258,6 +258,8 @@ __device__ __forceinline__ bool singleton_infeasible(const LaneQp<BK>& qp) {
 //   4 / 5 |.| row above / below its kink (linear cost)          6 equality row (lower == upper)
 // bit 63 marks a valid word when it travels through the hint buffer.
 constexpr unsigned long long kCodeValid = 1ull << 63;
+// bit 62: the word was copied from the scenario's run-start hint when it restarted (the state is a run's first state)
+constexpr unsigned long long kCodeFresh = 1ull << 62;
 
 template <class BK>
 __device__ __forceinline__ unsigned long long active_code(const LaneQp<BK>& qp, const double (&z)[BK::NCL]) {

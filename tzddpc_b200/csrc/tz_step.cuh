@@ -543,9 +543,11 @@ __global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel(const QpProg<BK
     // tried first; when its KKT certificate holds the step is solved exactly without a single ADMM iteration
     const bool use_hint = sp.warm == 2 && a.warm != nullptr;
     bool hint_ok = false;
+    bool fresh = false;             // first step of a run (or no usable hint): its active set becomes the run-start hint
     if (use_hint) {
       unsigned long long hint = 0ull;
       if (live) hint = (unsigned long long)__double_as_longlong(pre[4 * n + g][col]);
+      fresh = !(hint & kCodeValid) || (hint & kCodeFresh);
       // (the group reduction is a warp-wide shuffle: every lane must execute it, so no short-circuit on solve_it)
       const int invalid = gor<G>((hint & kCodeValid) ? 0 : 1);
       const bool valid = solve_it && invalid == 0;
@@ -555,7 +557,7 @@ __global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel(const QpProg<BK
         for (int k = 0; k < NCL; ++k) lam[k] = 0.0;
 #pragma unroll
         for (int j = 0; j < NZ; ++j) x0[j] = 0.0;
-        const unsigned long long code = hint & ~kCodeValid;
+        const unsigned long long code = hint & ~(kCodeValid | kCodeFresh);
         const bool ok = admm_certify<BK>(qp, inv_alpha, sp.polish > 0 ? sp.polish : 3, code, x0, lam, xk);
         if (ok && valid) {
 #pragma unroll
@@ -585,7 +587,19 @@ __global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel(const QpProg<BK
     else if (live && !param_ok) status = TZ_STATUS_INFEASIBLE;
     const bool good = live && (status == TZ_STATUS_OK || status == TZ_STATUS_MAXITER);
     if (use_hint) {
-      if (live) a.warm[(int64_t)g * LD + s] = good ? __longlong_as_double((long long)(st.code | kCodeValid)) : 0.0;
+      // hint rows [0, G): the active set for the next step; rows [G, 2G): the active set of the run's first step, which
+      // becomes the hint again when the scenario restarts from x_restart (same state, same program, same active set)
+      if (live) {
+        unsigned long long wnext = 0ull;
+        if (good) {
+          wnext = st.code | kCodeValid;
+          if (fresh) a.warm[(int64_t)(G + g) * LD + s] = __longlong_as_double((long long)wnext);
+        } else if (a.x_restart != nullptr) {
+          const unsigned long long h0 = (unsigned long long)__double_as_longlong(a.warm[(int64_t)(G + g) * LD + s]);
+          wnext = (h0 & kCodeValid) ? (h0 | kCodeFresh) : 0ull;
+        }
+        a.warm[(int64_t)g * LD + s] = __longlong_as_double((long long)wnext);
+      }
     } else if (good && a.warm != nullptr) {
       if (g == 0) {
 #pragma unroll
