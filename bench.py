@@ -392,7 +392,10 @@ def run_gpu(args):
                        "l2": f"per-step HBM traffic {bstep * S / 1e6:.0f} MB > 126 MB L2 (inputs larger than L2)",
                        "solver": {"warm_start": {0: "cold", 1: "previous (x, y)", 2: "active-set hint of the previous step (KKT-certified)"}[int(args.warm_start)],
                                   "eps": opts.eps_abs, "polish": True, "certificate": "active-set KKT"},
-                       "kernel_bucket": prog.bucket},
+                       "kernel_bucket": prog.bucket,
+                       "episodes": "a scenario whose step is infeasible (the reference raises: end of that run) starts a new "
+                                   "run from x0; the 5-dim example reaches that point every ~62 steps",
+                       "noise": f"{nring} pre-drawn realisations per scenario, cycled"},
             "gpu_launches": K_steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "bytes_per_scenario_step": bstep,
