@@ -356,21 +356,38 @@ def run_gpu(args):
     for t in range(W_steps):
         step(t)
     barrier()
+    # The K timed steps are captured in ONE CUDA graph (K kernel nodes, no host work between steps), so that the number
+    # does not depend on how fast this process's Python loop launches (8 ranks share the host's cores).  --dump-steps
+    # (diagnostics) times eager launches step by step instead.
+    use_graph = not args.no_graph and not args.dump_steps
+    graph = None
+    if use_graph:
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            for k in range(K_steps):
+                step(W_steps + k)
+        barrier()
     sampler = ClockSampler(local) if rank == 0 else None
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K_steps + 1)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range((1 if use_graph else K_steps) + 1)]
     t_wall0 = time.perf_counter()
     ev[0].record()
-    for k in range(K_steps):
-        step(W_steps + k)
-        ev[k + 1].record()
-    if sampler is not None:          # the launches are asynchronous: sample the clocks while the GPU works through them
+    if use_graph:
+        graph.replay()
+        ev[1].record()
+    else:
+        for k in range(K_steps):
+            step(W_steps + k)
+            ev[k + 1].record()
+    if sampler is not None:          # the work is asynchronous: sample the clocks while the GPU goes through it
         while not ev[-1].query():
             sampler.sample()
             time.sleep(0.0005)
     barrier()
     t_wall1 = time.perf_counter()
     elapsed_ms = ev[0].elapsed_time(ev[-1])
-    kern_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(K_steps)]
+    kern_ms = [elapsed_ms / K_steps] if use_graph else [ev[k].elapsed_time(ev[k + 1]) for k in range(K_steps)]
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     elapsed_ms = shard.max_over_ranks(elapsed_ms, dev)
     # final statistics: the only collective of the path, one all-reduce after the loop
@@ -396,7 +413,7 @@ def run_gpu(args):
                        "episodes": "a scenario whose step is infeasible (the reference raises: end of that run) starts a new "
                                    "run from x0; the 5-dim example reaches that point every ~62 steps",
                        "noise": f"{nring} pre-drawn realisations per scenario, cycled"},
-            "gpu_launches": K_steps,
+            "gpu_launches": K_steps, "launch_mode": "one CUDA graph of the K steps" if use_graph else "eager",
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "bytes_per_scenario_step": bstep,
                          "kernel_ms_avg": avg_kernel_ms, "kernel": "tz::step_kernel_param"},
@@ -484,6 +501,7 @@ def main():
     ap.add_argument("--cpu-cores", type=int, default=0, help="processes of the CPU baseline (0 = all host cores)")
     ap.add_argument("--dump-steps", default="", help="write per-step kernel ms and solver statistics to this .npz (diagnostics)")
     ap.add_argument("--ablate", type=int, default=0, help="diagnostics only: 1 = do not write Ze[1].Z, 2 = nor the trajectory")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of one CUDA graph of the K steps")
     ap.add_argument("--no-batch1", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
