@@ -220,6 +220,28 @@ int tz_identify(int64_t S, int32_t T, int32_t n, int32_t m, int32_t gW,
                 const double* X, const double* U, const double* WZ, const double* K,
                 double* AB, double* dAB, double* dK, double* Pinv, int32_t* status, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Counter-based random numbers (Philox4x32-10): key = seed, counter = (global scenario index, t, purpose, block).
+ * The draws do not depend on how scenarios are sharded over GPUs (pass the shard's first scenario as scenario_offset);
+ * oracle/philox.py restates the stream in numpy.
+ * ------------------------------------------------------------------------------------ */
+
+/* One block of the generator, on the host (for tests and bindings that want to reproduce the stream). */
+void tz_philox4x32_10_host(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t* out4);
+
+/* Closed-loop noise of step t:  w = c_W + G_W beta,  beta ~ U[-1,1)^gW (W.sample(), examples/2.pulley_sim.py:92) or, with
+ * vertex != 0, beta in {-1,+1}^gW (a random vertex of W, examples/1.double_integrator_sim.py:85).  out: n x S (SoA, ld >= S). */
+int tz_sample_noise(int64_t S, int64_t ld, int32_t n, int32_t gW, const double* WZ, int32_t vertex, uint64_t seed,
+                    int64_t scenario_offset, uint32_t t, double* out, void* stream);
+
+/* generate_trajectories of examples/utils.py:6-45, batched over S data sets (one trajectory each), on the device:
+ *   x_0 ~ X0, u_t ~ U, x_{t+1} = A x_t + B u_t + (random vertex of W); the first returned state row is the origin (the
+ *   reference's quirk).  X0Z: n x (1+g0), UZ: m x (1+gU), WZ: n x (1+gW) as [centre, generators].
+ *   U: S x T x m, X: S x T x n -- the layout tz_identify reads. */
+int tz_generate_trajectories(int64_t S, int32_t T, int32_t n, int32_t m, int32_t g0, int32_t gU, int32_t gW,
+                             const double* A, const double* B, const double* X0Z, const double* UZ, const double* WZ,
+                             uint64_t seed, int64_t scenario_offset, double* U, double* X, void* stream);
+
 /* Generic batched ADMM QP on an explicit instance batch (the solver stage alone):
  *   minimise 0.5 z'Pz + q_s'z  s.t. l_s <= A z <= u_s   with (P, A) from `prog`
  *   q: nz x S, l,u: nc x S (SoA, unscaled);  z: nz x S, y: nc x S. */

@@ -41,7 +41,7 @@ _lib = None
 EXPORTS = ["tz_version", "tz_last_error", "tz_device_cc", "tz_program_create", "tz_program_destroy", "tz_program_bucket", "tz_program_warm_rows",
            "tz_solver_opts_default", "tz_solve", "tz_closed_loop_step", "tz_closed_loop_step_host_scratch_bytes",
            "tz_closed_loop_step_host", "tz_interval_hull", "tz_reach_step", "tz_girard_reduce", "tz_tube_rollout",
-           "tz_identify", "tz_qp_solve"]
+           "tz_identify", "tz_qp_solve", "tz_philox4x32_10_host", "tz_sample_noise", "tz_generate_trajectories"]
 
 
 def lib() -> C.CDLL:
@@ -84,6 +84,13 @@ def lib() -> C.CDLL:
     L.tz_girard_reduce.argtypes = [i64, i32, i32, dbl, i32, vp, i32, vp, vp, vp]
     L.tz_tube_rollout.restype = C.c_int
     L.tz_tube_rollout.argtypes = [i64] + [i32] * 7 + [dbl, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp]
+    u32, u64 = C.c_uint32, C.c_uint64
+    L.tz_philox4x32_10_host.restype = None
+    L.tz_philox4x32_10_host.argtypes = [u32] * 6 + [C.POINTER(u32)]
+    L.tz_sample_noise.restype = C.c_int
+    L.tz_sample_noise.argtypes = [i64, i64, i32, i32, vp, i32, u64, i64, u32, vp, vp]
+    L.tz_generate_trajectories.restype = C.c_int
+    L.tz_generate_trajectories.argtypes = [i64] + [i32] * 6 + [vp] * 5 + [u64, i64, vp, vp, vp]
     L.tz_identify.restype = C.c_int
     L.tz_identify.argtypes = [i64, i32, i32, i32, i32] + [vp] * 10
     L.tz_qp_solve.restype = C.c_int

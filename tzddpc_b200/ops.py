@@ -175,6 +175,34 @@ def tube_rollout(CK: Tensor, GK: Tensor, GD: Tensor, Z0: Tensor, XU: Tensor, W: 
     return Zf, gf, lo, hi
 
 
+@torch.library.custom_op("tzddpc::sample_noise", mutates_args=(), device_types="cuda")
+def sample_noise(WZ: Tensor, S: int, vertex: bool, seed: int, scenario_offset: int, t: int) -> Tensor:
+    """Closed-loop noise of step t for S scenarios: (n, S) = c_W + G_W beta, Philox stream keyed by `seed`, counter
+    (scenario_offset + s, t).  W.sample() (examples/2.pulley_sim.py:92) or a random vertex (examples/1.double_integrator_sim.py:85)."""
+    _chk(WZ)
+    n = WZ.shape[0]
+    out = torch.empty((n, S), dtype=torch.float64, device=WZ.device)
+    with torch.cuda.device(WZ.device):
+        rc = _abi.lib().tz_sample_noise(S, S, n, WZ.shape[1] - 1, _ptr(WZ), int(vertex), seed, scenario_offset, t, _ptr(out), _stream(WZ))
+    _abi.check(rc, "tz_sample_noise")
+    return out
+
+
+@torch.library.custom_op("tzddpc::generate_trajectories", mutates_args=(), device_types="cuda")
+def generate_trajectories(A: Tensor, B: Tensor, X0Z: Tensor, UZ: Tensor, WZ: Tensor, S: int, T: int, seed: int,
+                          scenario_offset: int) -> Tuple[Tensor, Tensor]:
+    """examples/utils.py:6-45 batched over S data sets on the device.  Returns U (S, T, m), X (S, T, n)."""
+    _chk(A), _chk(B), _chk(X0Z), _chk(UZ), _chk(WZ)
+    n, m = B.shape
+    U = torch.empty((S, T, m), dtype=torch.float64, device=A.device)
+    X = torch.empty((S, T, n), dtype=torch.float64, device=A.device)
+    with torch.cuda.device(A.device):
+        rc = _abi.lib().tz_generate_trajectories(S, T, n, m, X0Z.shape[1] - 1, UZ.shape[1] - 1, WZ.shape[1] - 1, _ptr(A), _ptr(B),
+                                                 _ptr(X0Z), _ptr(UZ), _ptr(WZ), seed, scenario_offset, _ptr(U), _ptr(X), _stream(A))
+    _abi.check(rc, "tz_generate_trajectories")
+    return U, X
+
+
 @torch.library.custom_op("tzddpc::identify", mutates_args=(), device_types="cuda")
 def identify(X: Tensor, U: Tensor, WZ: Tensor, K: Optional[Tensor], want_pinv: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
     """X: (S, T, n), U: (S, T, m), WZ: (n, 1+gW), K: (S, m, n).  Returns AB (S,n,n+m), dAB, dK (S,n,n), Pinv, status.

@@ -273,10 +273,14 @@ class TZDDPC(object):
         return float(cost[0]), v[0], xbar[0], tube
 
     # ---- batched closed loop (examples/2.pulley_sim.py:62-103, one scenario per column) --------
-    def simulate(self, A_true: np.ndarray, B_true: np.ndarray, x0: np.ndarray, noise, keep_tubes: bool = False,
-                 options: Optional[SolverOptions] = None, restart: bool = False):
+    def simulate(self, A_true: np.ndarray, B_true: np.ndarray, x0: np.ndarray, noise=None, keep_tubes: bool = False,
+                 options: Optional[SolverOptions] = None, restart: bool = False, steps: Optional[int] = None,
+                 seed: Optional[int] = None, vertex_noise: bool = False, scenario_offset: int = 0):
         """Run the closed loop for S scenarios in lock step.
-        x0: (S, n); noise: (steps, S, n) array or CUDA tensor (steps, n, S).
+        x0: (S, n); noise: (steps, S, n) array or CUDA tensor (steps, n, S) -- or None with `steps` and `seed`: the noise
+        w_t = W.sample() (examples/2.pulley_sim.py:92; a random vertex of W with vertex_noise, examples/1.double_integrator_sim.py:85)
+        is then drawn on the device from the Philox stream (seed, scenario_offset + scenario, t), so that a scenario sees the
+        same realisation however the batch is sharded over GPUs.
         restart: an infeasible scenario (the reference raises and the run ends, tzddpc/tzddpc.py:374-375) starts a
         new run from its x0 instead of keeping its state.
         Returns dict with x (steps+1, S, n), xbar, e, u, v0, cost (steps, S), status (steps, S), stats (steps, 8)."""
@@ -285,7 +289,11 @@ class TZDDPC(object):
         o = options or self.solver_options
         x0 = np.atleast_2d(np.asarray(x0, dtype=np.float64))
         S = x0.shape[0]
-        if isinstance(noise, torch.Tensor):
+        if noise is None:
+            assert steps is not None and seed is not None, "give either `noise` or `steps` and `seed`"
+            WZ = self._t(self.zonotopes.W.Z)
+            w = torch.stack([ops.sample_noise(WZ, S, bool(vertex_noise), int(seed), int(scenario_offset), t) for t in range(steps)])
+        elif isinstance(noise, torch.Tensor):
             w = noise
         else:
             w = self._t(np.transpose(np.asarray(noise, dtype=np.float64), (0, 2, 1)))
