@@ -337,39 +337,46 @@ __global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel(const QpProg<BK
   const int tid = threadIdx.x;
   const int n = ax.n, m = ax.m, nv = ax.nv;
   int* tabi = reinterpret_cast<int*>(tabd + ax.n_dbl + n * n + n * m);
-  {  // stage the program and its tables once per CTA (persistent kernel: amortised over all tiles of this CTA)
-    const double* src = reinterpret_cast<const double*>(gpg);
-    double* dst = reinterpret_cast<double*>(&sm.pg);
-    for (int i = tid; i < (int)(sizeof(QpProg<BK>) / sizeof(double)); i += TPB) dst[i] = src[i];
-    for (int i = tid; i < ax.n_dbl; i += TPB) tabd[i] = ax.tab[i];
+  const int lane = tid & 31, wib = tid >> 5;
+  WarpBuf<BK>& wb = sm.wb[wib];
+  const bool explicit_qp = a.q_in != nullptr;
+  const int64_t ntiles = (a.S + BK::SPO - 1) / BK::SPO;
+  const int64_t nwarps = (int64_t)gridDim.x * BK::WPB;
+  const int64_t otile0 = (int64_t)blockIdx.x * BK::WPB + wib;
+  const double* hintp = (sp.warm == 2 && !explicit_qp) ? a.warm : nullptr;
+  // inputs of this warp's first output tile: in flight while the program is staged (cp.async group 0)
+  if (!explicit_qp && otile0 < ntiles) prefetch_inputs<BK>(wb.pre[0], a, hintp, n, otile0, lane);
+  {  // stage the program and its tables once per CTA (persistent kernel: amortised over all tiles of this CTA): 16-byte
+     // cp.async copies, all in flight at once (a load/store loop serialised ~10 dependent round trips to L2 per thread)
+    const char* src = reinterpret_cast<const char*>(gpg);
+    char* dst = reinterpret_cast<char*>(&sm.pg);
+    static_assert(sizeof(QpProg<BK>) % 8 == 0, "QpProg must be a whole number of doubles");
+    constexpr int NCH = (int)(sizeof(QpProg<BK>) / 16);
+    for (int i = tid; i < NCH; i += TPB) cp_async16(dst + 16 * i, src + 16 * i);
+    if (tid == 0 && (sizeof(QpProg<BK>) % 16) != 0) cp_async8(dst + 16 * NCH, src + 16 * NCH);
+    for (int i = tid; i < ax.n_dbl; i += TPB) cp_async8(tabd + i, ax.tab + i);
     if (a.x != nullptr) {
-      for (int i = tid; i < n * n; i += TPB) tabd[ax.n_dbl + i] = a.A_true[i];
-      for (int i = tid; i < n * m; i += TPB) tabd[ax.n_dbl + n * n + i] = a.B_true[i];
+      for (int i = tid; i < n * n; i += TPB) cp_async8(tabd + ax.n_dbl + i, a.A_true + i);
+      for (int i = tid; i < n * m; i += TPB) cp_async8(tabd + ax.n_dbl + n * n + i, a.B_true + i);
     }
     const int* gi = reinterpret_cast<const int*>(ax.tab + ax.n_dbl);
     for (int i = tid; i < ax.n_int; i += TPB) tabi[i] = gi[i];
+    cp_async_commit();
+    cp_async_wait<0>();
   }
   __syncthreads();
   for (int i = tid; i < BK::NC * NZ; i += TPB) (&sm.Aa[0][0])[i] = sp.alpha * (&sm.pg.A[0][0])[i];
   __syncthreads();
   const QpProg<BK>& pg = sm.pg;
-  const int lane = tid & 31, wib = tid >> 5;
-  WarpBuf<BK>& wb = sm.wb[wib];
   const int g = lane % G;                 // lane within the scenario's group
   const int sl = lane / G;                // scenario within the warp's tile (solve-phase mapping)
   const int64_t LD = a.ld;
-  const bool explicit_qp = a.q_in != nullptr;
-  const int64_t ntiles = (a.S + BK::SPO - 1) / BK::SPO;
-  const int64_t nwarps = (int64_t)gridDim.x * BK::WPB;
   const double inv_alpha = 1.0 / sp.alpha;
   const double* sCZ = tabd + ax.o_CZ;
   for (int i = lane; i < TZ_NSTATS * BK::SPO; i += 32) (&wb.stacc[0][0])[i] = 0.0;
   __syncwarp();
 
   int buf = 0;
-  const int64_t otile0 = (int64_t)blockIdx.x * BK::WPB + wib;
-  const double* hintp = (sp.warm == 2 && !explicit_qp) ? a.warm : nullptr;
-  if (!explicit_qp && otile0 < ntiles) prefetch_inputs<BK>(wb.pre[0], a, hintp, n, otile0, lane);
   for (int64_t otile = otile0; otile < ntiles; otile += nwarps, buf ^= 1) {
     if (!explicit_qp) {        // inputs of the NEXT output tile stream in while this one is solved
       if (otile + nwarps < ntiles) {
