@@ -54,7 +54,10 @@ struct Bucket {
   static constexpr int OM_V = 1, OM_P = 1 + NZ, NW = 1 + NZ + NPAR;
   static constexpr int OM_C = NW, OM_XP = NW + HP, KOM = NW + 2 * HP;
   static constexpr int PRE_ROWS = 4 * HP + G;         // prefetched input rows of an output tile: [xbar0 | e0 | x | noise | hint words]
-  static constexpr int NCOLP = (NCOL + 1) & ~1;       // row pitch of R / Rchk (even: 16-byte aligned rows)
+  static constexpr int NCOL2 = (NCOL + 1) / 2;        // 16-byte pairs of columns per row of R / Rchk
+  // row pitch of R / Rchk: even (16-byte aligned rows) and not a multiple of 64 bytes, so that the rows read by the G
+  // lanes of a group (16 bytes each, one LDS.128) fall into different banks (a 192-byte pitch gave a 2-way conflict)
+  static constexpr int NCOLP = 2 * NCOL2 + ((2 * NCOL2) % 8 == 0 ? 2 : 0);
   static_assert(NCL <= 32 && (G & (G - 1)) == 0 && G <= 32 && N2 >= 1 && NAG >= 1, "bad bucket");
 };
 

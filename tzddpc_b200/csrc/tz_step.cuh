@@ -405,9 +405,9 @@ __global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel(const QpProg<BK
 
     if (!explicit_qp) {
       // ---- parameters p = [xbar0 | e0] (every lane of the group loads them: same sectors)
-      double w[BK::NCOLP];                   // w = [1 | p | |p| | general atoms |Bt p + gam|]
+      double w[2 * BK::NCOL2];               // w = [1 | p | |p| | general atoms |Bt p + gam|] (+ a zero pad)
       w[0] = 1.0;
-      w[BK::NCOLP - 1] = 0.0;
+      if constexpr (2 * BK::NCOL2 > NCOL) w[2 * BK::NCOL2 - 1] = 0.0;
 #pragma unroll
       for (int j = 0; j < HP; ++j) {
         double xv = 0.0, ev = 0.0;
@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel(const QpProg<BK
         const double2* Rr = reinterpret_cast<const double2*>(&pg.R[i][0]);
         double r = 0.0, r1 = 0.0;
 #pragma unroll
-        for (int j = 0; j < BK::NCOLP / 2; ++j) {
+        for (int j = 0; j < BK::NCOL2; ++j) {
           const double2 c2 = Rr[j];
           r = fma(c2.x, w[2 * j], r);
           r1 = fma(c2.y, w[2 * j + 1], r1);
@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel(const QpProg<BK
           const double2* Rc = reinterpret_cast<const double2*>(&pg.Rchk[i % BK::NCHK][0]);
           double r = 0.0, ra = 0.0;
 #pragma unroll
-          for (int j2 = 0; j2 < BK::NCOLP / 2; ++j2) {
+          for (int j2 = 0; j2 < BK::NCOL2; ++j2) {
             const double2 c2 = Rc[j2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
