@@ -279,6 +279,72 @@ def batch1_latency(tz, ops, torch, dev, steps_per_graph=12, replays=100):
             "kernel_bucket": prog.bucket}
 
 
+def datasets_leg(args, tz, ops, torch, dev, cfg, noise, nring):
+    """The default workload with the data-set axis: D data sets (seeds cfg.seed + 101 d) of the same plant, one identified
+    model / gain / program each (the reference: one TZDDPC object per data set), S / D noise realisations per data set."""
+    from tzddpc_b200 import _abi, configs
+    D, S = args.datasets, args.scenarios
+    per = S // D
+    assert per % 16 == 0 and per * D == S, "scenarios must split into D blocks of a multiple of 16"
+    n, m, N = cfg.n, cfg.m, cfg.horizon
+    Z = tz.Zonotope
+    zon = tz.SystemZonotopes(Z(*cfg.X0), Z(*cfg.U), Z(*cfg.X), Z(*cfg.W))
+    t0 = time.perf_counter()
+    ctls = []
+    for d in range(D):
+        u_data, x_data = configs.generate_dataset(cfg, np.random.default_rng(cfg.seed + 101 * d))
+        c = tz.TZDDPC(tz.Data(u_data, x_data), device=dev)
+        c.verbose = False
+        c.build_zonotopes(zon)
+        Kg = configs.lqr_gain(c.Mdata.center[:, :n], c.Mdata.center[:, n:])
+        c.build_zonotopes_theta(zon, K=Kg)
+        c.build_problem(N, tz.StageCost(**cfg.cost), tz.BoxConstraint(**cfg.box) if cfg.box else tz.BoxConstraint())
+        ctls.append(c)
+    ens = tz.TZDDPCEnsemble(ctls, per)
+    setup_s = time.perf_counter() - t0
+    prog = ens._program
+    g1, nv = prog.compiled.g1, prog.compiled.nv
+    f64 = dict(dtype=torch.float64, device=dev)
+    x0 = torch.tensor(cfg.X0[0], **f64)
+    x = x0[:, None].repeat(1, S).contiguous()
+    xbar, xr, e = x.clone(), x.clone(), torch.zeros((n, S), **f64)
+    At, Bt = torch.tensor(cfg.A, **f64), torch.tensor(cfg.B, **f64)
+    ze1 = torch.empty((n * (1 + g1), S), **f64)
+    traj = torch.empty(((N + 1) * n, S), **f64)
+    vbuf, cost = torch.empty((nv, S), **f64), torch.empty(S, **f64)
+    status = torch.zeros(S, dtype=torch.int32, device=dev)
+    warm = torch.zeros((prog.warm_rows, S), **f64)
+    Kd = min(args.steps, 100)
+    stats = torch.zeros((5 + Kd, _abi.TZ_NSTATS), **f64)
+    po = tz.SolverOptions(warm_start=2, check_every=args.check_every, eps_abs=args.eps, eps_rel=args.eps, polish=args.polish).pack()
+    h = prog.handle.value
+
+    def step(t):
+        ops.closed_loop_step_set(h, x, xbar, e, noise[t % nring], xr, At, Bt, status, cost, vbuf, traj, ze1, None, None, warm,
+                                 stats[t], po)
+
+    for t in range(5):
+        step(t)
+    torch.cuda.synchronize(dev)
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        for k in range(Kd):
+            step(5 + k)
+    torch.cuda.synchronize(dev)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    graph.replay()
+    b.record()
+    torch.cuda.synchronize(dev)
+    ms = a.elapsed_time(b) / Kd
+    tot = stats[5:].sum(0).cpu().numpy()
+    return {"datasets": D, "scenarios_per_dataset": per, "ms_per_step": ms, "value": S / (ms * 1e-3), "unit": UNIT, "steps": Kd,
+            "setup_s": setup_s, "api": "TZDDPCEnsemble -> tz_closed_loop_step_set (one launch per step, one program per data set)",
+            "status_ok_frac": float(1.0 - (tot[3] + tot[4] + tot[6]) / max(tot[7], 1.0)), "iters_mean": float(tot[5] / max(tot[7], 1.0))}
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -423,42 +489,64 @@ def run_gpu(args):
                              "mean_norm_x": float(tot_stats[0] / cnt)},
             "clocks": clocks}
 
-    # ---- e2e: host buffers through the C-ABI host entry point, every output back on the host
+    # ---- e2e: host buffers through the C-ABI host entry point, every output of the step back on the host.
+    # Headline `e2e`: the tube crosses the bus PACKED (TzSolverOpts.tube_packed: the n_nz entries of Ze[1].Z that are not
+    # structurally zero; the binding scatters them into the dense matrix when `.Z.value` is read, as the reference's
+    # `.Z.value` evaluates its expression on access).  `e2e_dense_tube`: the same call with the dense n x (1+g1) matrix.
     if not args.no_e2e:
         Ke = max(3, min(args.e2e_steps, K_steps))
         pin = lambda *shape, dt=torch.float64: torch.empty(shape, dtype=dt).pin_memory()     # noqa: E731
         hx, hxb, he = pin(n, S), pin(n, S), pin(n, S)
-        hx.copy_(x0[:, None].cpu().expand(n, S)); hxb.copy_(hx); he.zero_()
         hnoise = pin(Ke + 2, n, S)
         hnoise.copy_(noise[torch.arange(Ke + 2, device=dev) % nring].cpu())
+        nnz = len(prog.tube_pattern)
         hcost, hv, htraj, hze = pin(S), pin(nv, S), pin(nt, S), pin(nent, S)
         hstat = pin(S, dt=torch.int32)
-        scratch = torch.empty(_abi.lib().tz_closed_loop_step_host_scratch_bytes(h, S) // 8 + 8, **f64)
+        scratch = torch.zeros(_abi.lib().tz_closed_loop_step_host_scratch_bytes(h, S) // 8 + 8, **f64)
         import ctypes as C
-        o_ = ops._opts(po)
         Ah, Bh = np.ascontiguousarray(cfg.A), np.ascontiguousarray(cfg.B)
 
-        def host_step(t):
-            rc = _abi.lib().tz_closed_loop_step_host(
-                C.c_void_p(h), C.byref(o_), S, C.c_void_p(hx.data_ptr()), C.c_void_p(hxb.data_ptr()), C.c_void_p(he.data_ptr()),
-                C.c_void_p(hnoise[t].data_ptr()), C.c_void_p(Ah.ctypes.data), C.c_void_p(Bh.ctypes.data),
-                C.c_void_p(hcost.data_ptr()), C.c_void_p(hv.data_ptr()), C.c_void_p(htraj.data_ptr()), C.c_void_p(hze.data_ptr()),
-                C.c_void_p(hstat.data_ptr()), C.c_void_p(scratch.data_ptr()), args.e2e_chunks)
-            _abi.check(rc, "tz_closed_loop_step_host")
+        def e2e_leg(packed):
+            o_ = ops._opts(tz.SolverOptions(warm_start=int(args.warm_start), check_every=args.check_every, eps_abs=args.eps, eps_rel=args.eps,
+                                            polish=args.polish, tube_packed=int(packed)).pack())
+            hx.copy_(x0[:, None].cpu().expand(n, S)); hxb.copy_(hx); he.zero_()
+            scratch.zero_()
 
-        for t in range(2):
-            host_step(t)
-        barrier()
-        t0 = time.perf_counter()
-        for t in range(Ke):
-            host_step(2 + t)
-        barrier()
-        dt = time.perf_counter() - t0
-        dt = shard.max_over_ranks(dt, dev)
-        line["e2e"] = {"value": world * S * Ke / dt, "unit": UNIT, "h2d_bytes_per_step": int(4 * n * S * 8 + 8 * (n * n + n * m)),
-                       "d2h_bytes_per_step": int(S * (8 * (3 * n + 1 + nv + nt + nent) + 4)), "steps": Ke,
-                       "ms_per_step": 1e3 * dt / Ke, "api": "tz_closed_loop_step_host (pinned host buffers)",
-                       "status_ok_frac": float((hstat == 0).double().mean().item())}
+            def host_step(t):
+                rc = _abi.lib().tz_closed_loop_step_host(
+                    C.c_void_p(h), C.byref(o_), S, C.c_void_p(hx.data_ptr()), C.c_void_p(hxb.data_ptr()), C.c_void_p(he.data_ptr()),
+                    C.c_void_p(hnoise[t].data_ptr()), C.c_void_p(Ah.ctypes.data), C.c_void_p(Bh.ctypes.data),
+                    C.c_void_p(hcost.data_ptr()), C.c_void_p(hv.data_ptr()), C.c_void_p(htraj.data_ptr()), C.c_void_p(hze.data_ptr()),
+                    C.c_void_p(hstat.data_ptr()), C.c_void_p(scratch.data_ptr()), args.e2e_chunks)
+                _abi.check(rc, "tz_closed_loop_step_host")
+
+            for t in range(2):
+                host_step(t)
+            barrier()
+            t0 = time.perf_counter()
+            for t in range(Ke):
+                host_step(2 + t)
+            barrier()
+            dt = shard.max_over_ranks(time.perf_counter() - t0, dev)
+            rows = nnz if packed else nent
+            return {"value": world * S * Ke / dt, "unit": UNIT, "h2d_bytes_per_step": int(4 * n * S * 8 + 8 * (n * n + n * m)),
+                    "d2h_bytes_per_step": int(S * (8 * (3 * n + 1 + nv + nt + rows) + 4)), "steps": Ke,
+                    "ms_per_step": 1e3 * dt / Ke, "api": "tz_closed_loop_step_host (pinned host buffers)",
+                    "tube": (f"packed: {nnz} of {nent} entries of Ze[1].Z per scenario (the others are zero for every "
+                             f"(xbar0, e0)); pattern from tz_program_tube_pattern") if packed else "dense n x (1+g1)",
+                    "solver": "active-set hints carried between calls in the caller's device scratch (warm_start)",
+                    "status_ok_frac": float((hstat == 0).double().mean().item())}
+
+        line["e2e"] = e2e_leg(True)
+        line["e2e_dense_tube"] = e2e_leg(False)
+
+    # ---- data-set axis (north_star: scenarios = noise realisations x initial states x data sets): D data sets, one
+    # program each, the whole batch in one launch per step (tz_closed_loop_step_set); rank 0 at N = 1 only
+    if rank == 0 and world == 1 and args.datasets > 0:
+        try:
+            line["datasets_axis"] = datasets_leg(args, tz, ops, torch, dev, cfg, noise, nring)
+        except Exception as exc:      # noqa: BLE001  (secondary leg: never fail the headline line)
+            line["datasets_axis"] = {"error": repr(exc)[:300]}
 
     # ---- batch-1 latency (BASELINE.json metric: "us/step at batch 1"): examples/1.double_integrator_sim.py as shipped, one
     # scenario, the closed loop captured in a CUDA graph (50 fused steps per replay) so that no host work sits between steps
@@ -497,6 +585,7 @@ def main():
     ap.add_argument("--polish", type=int, default=3, help="augmented-Lagrangian iterations of the certificate / polish")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--e2e-chunks", type=int, default=4)
+    ap.add_argument("--datasets", type=int, default=64, help="data sets of the data-set-axis leg (0 = skip)")
     ap.add_argument("--cpu-steps", type=int, default=1500)
     ap.add_argument("--cpu-cores", type=int, default=0, help="processes of the CPU baseline (0 = all host cores)")
     ap.add_argument("--dump-steps", default="", help="write per-step kernel ms and solver statistics to this .npz (diagnostics)")

@@ -96,6 +96,10 @@ int tz_program_bucket(const TzProgram* prog, char* buf, size_t cap);
 /* rows of the `warm` scratch array (rows x S doubles) that tz_solve / tz_closed_loop_step accept */
 int tz_program_warm_rows(const TzProgram* prog);
 
+/* Sparsity pattern of Ze[1].Z: returns n_nz, the number of entries that are not structurally zero, and (when
+ * entries_host != NULL, cap >= n_nz) writes their row-major indices r*(1+g1)+j into entries_host.  Centre column included. */
+int tz_program_tube_pattern(const TzProgram* prog, int32_t* entries_host, int32_t cap);
+
 typedef struct TzSolverOpts {
   double rho;        /* base ADMM penalty (scaled problem)         default 0.1  */
   double rho_active; /* multiplier for rows detected active        default 100  */
@@ -112,6 +116,10 @@ typedef struct TzSolverOpts {
   int32_t cert_first;/* first iteration at which the active-set KKT certificate is tried (then on a
                         geometric schedule); a certified iterate is an exact solution and ends the
                         solve at once.  0 = off (terminate on residuals only)        default 3    */
+  int32_t tube_packed;/* 0: `ze1` is the dense n(1+g1) x S matrix the reference returns (Zek.Z.value).
+                        1: `ze1` is n_nz x S -- row i holds entry tz_program_tube_pattern()[i] of Ze[1].Z; the other
+                        entries are zero for EVERY (xbar0, e0) (boxed M_K / M_Delta: 88 % of the 5-dim tube) and are
+                        neither written to HBM nor copied to the host                  default 0 */
 } TzSolverOpts;
 
 void tz_solver_opts_default(TzSolverOpts* o);
@@ -122,7 +130,7 @@ void tz_solver_opts_default(TzSolverOpts* o);
  *   out: cost                S
  *        v                   (N*m) x S
  *        xbar_traj           ((N+1)*n) x S
- *        ze1                 (n*(1+g1)) x S   Ze[1].Z, entry (r, j) at row r*(1+g1)+j
+ *        ze1                 (n*(1+g1)) x S   Ze[1].Z, entry (r, j) at row r*(1+g1)+j   (n_nz x S with opts->tube_packed)
  *        status, iters       S   (int32)
  *   warm: tz_program_warm_rows(prog) x S scratch carrying the ADMM iterate between calls, or NULL
  *   any of cost / v / xbar_traj / ze1 / iters may be NULL (not written).
@@ -154,10 +162,36 @@ int tz_closed_loop_step(const TzProgram* prog, const TzSolverOpts* opts, int64_t
                         double* cost, double* v, double* xbar_traj, double* ze1, double* u_out,
                         int32_t* status, int32_t* iters, double* warm, double* stats, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Data-set axis (BASELINE.json north_star: scenarios = noise realisations x initial states x data sets).
+ * The reference builds one TZDDPC object -- one model M_Sigma, one problem -- per data set (tzddpc/tzddpc.py:20-28,
+ * 67-85,132-241) and runs them one after another.  A program set runs D such programs in ONE launch: scenarios
+ * [begin[j], begin[j+1]) of the batch use progs[j].  The programs must be the same problem (dimensions, horizon,
+ * cost / constraint structure, hence kernel bucket and table sizes) built from different data; begin[0] = 0, begin[j]
+ * a multiple of 16, begin[D] = S of every later call.  The set borrows the programs: destroy it before them.
+ * tz_solve_set / tz_closed_loop_step_set take the arguments of tz_solve / tz_closed_loop_step.
+ * ------------------------------------------------------------------------------------ */
+typedef struct TzProgramSet TzProgramSet;   /* opaque */
+int tz_program_set_create(const TzProgram* const* progs, int32_t nprog, const int64_t* begin, TzProgramSet** out);
+void tz_program_set_destroy(TzProgramSet* set);
+int64_t tz_program_set_scenarios(const TzProgramSet* set);
+int tz_solve_set(const TzProgramSet* set, const TzSolverOpts* opts, int64_t S,
+                 const double* xbar0, const double* e0,
+                 double* cost, double* v, double* xbar_traj, double* ze1,
+                 int32_t* status, int32_t* iters, double* warm, void* stream);
+int tz_closed_loop_step_set(const TzProgramSet* set, const TzSolverOpts* opts, int64_t S,
+                            double* x, double* xbar, double* e, const double* noise, const double* x_restart,
+                            const double* A_true, const double* B_true,
+                            double* cost, double* v, double* xbar_traj, double* ze1, double* u_out,
+                            int32_t* status, int32_t* iters, double* warm, double* stats, void* stream);
+
 /* Same step with HOST buffers (pinned or pageable): H2D of (x, xbar, e, noise), the fused
  * kernel, D2H of every non-NULL output, chunked over `nchunks` internal streams so that
  * copies overlap compute; synchronises before returning.  `dev_scratch` is caller-owned
- * device memory of at least tz_closed_loop_step_host_scratch_bytes(prog, S). */
+ * device memory of at least tz_closed_loop_step_host_scratch_bytes(prog, S).  With opts->warm_start != 0 its tail
+ * carries the solver's warm-start rows (active-set hints) from one call to the next: zero it once before the first
+ * call of a run and pass the same buffer every step (a stale or foreign hint is KKT-checked before use, so it can cost
+ * time but not correctness).  With opts->tube_packed, ze1_host is n_nz x S. */
 size_t tz_closed_loop_step_host_scratch_bytes(const TzProgram* prog, int64_t S);
 int tz_closed_loop_step_host(const TzProgram* prog, const TzSolverOpts* opts, int64_t S,
                              double* x_host, double* xbar_host, double* e_host, const double* noise_host,

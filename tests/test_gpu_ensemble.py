@@ -1,0 +1,156 @@
+"""Data-set axis and packed tube (GPU).
+
+* `TZDDPCEnsemble` -- D data sets, one program each, one launch per closed-loop step (tz_closed_loop_step_set) -- must give,
+  for every data set's slice of the batch, exactly what that data set's own controller gives (tz_closed_loop_step), and
+  the oracle's answer for the oracle built on that data set (the reference: one TZDDPC object per data set,
+  tzddpc/tzddpc.py:20-28,67-85,132-241).
+* packed tube (`SolverOptions.tube_packed`): scattering the n_nz rows by `tube_pattern` must reproduce the dense Ze[1].Z
+  bit for bit (examples/2.pulley_sim.py:96).
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests import common
+from tzddpc_b200 import configs
+
+pytestmark = pytest.mark.gpu
+
+
+def _controllers(cfg, D, with_oracle=False):
+    ctls, oracles = [], []
+    for d in range(D):
+        u, x = common.dataset(cfg, seed=cfg.seed + 101 * d)
+        o, K = common.make_oracle(cfg, u, x) if with_oracle else (None, None)
+        if K is None:
+            import oracle
+            oo = oracle.OracleTZDDPC(oracle.Data(u, x))
+            oo.build_zonotopes(common.oracle_zonotopes(cfg))
+            C = oo.Mdata.center
+            K = configs.lqr_gain(C[:, :cfg.n], C[:, cfg.n:])
+        ctls.append(common.make_product(cfg, u, x, K))
+        oracles.append(o)
+    return ctls, oracles
+
+
+@pytest.mark.parametrize("name", ["double_integrator", "pulley", "fivedim"])
+def test_ensemble_closed_loop_equals_per_dataset_controllers(cuda_lib, name):
+    import tzddpc_b200 as tz
+    cfg = configs.CONFIGS[name]()
+    D, per, steps = 5, 48, 12
+    ctls, _ = _controllers(cfg, D)
+    ens = tz.TZDDPCEnsemble(ctls, per)
+    assert ens.num_scenarios == D * per and ens.num_datasets == D
+    rng = np.random.default_rng(3)
+    noise = common.noise_for(cfg, steps, D * per, rng)
+    x0 = np.tile(np.asarray(cfg.X0[0], dtype=np.float64), (D * per, 1))
+    for ws in (0, 2):
+        opts = tz.SolverOptions(warm_start=ws)
+        r = ens.simulate(cfg.A, cfg.B, x0, noise=noise, keep_tubes=True, options=opts, restart=True)
+        for d, c in enumerate(ctls):
+            sl = slice(d * per, (d + 1) * per)
+            rd = c.simulate(cfg.A, cfg.B, x0[sl], noise=noise[:, sl], keep_tubes=True, options=opts, restart=True)
+            for k in ("x", "xbar", "e", "u", "v", "cost", "status", "tubes"):
+                np.testing.assert_array_equal(r[k][:, sl], rd[k], err_msg=f"{k}, data set {d}, warm_start {ws}")
+        # the data sets differ, so do their answers
+        assert not np.array_equal(r["v"][:, :per], r["v"][:, per:2 * per])
+        # statistics are accumulated over all programs of the launch
+        np.testing.assert_allclose(r["stats"][:, 7], D * per)
+
+
+def test_ensemble_solve_matches_each_datasets_oracle(cuda_lib):
+    import tzddpc_b200 as tz
+    cfg = configs.CONFIGS["pulley"]()
+    D, per = 3, 16
+    ctls, oracles = _controllers(cfg, D, with_oracle=True)
+    ens = tz.TZDDPCEnsemble(ctls, per)
+    rng = np.random.default_rng(11)
+    Xi = oracles[0].zonotopes.X.interval
+    xb = Xi.left_limit + (Xi.right_limit - Xi.left_limit) * rng.uniform(0.2, 0.8, (D * per, cfg.n))
+    ee = rng.uniform(-0.2, 0.2, (D * per, cfg.n))
+    dev = ens.device
+    r = ens.solve_batch(torch.tensor(xb.T.copy(), device=dev), torch.tensor(ee.T.copy(), device=dev))
+    cost, v, traj, status = r.cost.cpu().numpy(), r.v.cpu().numpy(), r.xbar.cpu().numpy(), r.status.cpu().numpy()
+    wmax = ctls[0]._program.compiled.wmax
+    checked = 0
+    for s in range(D * per):
+        ro = oracles[s // per].solve_status(xb[s], ee[s])
+        if ro.status == 2:
+            assert status[s] == 2
+            continue
+        assert status[s] == 0
+        assert common.cost_close(cost[s], ro.cost, wmax), (s, cost[s], ro.cost)
+        np.testing.assert_allclose(v[0, s], ro.v[0, 0], rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(traj[cfg.n:2 * cfg.n, s], ro.xbar[1], rtol=1e-6, atol=1e-6)
+        checked += 1
+    assert checked >= D * per // 2
+
+
+def test_program_set_with_more_programs_than_ctas_and_ragged_last(cuda_lib):
+    """600 set entries (cycling through 3 programs) > one wave of CTAs: a CTA serves several programs in turn; the last
+    entry is a partial tile."""
+    import ctypes as C
+    import tzddpc_b200 as tz
+    from tzddpc_b200 import _abi, ops
+    cfg = configs.CONFIGS["fivedim"]()
+    ctls, _ = _controllers(cfg, 3)
+    nprog, per, last = 600, 16, 6
+    progs = [ctls[j % 3]._program for j in range(nprog)]
+    begin = np.concatenate([np.arange(nprog) * per, [(nprog - 1) * per + last]]).astype(np.int64)
+    pset = _abi.ProgramSet(progs, begin)
+    S = int(begin[-1])
+    dev = ctls[0].device
+    rng = np.random.default_rng(5)
+    x0 = np.asarray(cfg.X0[0], dtype=np.float64)
+    xb = torch.tensor((x0[:, None] + 0.05 * rng.standard_normal((cfg.n, S))), device=dev)
+    ee = torch.tensor(0.02 * rng.standard_normal((cfg.n, S)), device=dev)
+    o = tz.SolverOptions()
+    cost, v, traj, ze1, status, iters = ops.solve_set(pset.handle.value, ctls[0]._dims, xb, ee, None, True, o.pack())
+    for j in range(3):
+        idx = np.concatenate([np.arange(begin[k], begin[k + 1]) for k in range(j, nprog, 3)])
+        it = torch.as_tensor(idx, device=dev)
+        r = ctls[j].solve_batch(xb[:, it].contiguous(), ee[:, it].contiguous())
+        assert torch.equal(r.status, status[it])
+        assert torch.equal(r.cost, cost[it]) and torch.equal(r.v, v[:, it]) and torch.equal(r.xbar, traj[:, it])
+        assert torch.equal(r.tube._ze1, ze1[:, it])
+    assert int((status == 0).sum()) > S // 2
+    # error paths: misaligned start, structure mismatch is covered by identical programs here; wrong batch size
+    with pytest.raises(RuntimeError, match="multiple of 16"):
+        _abi.ProgramSet(progs[:2], np.array([0, 8, 24], dtype=np.int64))
+    with pytest.raises(RuntimeError, match="created for"):
+        ops.solve_set(pset.handle.value, ctls[0]._dims, xb[:, :32].contiguous(), ee[:, :32].contiguous(), None, True, o.pack())
+
+
+@pytest.mark.parametrize("name", ["double_integrator", "pulley", "fivedim"])
+def test_packed_tube_scatters_to_the_dense_tube(cuda_lib, name):
+    import tzddpc_b200 as tz
+    cfg = configs.CONFIGS[name]()
+    u, x = common.dataset(cfg)
+    o, K = common.make_oracle(cfg, u, x)
+    t = common.make_product(cfg, u, x, K)
+    prog = t._program
+    n, g1 = cfg.n, prog.compiled.g1
+    pat = prog.tube_pattern
+    assert len(pat) < n * (1 + g1) and len(np.unique(pat)) == len(pat) and pat.max() < n * (1 + g1)
+    S, steps = 70, 8          # a ragged batch (partial tiles)
+    rng = np.random.default_rng(9)
+    noise = common.noise_for(cfg, steps, S, rng)
+    x0 = np.tile(np.asarray(cfg.X0[0], dtype=np.float64), (S, 1))
+    rd = t.simulate(cfg.A, cfg.B, x0, noise=noise, keep_tubes=True, options=tz.SolverOptions(warm_start=2))
+    rp = t.simulate(cfg.A, cfg.B, x0, noise=noise, keep_tubes=True, options=tz.SolverOptions(warm_start=2, tube_packed=1))
+    for k in ("x", "xbar", "e", "u", "v", "cost", "status"):
+        np.testing.assert_array_equal(rd[k], rp[k])
+    ok = rd["status"] == 0
+    np.testing.assert_array_equal(rd["tubes"][ok], rp["tubes"][ok])
+    # every entry outside the pattern is zero in the dense tube, whatever the scenario
+    mask = np.ones(n * (1 + g1), dtype=bool)
+    mask[pat] = False
+    assert not rd["tubes"][ok].reshape(-1, n * (1 + g1))[:, mask].any()
+    # solve(): TubeHandle expands the packed buffer on access
+    t.solver_options = tz.SolverOptions(tube_packed=1)
+    cost, v, xbar, tube = t.solve(x0[0], np.zeros(n))
+    t.solver_options = tz.SolverOptions()
+    cost2, v2, xbar2, tube2 = t.solve(x0[0], np.zeros(n))
+    np.testing.assert_array_equal(tube.Z.value, tube2.Z.value)
+    assert tube.Z.value.shape == (n, 1 + g1)
+    np.testing.assert_array_equal(tube.device_tensor.cpu().numpy(), tube2.device_tensor.cpu().numpy())

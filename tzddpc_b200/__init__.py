@@ -9,6 +9,7 @@ from .objects import (Data, DataDrivenDataset, OptimizationProblem, Optimization
 from .ops import SolverOptions  # noqa: F401
 from .program import BoxConstraint, StageCost  # noqa: F401
 from .tzddpc import TZDDPC, TubeHandle  # noqa: F401
+from .ensemble import TZDDPCEnsemble  # noqa: F401
 from .zonotope import Interval, MatrixZonotope, Zonotope, concatenate_zonotope  # noqa: F401
 
 __version__ = "0.1.0"

@@ -28,7 +28,7 @@ class TzProgramDesc(C.Structure):
 
 class TzSolverOpts(C.Structure):
     _fields_ = [(k, C.c_double) for k in ("rho", "rho_active", "rho_inactive", "sigma", "alpha", "eps_abs", "eps_rel")] + \
-               [(k, C.c_int32) for k in ("max_iter", "check_every", "polish", "warm_start", "cert_first")]
+               [(k, C.c_int32) for k in ("max_iter", "check_every", "polish", "warm_start", "cert_first", "tube_packed")]
 
 
 class TzddpcLibraryMissing(RuntimeError):
@@ -41,7 +41,9 @@ _lib = None
 EXPORTS = ["tz_version", "tz_last_error", "tz_device_cc", "tz_program_create", "tz_program_destroy", "tz_program_bucket", "tz_program_warm_rows",
            "tz_solver_opts_default", "tz_solve", "tz_closed_loop_step", "tz_closed_loop_step_host_scratch_bytes",
            "tz_closed_loop_step_host", "tz_interval_hull", "tz_reach_step", "tz_girard_reduce", "tz_tube_rollout",
-           "tz_identify", "tz_qp_solve", "tz_philox4x32_10_host", "tz_sample_noise", "tz_generate_trajectories"]
+           "tz_identify", "tz_qp_solve", "tz_philox4x32_10_host", "tz_sample_noise", "tz_generate_trajectories",
+           "tz_program_tube_pattern", "tz_program_set_create", "tz_program_set_destroy", "tz_program_set_scenarios",
+           "tz_solve_set", "tz_closed_loop_step_set"]
 
 
 def lib() -> C.CDLL:
@@ -72,6 +74,18 @@ def lib() -> C.CDLL:
     L.tz_solve.argtypes = [vp, C.POINTER(TzSolverOpts), i64] + [vp] * 10
     L.tz_closed_loop_step.restype = C.c_int
     L.tz_closed_loop_step.argtypes = [vp, C.POINTER(TzSolverOpts), i64] + [vp] * 17
+    L.tz_program_tube_pattern.restype = C.c_int
+    L.tz_program_tube_pattern.argtypes = [vp, vp, i32]
+    L.tz_program_set_create.restype = C.c_int
+    L.tz_program_set_create.argtypes = [vp, i32, vp, C.POINTER(vp)]
+    L.tz_program_set_destroy.restype = None
+    L.tz_program_set_destroy.argtypes = [vp]
+    L.tz_program_set_scenarios.restype = i64
+    L.tz_program_set_scenarios.argtypes = [vp]
+    L.tz_solve_set.restype = C.c_int
+    L.tz_solve_set.argtypes = [vp, C.POINTER(TzSolverOpts), i64] + [vp] * 10
+    L.tz_closed_loop_step_set.restype = C.c_int
+    L.tz_closed_loop_step_set.argtypes = [vp, C.POINTER(TzSolverOpts), i64] + [vp] * 17
     L.tz_closed_loop_step_host_scratch_bytes.restype = C.c_size_t
     L.tz_closed_loop_step_host_scratch_bytes.argtypes = [vp, i64]
     L.tz_closed_loop_step_host.restype = C.c_int
@@ -144,11 +158,38 @@ class Program:
         L.tz_program_bucket(h, buf, 64)
         self.bucket = buf.value.decode()
         self.warm_rows = int(L.tz_program_warm_rows(h))
+        nnz = int(L.tz_program_tube_pattern(h, None, 0))
+        pat = np.zeros(max(nnz, 1), dtype=np.int32)
+        L.tz_program_tube_pattern(h, pat.ctypes.data, nnz)
+        self.tube_pattern = pat[:nnz]          # row-major indices of the entries of Ze[1].Z that are not structurally zero
 
     def __del__(self):
         try:
             if getattr(self, "handle", None):
                 lib().tz_program_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class ProgramSet:
+    """Owner of a TzProgramSet: D programs of one structure (one per data set), scenarios [begin[j], begin[j+1]) use program j."""
+
+    def __init__(self, programs, begin):
+        L = lib()
+        self.programs = list(programs)                      # keeps the borrowed handles alive
+        self.begin = np.ascontiguousarray(np.asarray(begin, dtype=np.int64))
+        assert len(self.begin) == len(self.programs) + 1
+        arr = (C.c_void_p * len(self.programs))(*[p.handle.value for p in self.programs])
+        h = C.c_void_p()
+        check(L.tz_program_set_create(arr, len(self.programs), self.begin.ctypes.data, C.byref(h)), "tz_program_set_create")
+        self.handle = h
+        self.scenarios = int(self.begin[-1])
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                lib().tz_program_set_destroy(self.handle)
                 self.handle = None
         except Exception:
             pass

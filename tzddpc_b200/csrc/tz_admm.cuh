@@ -87,7 +87,7 @@ struct QpProg {
 
 struct SolverParams {     // TzSolverOpts, device side
   double rho, rho_act, rho_inact, sigma, alpha, eps_abs, eps_rel;
-  int max_iter, check_every, polish, warm, cert_first;
+  int max_iter, check_every, polish, warm, cert_first, tube_packed;
 };
 
 // compare-select min/max: 3 instructions instead of the ~8 of IEEE fmin/fmax (no NaN quieting needed:

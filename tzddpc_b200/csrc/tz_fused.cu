@@ -21,6 +21,9 @@ namespace tz {
 extern template int launch_bucket<B1>(const TzProgram*, const SolverParams&, const StepArgs&, cudaStream_t);
 extern template int launch_bucket<B2>(const TzProgram*, const SolverParams&, const StepArgs&, cudaStream_t);
 extern template int launch_bucket<B3>(const TzProgram*, const SolverParams&, const StepArgs&, cudaStream_t);
+extern template int launch_bucket_set<B1>(const TzProgram*, const SetEntry*, int, int64_t, const SolverParams&, const StepArgs&, cudaStream_t);
+extern template int launch_bucket_set<B2>(const TzProgram*, const SetEntry*, int, int64_t, const SolverParams&, const StepArgs&, cudaStream_t);
+extern template int launch_bucket_set<B3>(const TzProgram*, const SetEntry*, int, int64_t, const SolverParams&, const StepArgs&, cudaStream_t);
 
 struct RowClasses { int n2 = 0, nu = 0, nl = 0; };
 
@@ -227,6 +230,7 @@ extern "C" int tz_program_create(const TzProgramDesc* d, TzProgram** out) {
   ax.o_XB = 0; ax.o_CZ = (int)nXB; ax.o_K = (int)(nXB + nCZ); ax.o_coef = (int)(nXB + nCZ + nK);
   ax.o_ent = 0; ax.o_idx = (int)ent.size();
   ax.n_nz = (int)ent.size();
+  p->tube_ent = ent;
   ax.n = n; ax.m = d->m; ax.N = d->horizon; ax.nv = d->nv; ax.g1 = d->g1;
   p->smem_tab = (smem_tab + 15) & ~(size_t)15;
   *out = p;
@@ -256,6 +260,7 @@ extern "C" void tz_solver_opts_default(TzSolverOpts* o) {
   o->rho = 0.1; o->rho_active = 100.0; o->rho_inactive = 0.1; o->sigma = 1e-6; o->alpha = 1.6;
   o->eps_abs = 1e-6; o->eps_rel = 1e-6; o->max_iter = 4000; o->check_every = 8; o->polish = 3; o->warm_start = 0;
   o->cert_first = 3;
+  o->tube_packed = 0;
 }
 
 static SolverParams to_params(const TzSolverOpts* o) {
@@ -263,7 +268,16 @@ static SolverParams to_params(const TzSolverOpts* o) {
   tz_solver_opts_default(&d);
   if (o) d = *o;
   return SolverParams{d.rho, d.rho_active, d.rho_inactive, d.sigma, d.alpha, d.eps_abs, d.eps_rel,
-                      d.max_iter, d.check_every, d.polish, d.warm_start, d.cert_first};
+                      d.max_iter, d.check_every, d.polish, d.warm_start, d.cert_first, d.tube_packed != 0 ? 1 : 0};
+}
+
+// two scenarios per lane in the output phase need 16-byte aligned rows: S, ld even and aligned base pointers
+static int vec2_ok(const StepArgs& a) {
+  const void* ptrs[] = {a.x, a.xbar, a.e, a.noise, a.x_restart, a.cost, a.v, a.xbar_traj, a.ze1, a.u_out, a.xbar0, a.e0};
+  bool ok = (a.S % 2 == 0) && (a.ld % 2 == 0);
+  for (const void* q : ptrs) ok = ok && ((reinterpret_cast<uintptr_t>(q) & 15u) == 0);
+  ok = ok && ((reinterpret_cast<uintptr_t>(a.status) & 7u) == 0) && ((reinterpret_cast<uintptr_t>(a.iters) & 7u) == 0);
+  return ok ? 1 : 0;
 }
 
 static int launch(const TzProgram* p, const TzSolverOpts* o, const StepArgs& a_in, void* stream) {
@@ -271,13 +285,7 @@ static int launch(const TzProgram* p, const TzSolverOpts* o, const StepArgs& a_i
   TZ_REQUIRE(a_in.S >= 0, "negative batch");
   if (a_in.S == 0) return TZ_OK;
   StepArgs a = a_in;
-  {  // two scenarios per lane in the output phase need 16-byte aligned rows: S, ld even and aligned base pointers
-    const void* ptrs[] = {a.x, a.xbar, a.e, a.noise, a.x_restart, a.cost, a.v, a.xbar_traj, a.ze1, a.u_out};
-    bool ok = (a.S % 2 == 0) && (a.ld % 2 == 0);
-    for (const void* q : ptrs) ok = ok && ((reinterpret_cast<uintptr_t>(q) & 15u) == 0);
-    ok = ok && ((reinterpret_cast<uintptr_t>(a.status) & 7u) == 0) && ((reinterpret_cast<uintptr_t>(a.iters) & 7u) == 0);
-    a.vec2 = ok ? 1 : 0;
-  }
+  a.vec2 = vec2_ok(a);
   const SolverParams sp = to_params(o);
   TZ_REQUIRE(sp.max_iter >= 1 && sp.rho > 0 && sp.rho_act > 0 && sp.rho_inact > 0 && sp.alpha > 0 && sp.alpha < 2,
              "bad solver options");
@@ -314,6 +322,121 @@ extern "C" int tz_closed_loop_step(const TzProgram* prog, const TzSolverOpts* op
   return launch(prog, opts, a, stream);
 }
 
+// ---- tube pattern (packed Ze[1].Z) ------------------------------------------------------------------
+extern "C" int tz_program_tube_pattern(const TzProgram* p, int32_t* entries_host, int32_t cap) {
+  if (!p) return fail(TZ_EINVAL, "null program");
+  const int nnz = p->aux.n_nz;
+  if (entries_host) {
+    TZ_REQUIRE(cap >= nnz, "tube pattern needs %d entries (cap %d)", nnz, cap);
+    std::memcpy(entries_host, p->tube_ent.data(), (size_t)nnz * sizeof(int32_t));
+  }
+  return nnz;
+}
+
+// ---- data-set axis: program sets ----------------------------------------------------------------------
+struct TzProgramSet {
+  std::vector<const TzProgram*> progs;
+  std::vector<int64_t> begin;          // nprog + 1
+  tz::SetEntry* entries_dev = nullptr;
+  int64_t max_scen = 0;
+};
+
+extern "C" int tz_program_set_create(const TzProgram* const* progs, int32_t nprog, const int64_t* begin, TzProgramSet** out) {
+  TZ_REQUIRE(progs && begin && out && nprog >= 1, "null argument / empty set");
+  const TzProgram* p0 = progs[0];
+  TZ_REQUIRE(p0 != nullptr, "null program 0");
+  TZ_REQUIRE(begin[0] == 0, "begin[0] must be 0");
+  std::vector<tz::SetEntry> ent((size_t)nprog);
+  int64_t mx = 0;
+  for (int j = 0; j < nprog; ++j) {
+    const TzProgram* p = progs[j];
+    TZ_REQUIRE(p != nullptr, "null program %d", j);
+    const Aux &a = p->aux, &b = p0->aux;
+    // one kernel instance and one table layout serve the whole set: the programs must be the same problem (dimensions,
+    // horizon, cost and constraint structure) built from different data
+    TZ_REQUIRE(p->bucket == p0->bucket && p->smem_tab == p0->smem_tab && a.n_dbl == b.n_dbl && a.n_int == b.n_int &&
+               a.o_XB == b.o_XB && a.o_CZ == b.o_CZ && a.o_K == b.o_K && a.o_coef == b.o_coef && a.o_ent == b.o_ent &&
+               a.o_idx == b.o_idx && a.n_nz == b.n_nz && a.n == b.n && a.m == b.m && a.N == b.N && a.nv == b.nv && a.g1 == b.g1,
+               "program %d does not have the structure of program 0 (bucket / table sizes differ)", j);
+    TZ_REQUIRE(p->tube_ent == p0->tube_ent, "program %d: Ze[1] has a different sparsity pattern than program 0", j);
+    const int64_t cnt = begin[j + 1] - begin[j];
+    TZ_REQUIRE(cnt >= 0, "begin[] must be non-decreasing");
+    TZ_REQUIRE(begin[j] % 16 == 0, "begin[%d] = %lld: the scenarios of a program must start on a multiple of 16", j,
+               (long long)begin[j]);
+    ent[j] = tz::SetEntry{p->packed_dev, a.tab, begin[j], begin[j + 1]};
+    if (cnt > mx) mx = cnt;
+  }
+  TzProgramSet* s = new (std::nothrow) TzProgramSet();
+  if (!s) return fail(TZ_ENOMEM, "out of host memory");
+  s->progs.assign(progs, progs + nprog);
+  s->begin.assign(begin, begin + nprog + 1);
+  s->max_scen = mx;
+  cudaError_t err = cudaMalloc(&s->entries_dev, ent.size() * sizeof(tz::SetEntry));
+  if (err == cudaSuccess) err = cudaMemcpy(s->entries_dev, ent.data(), ent.size() * sizeof(tz::SetEntry), cudaMemcpyHostToDevice);
+  if (err != cudaSuccess) {
+    if (s->entries_dev) cudaFree(s->entries_dev);
+    delete s;
+    return fail(TZ_ECUDA, "program set upload: %s", cudaGetErrorString(err));
+  }
+  *out = s;
+  return TZ_OK;
+}
+
+extern "C" void tz_program_set_destroy(TzProgramSet* s) {
+  if (!s) return;
+  if (s->entries_dev) cudaFree(s->entries_dev);
+  delete s;
+}
+
+extern "C" int64_t tz_program_set_scenarios(const TzProgramSet* s) { return s ? s->begin.back() : -1; }
+
+static int launch_set(const TzProgramSet* s, const TzSolverOpts* o, const StepArgs& a_in, void* stream) {
+  TZ_REQUIRE(s != nullptr, "null program set");
+  TZ_REQUIRE(a_in.S == s->begin.back(), "batch of %lld scenarios, the set was created for %lld", (long long)a_in.S,
+             (long long)s->begin.back());
+  if (a_in.S == 0) return TZ_OK;
+  StepArgs a = a_in;
+  a.vec2 = vec2_ok(a);             // (every program starts on a multiple of 16 scenarios: alignment carries over)
+  for (size_t j = 0; j + 1 < s->begin.size(); ++j)
+    if ((s->begin[j + 1] - s->begin[j]) % 2 != 0) a.vec2 = 0;
+  const SolverParams sp = to_params(o);
+  TZ_REQUIRE(sp.max_iter >= 1 && sp.rho > 0 && sp.rho_act > 0 && sp.rho_inact > 0 && sp.alpha > 0 && sp.alpha < 2,
+             "bad solver options");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const TzProgram* p0 = s->progs[0];
+  const int np = (int)s->progs.size();
+  switch (p0->bucket) {
+    case 0: return launch_bucket_set<B0>(p0, s->entries_dev, np, s->max_scen, sp, a, st);
+    case 1: return launch_bucket_set<B1>(p0, s->entries_dev, np, s->max_scen, sp, a, st);
+    case 2: return launch_bucket_set<B2>(p0, s->entries_dev, np, s->max_scen, sp, a, st);
+    case 3: return launch_bucket_set<B3>(p0, s->entries_dev, np, s->max_scen, sp, a, st);
+  }
+  return fail(TZ_EINVAL, "corrupt program handle");
+}
+
+extern "C" int tz_solve_set(const TzProgramSet* set, const TzSolverOpts* opts, int64_t S, const double* xbar0,
+                            const double* e0, double* cost, double* v, double* xbar_traj, double* ze1, int32_t* status,
+                            int32_t* iters, double* warm, void* stream) {
+  TZ_REQUIRE(S == 0 || (xbar0 && e0 && status), "xbar0, e0 and status are required");
+  StepArgs a{};
+  a.S = S; a.ld = S; a.xbar0 = xbar0; a.e0 = e0; a.cost = cost; a.v = v; a.xbar_traj = xbar_traj; a.ze1 = ze1;
+  a.status = status; a.iters = iters; a.warm = warm;
+  return launch_set(set, opts, a, stream);
+}
+
+extern "C" int tz_closed_loop_step_set(const TzProgramSet* set, const TzSolverOpts* opts, int64_t S, double* x, double* xbar,
+                                       double* e, const double* noise, const double* x_restart, const double* A_true,
+                                       const double* B_true, double* cost, double* v, double* xbar_traj, double* ze1,
+                                       double* u_out, int32_t* status, int32_t* iters, double* warm, double* stats,
+                                       void* stream) {
+  TZ_REQUIRE(S == 0 || (x && xbar && e && A_true && B_true && status), "x, xbar, e, A_true, B_true, status are required");
+  StepArgs a{};
+  a.S = S; a.ld = S; a.xbar0 = xbar; a.e0 = e; a.x = x; a.xbar = xbar; a.e = e; a.noise = noise; a.x_restart = x_restart; a.A_true = A_true; a.B_true = B_true;
+  a.cost = cost; a.v = v; a.xbar_traj = xbar_traj; a.ze1 = ze1; a.u_out = u_out; a.status = status; a.iters = iters;
+  a.warm = warm; a.stats = stats;
+  return launch_set(set, opts, a, stream);
+}
+
 extern "C" int tz_qp_solve(const TzProgram* prog, const TzSolverOpts* opts, int64_t S, const double* q, const double* l,
                            const double* u, double* z, double* y, int32_t* status, int32_t* iters, void* stream) {
   TZ_REQUIRE(S == 0 || (q && l && u && z && status), "q, l, u, z, status are required");
@@ -330,7 +453,8 @@ extern "C" int tz_qp_solve(const TzProgram* prog, const TzSolverOpts* opts, int6
 static size_t host_scratch_doubles(const TzProgram* p, int64_t S) {
   const size_t n = p->n, nent = (size_t)p->n * (1 + p->g1), nt = (size_t)(p->N + 1) * p->n;
   // x, xbar, e, noise | cost | v | xbar_traj | ze1 | status (as int32, rounded up) | A, B
-  return (size_t)S * (4 * n + 1 + p->nv + nt + nent + 1) + (size_t)(n * n + n * p->m) + 16;
+  // ... | warm rows (active-set hints / ADMM iterate carried between calls when opts->warm_start != 0)
+  return (size_t)S * (4 * n + 1 + p->nv + nt + nent + 1 + (size_t)tz_program_warm_rows(p)) + (size_t)(n * n + n * p->m) + 16;
 }
 
 extern "C" size_t tz_closed_loop_step_host_scratch_bytes(const TzProgram* prog, int64_t S) {
@@ -349,6 +473,8 @@ extern "C" int tz_closed_loop_step_host(const TzProgram* prog, const TzSolverOpt
   if (S == 0) return TZ_OK;
   const TzProgram* p = prog;
   const int64_t n = p->n, m = p->m, nent = (int64_t)p->n * (1 + p->g1), nt = (int64_t)(p->N + 1) * p->n, nv = p->nv;
+  // packed tube (opts->tube_packed): only the entries of Ze[1].Z that are not structurally zero cross the bus
+  const int64_t tube_rows = (opts && opts->tube_packed) ? (int64_t)p->aux.n_nz : nent;
   if (nchunks < 1) nchunks = 1;
   if (nchunks > 16) nchunks = 16;
   if ((int64_t)nchunks > S) nchunks = (int)S;
@@ -359,6 +485,8 @@ extern "C" int tz_closed_loop_step_host(const TzProgram* prog, const TzSolverOpt
   double *dx = d, *dxb = dx + n * S, *de = dxb + n * S, *dw = de + n * S, *dcost = dw + n * S, *dv = dcost + S,
          *dtraj = dv + nv * S, *dze = dtraj + nt * S;
   int32_t* dst = reinterpret_cast<int32_t*>(dze + nent * S);
+  double* dwarm = dze + nent * S + S;      // behind the status words (S int32 <= S doubles)
+  const bool use_warm = opts && opts->warm_start != 0;
   cudaStream_t streams[16];
   for (int c = 0; c < nchunks; ++c) TZ_CUDA(cudaStreamCreateWithFlags(&streams[c], cudaStreamNonBlocking));
   int rc = TZ_OK;
@@ -396,6 +524,7 @@ extern "C" int tz_closed_loop_step_host(const TzProgram* prog, const TzSolverOpt
     a.xbar_traj = xbar_traj_host ? dtraj + s0 : nullptr;
     a.ze1 = ze1_host ? dze + s0 : nullptr;
     a.status = dst + s0;
+    a.warm = use_warm ? dwarm + s0 : nullptr;
     rc = launch(p, opts, a, st);
     if (rc != TZ_OK) break;
     err = d2h(x_host, dx, n, s0, cnt, st);
@@ -404,7 +533,7 @@ extern "C" int tz_closed_loop_step_host(const TzProgram* prog, const TzSolverOpt
     if (err == cudaSuccess && cost_host) err = d2h(cost_host, dcost, 1, s0, cnt, st);
     if (err == cudaSuccess && v_host) err = d2h(v_host, dv, nv, s0, cnt, st);
     if (err == cudaSuccess && xbar_traj_host) err = d2h(xbar_traj_host, dtraj, nt, s0, cnt, st);
-    if (err == cudaSuccess && ze1_host) err = d2h(ze1_host, dze, nent, s0, cnt, st);
+    if (err == cudaSuccess && ze1_host) err = d2h(ze1_host, dze, tube_rows, s0, cnt, st);
     if (err == cudaSuccess)
       err = cudaMemcpyAsync(status_host + s0, dst + s0, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
   }

@@ -189,7 +189,7 @@ __device__ __forceinline__ void zero_fill(const Aux& ax, const StepArgs& a, int6
 template <class BK, int W>
 __device__ __forceinline__ void output_phase(WarpBuf<BK>& wb, const double (*pre)[BK::SPO], const Aux& ax, const StepArgs& a,
                                              const double* __restrict__ tabd, const int* __restrict__ tabi, int64_t tile, int lane,
-                                             bool zero_done) {
+                                             bool zero_done, bool packed) {
   constexpr int SPW = BK::SPO, NW = BK::NW, NGRP = SPW / W, NSL = 32 / NGRP;
   using V = Vec<W>;
   V* const vt = nullptr;
@@ -214,7 +214,16 @@ __device__ __forceinline__ void output_phase(WarpBuf<BK>& wb, const double (*pre
   // ---- Ze[1].Z at the optimum (examples/2.pulley_sim.py:96: Zek.Z.value), dense n x (1+g1): zero-fill, then overwrite
   // the ~12 % entries that are not structurally zero (both writes merge in L2 before reaching HBM).  The warp barrier
   // between the two sits outside every lane-dependent branch (tiles at the end of a batch have dead lanes).
-  if (a.ze1) {
+  if (a.ze1 && packed) {
+    // packed tube: row i of the output is entry ent[i] of Ze[1].Z (tz_program_tube_pattern); structural zeros are not stored
+    if (any_live) {
+      double* base = a.ze1 + so;
+      const double* coef = tabd + ax.o_coef;
+      const int* idx = tabi + ax.o_idx;
+#pragma unroll 4
+      for (int i = slice; i < ax.n_nz; i += NSL) vstcs(base + (int64_t)i * LD, vmul(coef[i], om(idx[i])));
+    }
+  } else if (a.ze1) {
     if (any_live && !zero_done) zero_fill<BK, W>(ax, a, tile, lane);
     __syncwarp();
     if (any_live) {
@@ -326,12 +335,15 @@ __device__ __forceinline__ void output_phase(WarpBuf<BK>& wb, const double (*pre
 // Persistent kernel; every WARP loops on its own over tiles of SPW = 32/G scenarios, so there is
 // no CTA barrier after the program has been staged (a CTA barrier made fast warps wait for the
 // slowest ADMM solve of the CTA: 8 % of the samples in profiles/r1_v2_*).
+//
+// run_program: the work of one CTA on one program -- CTA share `vcta` of `ncta` over the scenarios [0, a.S) of that program.
+// step_kernel calls it once (its block index, its grid size); step_kernel_set (data-set axis: many programs in one launch)
+// calls it once per (program, share) job of the CTA.
 template <class BK>
-__global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel(const QpProg<BK>* __restrict__ gpg, const Aux ax,
-                                                                const SolverParams sp, const StepArgs a) {
+__device__ __forceinline__ void run_program(unsigned char* smem_raw, const QpProg<BK>* __restrict__ gpg, const Aux& ax,
+                                            const SolverParams& sp, const StepArgs& a, const unsigned vcta, const unsigned ncta) {
   constexpr int NZ = BK::NZ, NCL = BK::NCL, N2 = BK::N2, NU = BK::NU, NPAR = BK::NPAR, NAG = BK::NAG, NCHL = BK::NCHL,
                 NCOL = BK::NCOL, TPB = BK::TPB, G = BK::G, SPW = BK::SPW, NW = BK::NW, HP = BK::NPAR / 2;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem<BK>& sm = *reinterpret_cast<Smem<BK>*>(smem_raw);
   double* tabd = reinterpret_cast<double*>(smem_raw + sizeof(Smem<BK>));
   const int tid = threadIdx.x;
@@ -341,8 +353,8 @@ __global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel(const QpProg<BK
   WarpBuf<BK>& wb = sm.wb[wib];
   const bool explicit_qp = a.q_in != nullptr;
   const int64_t ntiles = (a.S + BK::SPO - 1) / BK::SPO;
-  const int64_t nwarps = (int64_t)gridDim.x * BK::WPB;
-  const int64_t otile0 = (int64_t)blockIdx.x * BK::WPB + wib;
+  const int64_t nwarps = (int64_t)ncta * BK::WPB;
+  const int64_t otile0 = (int64_t)vcta * BK::WPB + wib;
   const double* hintp = (sp.warm == 2 && !explicit_qp) ? a.warm : nullptr;
   // inputs of this warp's first output tile: in flight while the program is staged (cp.async group 0)
   if (!explicit_qp && otile0 < ntiles) prefetch_inputs<BK>(wb.pre[0], a, hintp, n, otile0, lane);
@@ -389,7 +401,7 @@ __global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel(const QpProg<BK
     }
     const double (*pre)[BK::SPO] = wb.pre[buf];
     // zero-fill slot of this warp: before solve tile 0, .., before solve tile TPO-1, or (== TPO) in the output phase
-    const int zslot = (!explicit_qp && a.ze1 != nullptr) ? (int)((blockIdx.x * BK::WPB + wib) % (BK::TPO + 1)) : BK::TPO;
+    const int zslot = (!explicit_qp && a.ze1 != nullptr && !sp.tube_packed) ? (int)((vcta * BK::WPB + wib) % (BK::TPO + 1)) : BK::TPO;
    #pragma unroll 1
    for (int half = 0; half < BK::TPO; ++half) {
     if (half == zslot) {
@@ -687,8 +699,8 @@ __global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel(const QpProg<BK
    }     // solve tiles of this output tile
     if (explicit_qp) continue;
     __syncwarp();
-    if (a.vec2) output_phase<BK, 2>(wb, pre, ax, a, tabd, tabi, otile, lane, zslot < BK::TPO);
-    else output_phase<BK, 1>(wb, pre, ax, a, tabd, tabi, otile, lane, zslot < BK::TPO);
+    if (a.vec2) output_phase<BK, 2>(wb, pre, ax, a, tabd, tabi, otile, lane, zslot < BK::TPO, sp.tube_packed != 0);
+    else output_phase<BK, 1>(wb, pre, ax, a, tabd, tabi, otile, lane, zslot < BK::TPO, sp.tube_packed != 0);
     __syncwarp();     // wb is rewritten by the next tile
   }
   if (a.stats != nullptr && a.x != nullptr) {
@@ -699,6 +711,51 @@ __global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel(const QpProg<BK
       for (int c = 0; c < BK::SPO; ++c) v_ += wb.stacc[lane][c];
       if (v_ != 0.0) atomicAdd(a.stats + lane, v_);
     }
+  }
+}
+
+// Persistent kernel of one program: one wave of CTAs.
+template <class BK>
+__global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel(const QpProg<BK>* __restrict__ gpg, const Aux ax,
+                                                                const SolverParams sp, const StepArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  run_program<BK>(smem_raw, gpg, ax, sp, a, blockIdx.x, gridDim.x);
+}
+
+// Data-set axis (BASELINE.json north_star: scenarios = noise realisations x initial states x DATA SETS): `nprog` programs
+// of identical structure -- the same problem built from different data sets, hence different (P, A, R, ...) -- in ONE
+// launch.  Scenarios [e.begin, e.end) of the batch belong to program e; every program gets `cps` CTA shares, job =
+// (program, share), and a CTA walks over its jobs re-staging the program in shared memory between them.
+struct SetEntry {
+  const void* pg;         // QpProg<bucket> image on the device
+  const double* tab;      // run-time tables (Aux::tab) of this program
+  int64_t begin, end;     // its scenarios
+};
+
+__device__ __forceinline__ StepArgs shift_args(const StepArgs& a, int64_t b, int64_t cnt) {
+  StepArgs r = a;
+  r.S = cnt;
+#define TZ_SH(f) if (r.f) r.f += b;
+  TZ_SH(xbar0) TZ_SH(e0) TZ_SH(x) TZ_SH(xbar) TZ_SH(e) TZ_SH(noise) TZ_SH(x_restart) TZ_SH(cost) TZ_SH(v) TZ_SH(xbar_traj)
+  TZ_SH(ze1) TZ_SH(u_out) TZ_SH(status) TZ_SH(iters) TZ_SH(warm)
+#undef TZ_SH
+  return r;
+}
+
+template <class BK>
+__global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel_set(const SetEntry* __restrict__ entries, const int nprog,
+                                                                    const int cps, const Aux ax0, const SolverParams sp,
+                                                                    const StepArgs a0) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int64_t njobs = (int64_t)nprog * cps;
+  for (int64_t job = blockIdx.x; job < njobs; job += gridDim.x) {
+    const int pj = (int)(job / cps), share = (int)(job - (int64_t)pj * cps);
+    const SetEntry en = entries[pj];
+    Aux ax = ax0;
+    ax.tab = en.tab;
+    const StepArgs a = shift_args(a0, en.begin, en.end - en.begin);
+    __syncthreads();                     // every warp is done with the previous job's program image
+    run_program<BK>(smem_raw, reinterpret_cast<const QpProg<BK>*>(en.pg), ax, sp, a, (unsigned)share, (unsigned)cps);
   }
 }
 
@@ -721,6 +778,7 @@ struct TzProgram {
   int nz = 0, nc = 0, n = 0, m = 0, N = 0, nv = 0, g1 = 0, npar = 0;
   int NZ = 0, NC = 0, G = 0;
   int NW = 0, OM_V = 0, OM_P = 0, OM_C = 0, HP = 0;     // om layout of the bucket (Bucket::OM_*)
+  std::vector<int32_t> tube_ent;         // entries of Ze[1].Z (row-major index) that are not structurally zero, in table order
   size_t smem_tab = 0;                   // bytes of the run-time tables staged behind Smem<bucket>
   int num_sms = 148;
 };
@@ -745,6 +803,32 @@ int launch_bucket(const TzProgram* p, const SolverParams& sp, const StepArgs& a,
   const int64_t wave = (int64_t)p->num_sms * BK::MINB;
   const unsigned grid = (unsigned)(need < wave ? need : wave);
   step_kernel<BK><<<grid, BK::TPB, smem, st>>>(reinterpret_cast<const QpProg<BK>*>(p->packed_dev), p->aux, sp, a);
+  TZ_CUDA(cudaGetLastError());
+  return TZ_OK;
+}
+
+// data-set axis: one launch over `nprog` programs (entries on the device); see step_kernel_set
+template <class BK>
+int launch_bucket_set(const TzProgram* p0, const SetEntry* entries_dev, int nprog, int64_t max_scen, const SolverParams& sp,
+                      const StepArgs& a, cudaStream_t st) {
+  const size_t smem = sizeof(Smem<BK>) + p0->smem_tab;
+  static bool configured = false;     // benign race: the attribute is idempotent
+  if (!configured) {
+    TZ_CUDA(cudaFuncSetAttribute(step_kernel_set<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(sizeof(Smem<BK>) + kMaxTabBytes)));
+    configured = true;
+  }
+  // CTA shares per program: the wave split evenly (rounded down, so that all jobs run in one round when nprog <= wave),
+  // never more than the largest program has warp-tiles for
+  const int64_t wave = (int64_t)p0->num_sms * BK::MINB;
+  const int64_t ntiles = (max_scen + BK::SPO - 1) / BK::SPO;
+  const int64_t need = (ntiles + BK::WPB - 1) / BK::WPB;
+  int64_t cps = wave / nprog;
+  if (cps < 1) cps = 1;
+  if (cps > need) cps = need;
+  const int64_t njobs = cps * nprog;
+  const unsigned grid = (unsigned)(njobs < wave ? njobs : wave);
+  step_kernel_set<BK><<<grid, BK::TPB, smem, st>>>(entries_dev, nprog, (int)cps, p0->aux, sp, a);
   TZ_CUDA(cudaGetLastError());
   return TZ_OK;
 }

@@ -30,11 +30,12 @@ class SolverOptions:
     polish: int = 3          # iterations of the active-set polish, 0 = off
     warm_start: int = 0      # 0 cold, 1 reuse (x, y) of the previous call, 2 active-set hint of the previous call
     cert_first: int = 3      # first ADMM iteration at which the active-set KKT certificate is tried, 0 = off
+    tube_packed: int = 0     # 1: Ze[1].Z is written as n_nz rows (Program.tube_pattern) instead of the dense n(1+g1) rows
 
     def pack(self) -> List[float]:
         return [self.rho, self.rho_active, self.rho_inactive, self.sigma, self.alpha, self.eps_abs, self.eps_rel,
                 float(self.max_iter), float(self.check_every), float(int(self.polish)), float(self.warm_start),
-                float(int(self.cert_first))]
+                float(int(self.cert_first)), float(int(self.tube_packed))]
 
 
 def _opts(o: List[float]) -> _abi.TzSolverOpts:
@@ -42,6 +43,7 @@ def _opts(o: List[float]) -> _abi.TzSolverOpts:
     s.rho, s.rho_active, s.rho_inactive, s.sigma, s.alpha, s.eps_abs, s.eps_rel = o[:7]
     s.max_iter, s.check_every, s.polish, s.warm_start = int(o[7]), int(o[8]), int(o[9]), int(o[10])
     s.cert_first = int(o[11]) if len(o) > 11 else 3
+    s.tube_packed = int(o[12]) if len(o) > 12 else 0
     return s
 
 
@@ -97,6 +99,47 @@ def closed_loop_step(prog: int, x: Tensor, xbar: Tensor, e: Tensor, noise: Tenso
                                             _ptr(x_restart), _ptr(A_true), _ptr(B_true), _ptr(cost), _ptr(v), _ptr(traj), _ptr(ze1),
                                             _ptr(u), _ptr(status), _ptr(iters), _ptr(warm), _ptr(stats), _stream(x))
     _abi.check(rc, "tz_closed_loop_step")
+
+
+@torch.library.custom_op("tzddpc::solve_set", mutates_args=("warm",), device_types="cuda")
+def solve_set(pset: int, dims: List[int], xbar0: Tensor, e0: Tensor, warm: Optional[Tensor], want_tube: bool,
+              opts: List[float]) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """`solve` over a program set (data-set axis: scenarios [begin[j], begin[j+1]) use the program of data set j).
+    dims = [n, nv, (N+1)n, tube rows]."""
+    _chk(xbar0), _chk(e0)
+    n, nv, nt, nent = dims
+    S = xbar0.shape[1]
+    dev = xbar0.device
+    cost = torch.empty(S, dtype=torch.float64, device=dev)
+    v = torch.empty((nv, S), dtype=torch.float64, device=dev)
+    traj = torch.empty((nt, S), dtype=torch.float64, device=dev)
+    ze1 = torch.empty((nent if want_tube else 0, S), dtype=torch.float64, device=dev)
+    status = torch.empty(S, dtype=torch.int32, device=dev)
+    iters = torch.empty(S, dtype=torch.int32, device=dev)
+    o = _opts(opts)
+    with torch.cuda.device(dev):
+        rc = _abi.lib().tz_solve_set(C.c_void_p(pset), C.byref(o), S, _ptr(xbar0), _ptr(e0), _ptr(cost), _ptr(v), _ptr(traj),
+                                     _ptr(ze1) if want_tube else None, _ptr(status), _ptr(iters), _ptr(warm), _stream(xbar0))
+    _abi.check(rc, "tz_solve_set")
+    return cost, v, traj, ze1, status, iters
+
+
+@torch.library.custom_op("tzddpc::closed_loop_step_set",
+                         mutates_args=("x", "xbar", "e", "cost", "v", "traj", "ze1", "u", "status", "iters", "warm", "stats"),
+                         device_types="cuda")
+def closed_loop_step_set(pset: int, x: Tensor, xbar: Tensor, e: Tensor, noise: Tensor, x_restart: Optional[Tensor],
+                         A_true: Tensor, B_true: Tensor, status: Tensor, cost: Optional[Tensor], v: Optional[Tensor],
+                         traj: Optional[Tensor], ze1: Optional[Tensor], u: Optional[Tensor], iters: Optional[Tensor],
+                         warm: Optional[Tensor], stats: Optional[Tensor], opts: List[float]) -> None:
+    """`closed_loop_step` over a program set: every data set's scenarios are stepped with that data set's program, one launch."""
+    _chk(x), _chk(xbar), _chk(e), _chk(noise), _chk(A_true), _chk(B_true), _chk(status, torch.int32)
+    S = x.shape[1]
+    o = _opts(opts)
+    with torch.cuda.device(x.device):
+        rc = _abi.lib().tz_closed_loop_step_set(C.c_void_p(pset), C.byref(o), S, _ptr(x), _ptr(xbar), _ptr(e), _ptr(noise),
+                                                _ptr(x_restart), _ptr(A_true), _ptr(B_true), _ptr(cost), _ptr(v), _ptr(traj),
+                                                _ptr(ze1), _ptr(u), _ptr(status), _ptr(iters), _ptr(warm), _ptr(stats), _stream(x))
+    _abi.check(rc, "tz_closed_loop_step_set")
 
 
 @torch.library.custom_op("tzddpc::interval_hull", mutates_args=(), device_types="cuda")

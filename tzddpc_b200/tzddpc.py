@@ -38,23 +38,36 @@ class _Value:
 
 class TubeHandle:
     """What `solve` returns in place of the reference's `CVXZonotope` Ze[1] (`tzddpc/tzddpc.py:377`):
-    `.Z.value` is the n x (1+g1) array [c, G] (batched: S x n x (1+g1)), fetched from the GPU lazily."""
+    `.Z.value` is the n x (1+g1) array [c, G] (batched: S x n x (1+g1)), fetched from the GPU lazily -- as the
+    reference's `.Z.value` evaluates its expression on access (examples/2.pulley_sim.py:96).
+    With `pattern` the device buffer is the packed tube (`SolverOptions.tube_packed`): row i = entry pattern[i] of Ze[1].Z,
+    every other entry is structurally zero; `.Z.value` scatters it into the dense matrix on the host."""
 
-    def __init__(self, ze1: torch.Tensor, n: int, g1: int, batched: bool):
-        self._ze1, self._n, self._g1, self._batched = ze1, n, g1, batched
+    def __init__(self, ze1: torch.Tensor, n: int, g1: int, batched: bool, pattern: Optional[np.ndarray] = None):
+        self._ze1, self._n, self._g1, self._batched, self._pattern = ze1, n, g1, batched, pattern
         self._host = None
 
     @property
     def Z(self) -> _Value:
         if self._host is None:
             S = self._ze1.shape[1]
-            a = self._ze1.reshape(self._n, 1 + self._g1, S).permute(2, 0, 1).cpu().numpy()
+            if self._pattern is None:
+                a = self._ze1.reshape(self._n, 1 + self._g1, S).permute(2, 0, 1).cpu().numpy()
+            else:
+                a = np.zeros((S, self._n * (1 + self._g1)))
+                a[:, self._pattern] = self._ze1.t().cpu().numpy()
+                a = a.reshape(S, self._n, 1 + self._g1)
             self._host = a if self._batched else a[0]
         return _Value(self._host)
 
     @property
     def device_tensor(self) -> torch.Tensor:
-        """(n, 1+g1, S) view of the device buffer (entry (r, j) of scenario s at [r, j, s])."""
+        """(n, 1+g1, S) view of the device buffer (entry (r, j) of scenario s at [r, j, s]); packed tubes are expanded."""
+        if self._pattern is not None:
+            S = self._ze1.shape[1]
+            d = torch.zeros((self._n * (1 + self._g1), S), dtype=torch.float64, device=self._ze1.device)
+            d[torch.as_tensor(self._pattern, dtype=torch.long, device=d.device)] = self._ze1
+            return d.reshape(self._n, 1 + self._g1, -1)
         return self._ze1.reshape(self._n, 1 + self._g1, -1)
 
     @property
@@ -83,6 +96,10 @@ class TZDDPC(object):
     Mdelta: MatrixZonotope
     MdataK: MatrixZonotope
     theta: Theta
+
+    # the launch entry points (TZDDPCEnsemble swaps in the program-set variants)
+    _solve_op = staticmethod(ops.solve)
+    _step_op = staticmethod(ops.closed_loop_step)
 
     def __init__(self, data: Data, device: Optional[Union[str, torch.device]] = None):
         """:param data: input/state data, each T x dim (tzddpc/tzddpc.py:20-28)."""
@@ -242,9 +259,11 @@ class TZDDPC(object):
         """xbar0, e0: (n, S) float64 CUDA tensors (scenario-fastest)."""
         assert self._program is not None, "call build_problem first"
         o = options or self.solver_options
-        cost, v, traj, ze1, status, iters = ops.solve(self._program.handle.value, self._dims, xbar0, e0, warm,
-                                                      want_tube, o.pack())
-        tube = TubeHandle(ze1, self.dim_x, self._program.compiled.g1, True) if want_tube else None
+        pattern = self._program.tube_pattern if o.tube_packed else None
+        dims = self._dims[:3] + [len(pattern) if o.tube_packed else self._dims[3]]
+        cost, v, traj, ze1, status, iters = self._solve_op(self._program.handle.value, dims, xbar0, e0, warm,
+                                                           want_tube, o.pack())
+        tube = TubeHandle(ze1, self.dim_x, self._program.compiled.g1, True, pattern) if want_tube else None
         return BatchSolveResult(cost, v, traj, tube, status, iters)
 
     def solve(self, xbar0: np.ndarray, e0: np.ndarray, **kwargs):
@@ -269,7 +288,7 @@ class TZDDPC(object):
             raise Exception('Error while solving the TZDDPC problem. Details: non-finite data')
         if np.isinf(cost[0]):
             raise Exception('Problem is unbounded')                          # tzddpc/tzddpc.py:374-375
-        tube = TubeHandle(r.tube._ze1, n, self._program.compiled.g1, False)
+        tube = TubeHandle(r.tube._ze1, n, self._program.compiled.g1, False, r.tube._pattern)
         return float(cost[0]), v[0], xbar[0], tube
 
     # ---- batched closed loop (examples/2.pulley_sim.py:62-103, one scenario per column) --------
@@ -312,13 +331,14 @@ class TZDDPC(object):
         stat = torch.empty((steps, S), dtype=torch.int32, device=dev)
         iters = torch.empty((steps, S), dtype=torch.int32, device=dev)
         stats = torch.zeros((steps, _abi.TZ_NSTATS), **f64)
-        tubes = torch.empty((steps, self._dims[3], S), **f64) if keep_tubes else None
+        pattern = self._program.tube_pattern if o.tube_packed else None
+        tubes = torch.empty((steps, len(pattern) if o.tube_packed else self._dims[3], S), **f64) if keep_tubes else None
         warm = torch.zeros((self._program.warm_rows, S), **f64) if o.warm_start else None
         xs[0], xbars[0], es[0] = x, xbar, e
         xr = x.clone() if restart else None
         h = self._program.handle.value
         for t in range(steps):
-            ops.closed_loop_step(h, x, xbar, e, w[t].contiguous(), xr, At, Bt, stat[t], costs[t], vs[t], None,
+            self._step_op(h, x, xbar, e, w[t].contiguous(), xr, At, Bt, stat[t], costs[t], vs[t], None,
                                  tubes[t] if keep_tubes else None, us[t], iters[t], warm, stats[t], o.pack())
             xs[t + 1], xbars[t + 1], es[t + 1] = x, xbar, e
         out = {"x": xs.permute(0, 2, 1).cpu().numpy(), "xbar": xbars.permute(0, 2, 1).cpu().numpy(),
@@ -327,5 +347,10 @@ class TZDDPC(object):
                "iters": iters.cpu().numpy(), "stats": stats.cpu().numpy()}
         if keep_tubes:
             g1 = self._program.compiled.g1
-            out["tubes"] = tubes.reshape(steps, n, 1 + g1, S).permute(0, 3, 1, 2).cpu().numpy()
+            if pattern is None:
+                out["tubes"] = tubes.reshape(steps, n, 1 + g1, S).permute(0, 3, 1, 2).cpu().numpy()
+            else:
+                dense = np.zeros((steps, S, n * (1 + g1)))
+                dense[:, :, pattern] = tubes.permute(0, 2, 1).cpu().numpy()
+                out["tubes"] = dense.reshape(steps, S, n, 1 + g1)
         return out
