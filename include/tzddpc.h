@@ -254,6 +254,27 @@ int tz_identify(int64_t S, int32_t T, int32_t n, int32_t m, int32_t gW,
                 const double* X, const double* U, const double* WZ, const double* K,
                 double* AB, double* dAB, double* dK, double* Pinv, int32_t* status, void* stream);
 
+/* Batched robust gain synthesis -- the counterpart of compute_theta / is_gain_robust (tzddpc/utils.py:58-129), one CTA per
+ * data set.  OPT-IN: the reference's K is "any feasible point" of an LMI found by an SDP solver and its adversary needs
+ * DCCP + MOSEK (utils.py:37,43-56), so K is not reproducible; this routine keeps compute_theta's alternation
+ *   K <- stabilising gain of (An, Bn)  [LQR gain of the DARE, Q = R = I]
+ *   (An, Bn) <- argmax ||A + B K||_F over M_Sigma, independent beta_A / beta_B (utils.py:13-41)
+ *               [convex-concave iteration beta <- -sign(gradient) from the centre and num_init-1 Philox starts]
+ *   until max(rho(An + Bn K), rho(A0 + B0 K)) < 1, or it changes by less than tol, or max_iter (utils.py:80-94)
+ * and the Monte-Carlo check of utils.py:105-129 with N = ceil(ln(1/confidence)/ln(1/(1-accuracy))) samples of M_Sigma.
+ *   AB    D x n x (n+m)      centre of M_Sigma (tz_identify)          Pinv  D x (T-1) x (n+m)  (tz_identify)
+ *   WZ    n x (1+gW)         the noise zonotope [c_W, G_W]
+ *   K     D x m x n          dA D x n x n = An - A0,  dB D x n x m = Bn - B0   (Theta, tzddpc/objects.py)
+ *   rho   D x 3              [rho(A0 + B0 K), rho(An + Bn K), largest sampled rho]
+ *   robust, iters, status    D (int32): is_gain_robust, outer iterations, TZ_STATUS_OK / TZ_STATUS_NONFINITE (DARE failed)
+ * Draws: Philox stream (seed, dataset_offset + data set, start or sample index, purposes 4 / 5). */
+int tz_gain_synthesis(int64_t D, int32_t T, int32_t n, int32_t m, int32_t gW, const double* AB, const double* Pinv,
+                      const double* WZ, double tol, int32_t max_iter, int32_t num_init, double accuracy, double confidence,
+                      uint64_t seed, int64_t dataset_offset, double* K, double* dA, double* dB, double* rho,
+                      int32_t* robust, int32_t* iters, int32_t* status, void* stream);
+/* N of the robustness check (utils.py:120), or -1 for arguments outside (0, 1) */
+int32_t tz_gain_robust_samples(double accuracy, double confidence);
+
 /* ------------------------------------------------------------------------------------
  * Counter-based random numbers (Philox4x32-10): key = seed, counter = (global scenario index, t, purpose, block).
  * The draws do not depend on how scenarios are sharded over GPUs (pass the shard's first scenario as scenario_offset);

@@ -43,7 +43,7 @@ EXPORTS = ["tz_version", "tz_last_error", "tz_device_cc", "tz_program_create", "
            "tz_closed_loop_step_host", "tz_interval_hull", "tz_reach_step", "tz_girard_reduce", "tz_tube_rollout",
            "tz_identify", "tz_qp_solve", "tz_philox4x32_10_host", "tz_sample_noise", "tz_generate_trajectories",
            "tz_program_tube_pattern", "tz_program_set_create", "tz_program_set_destroy", "tz_program_set_scenarios",
-           "tz_solve_set", "tz_closed_loop_step_set"]
+           "tz_solve_set", "tz_closed_loop_step_set", "tz_gain_synthesis", "tz_gain_robust_samples"]
 
 
 def lib() -> C.CDLL:
@@ -107,6 +107,10 @@ def lib() -> C.CDLL:
     L.tz_generate_trajectories.argtypes = [i64] + [i32] * 6 + [vp] * 5 + [u64, i64, vp, vp, vp]
     L.tz_identify.restype = C.c_int
     L.tz_identify.argtypes = [i64, i32, i32, i32, i32] + [vp] * 10
+    L.tz_gain_synthesis.restype = C.c_int
+    L.tz_gain_synthesis.argtypes = [i64, i32, i32, i32, i32, vp, vp, vp, dbl, i32, i32, dbl, dbl, u64, i64] + [vp] * 8
+    L.tz_gain_robust_samples.restype = i32
+    L.tz_gain_robust_samples.argtypes = [dbl, dbl]
     L.tz_qp_solve.restype = C.c_int
     L.tz_qp_solve.argtypes = [vp, C.POINTER(TzSolverOpts), i64] + [vp] * 8
     _lib = L

@@ -269,6 +269,26 @@ def identify(X: Tensor, U: Tensor, WZ: Tensor, K: Optional[Tensor], want_pinv: b
     return AB, dAB, dK, Pinv, status
 
 
+@torch.library.custom_op("tzddpc::gain_synthesis", mutates_args=(), device_types="cuda")
+def gain_synthesis(AB: Tensor, Pinv: Tensor, WZ: Tensor, tol: float, max_iter: int, num_init: int, accuracy: float,
+                   confidence: float, seed: int, dataset_offset: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """compute_theta + is_gain_robust (tzddpc/utils.py:58-129) batched over D data sets.  AB: (D, n, n+m), Pinv: (D, T-1, n+m),
+    WZ: (n, 1+gW).  Returns K (D, m, n), dA (D, n, n), dB (D, n, m), rho (D, 3), robust, iters, status (D, int32)."""
+    _chk(AB), _chk(Pinv), _chk(WZ)
+    D, n, d = AB.shape
+    m, Tm = d - n, Pinv.shape[1]
+    dev = AB.device
+    f64 = dict(dtype=torch.float64, device=dev)
+    K, dA, dB, rho = torch.empty((D, m, n), **f64), torch.empty((D, n, n), **f64), torch.empty((D, n, m), **f64), torch.empty((D, 3), **f64)
+    robust, iters, status = (torch.empty(D, dtype=torch.int32, device=dev) for _ in range(3))
+    with torch.cuda.device(dev):
+        rc = _abi.lib().tz_gain_synthesis(D, Tm + 1, n, m, WZ.shape[1] - 1, _ptr(AB), _ptr(Pinv), _ptr(WZ), float(tol), int(max_iter),
+                                          int(num_init), float(accuracy), float(confidence), int(seed), int(dataset_offset),
+                                          _ptr(K), _ptr(dA), _ptr(dB), _ptr(rho), _ptr(robust), _ptr(iters), _ptr(status), _stream(AB))
+    _abi.check(rc, "tz_gain_synthesis")
+    return K, dA, dB, rho, robust, iters, status
+
+
 @torch.library.custom_op("tzddpc::qp_solve", mutates_args=(), device_types="cuda")
 def qp_solve(prog: int, q: Tensor, l: Tensor, u: Tensor, opts: List[float]) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     """Explicit-instance batched ADMM: q (nz, S), l/u (nc, S) -> z (nz, S), y (nc, S), status, iters."""

@@ -168,18 +168,29 @@ class TZDDPC(object):
 
     # ---- tzddpc/tzddpc.py:87-93 -------------------------------------------------------------
     def compute_theta(self, tol: float = 1e-5, num_max_iterations: int = 20, num_initial_points: int = 10,
-                      K: Optional[np.ndarray] = None) -> Theta:
-        """The reference alternates an LMI feasibility SDP with a DCCP/MOSEK adversary
-        (tzddpc/utils.py:13-103).  That stack is out of scope: pass `K`, or an LQR gain for the
-        identified centre (Q = I, R = I) is used."""
+                      K: Optional[np.ndarray] = None, accuracy: float = 1e-2, confidence: float = 1e-5, seed: int = 25) -> Theta:
+        """tzddpc/tzddpc.py:87-93 -> tzddpc/utils.py:58-103.  The reference alternates an LMI feasibility SDP with a
+        DCCP/MOSEK adversary; that stack is absent and its gain is solver-dependent.  With `K` the caller's gain is used as
+        is (Theta's deltas are zero).  Without it the batched GPU synthesis `tz_gain_synthesis` runs the same alternation
+        (LQR gain of the adversarial pair, closed-form convex-concave adversary, Monte-Carlo robustness check) and fills
+        Theta(K, An - A0, Bn - B0); the reference's assertion `K is not robust` (utils.py:100) is kept."""
         assert self.Mdata is not None, 'Mdata is not defined'
         n, m = self.dim_x, self.dim_u
-        if K is None:
-            from scipy.linalg import solve_discrete_are
-            A, B = self._AB[:, :n], self._AB[:, n:]
-            P = solve_discrete_are(A, B, np.eye(n), np.eye(m))
-            K = -np.linalg.solve(np.eye(m) + B.T @ P @ B, B.T @ P @ A)
-        self.theta = Theta(np.asarray(K, dtype=np.float64).reshape(m, n), np.zeros((n, n)), np.zeros((n, m)))
+        if K is not None:
+            self.theta = Theta(np.asarray(K, dtype=np.float64).reshape(m, n), np.zeros((n, n)), np.zeros((n, m)))
+            return self.theta
+        Kd, dA, dB, rho, robust, iters, status = ops.gain_synthesis(
+            self._t(self._AB)[None], self._Pinv[None].contiguous(), self._t(self.zonotopes.W.Z), tol, num_max_iterations,
+            num_initial_points, accuracy, confidence, seed, 0)
+        if int(status[0].item()) != 0:
+            raise Exception('Gain synthesis failed: the Riccati iteration of the identified pair did not converge')
+        self.theta_info = {"rho_center": float(rho[0, 0]), "rho_adversarial": float(rho[0, 1]), "rho_sampled_max": float(rho[0, 2]),
+                           "iterations": int(iters[0]), "robust": bool(robust[0].item())}
+        if self.verbose:
+            print(f'Optimization completed. Closed loop spectral radius: {max(self.theta_info["rho_center"], self.theta_info["rho_adversarial"])}'
+                  f' - K {Kd[0].flatten().tolist()}')
+        assert self.theta_info["robust"], f'K is not robust with accuracy-confidence of {accuracy, 1 - confidence}'
+        self.theta = Theta(Kd[0].cpu().numpy(), dA[0].cpu().numpy(), dB[0].cpu().numpy())
         return self.theta
 
     # ---- tzddpc/tzddpc.py:95-130 ------------------------------------------------------------
