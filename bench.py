@@ -290,17 +290,12 @@ def datasets_leg(args, tz, ops, torch, dev, cfg, noise, nring):
     Z = tz.Zonotope
     zon = tz.SystemZonotopes(Z(*cfg.X0), Z(*cfg.U), Z(*cfg.X), Z(*cfg.W))
     t0 = time.perf_counter()
-    ctls = []
-    for d in range(D):
-        u_data, x_data = configs.generate_dataset(cfg, np.random.default_rng(cfg.seed + 101 * d))
-        c = tz.TZDDPC(tz.Data(u_data, x_data), device=dev)
-        c.verbose = False
-        c.build_zonotopes(zon)
-        Kg = configs.lqr_gain(c.Mdata.center[:, :n], c.Mdata.center[:, n:])
-        c.build_zonotopes_theta(zon, K=Kg)
-        c.build_problem(N, tz.StageCost(**cfg.cost), tz.BoxConstraint(**cfg.box) if cfg.box else tz.BoxConstraint())
-        ctls.append(c)
-    ens = tz.TZDDPCEnsemble(ctls, per)
+    data = [tz.Data(*configs.generate_dataset(cfg, np.random.default_rng(cfg.seed + 101 * d))) for d in range(D)]
+    # one tz_identify + one tz_gain_synthesis launch for all data sets, then the host canonicalisation per data set
+    ens = tz.TZDDPCEnsemble.from_datasets(data, zon, N, tz.StageCost(**cfg.cost),
+                                          tz.BoxConstraint(**cfg.box) if cfg.box else tz.BoxConstraint(), scenarios_per_dataset=per,
+                                          device=dev)
+    torch.cuda.synchronize(dev)
     setup_s = time.perf_counter() - t0
     prog = ens._program
     g1, nv = prog.compiled.g1, prog.compiled.nv
@@ -341,7 +336,8 @@ def datasets_leg(args, tz, ops, torch, dev, cfg, noise, nring):
     ms = a.elapsed_time(b) / Kd
     tot = stats[5:].sum(0).cpu().numpy()
     return {"datasets": D, "scenarios_per_dataset": per, "ms_per_step": ms, "value": S / (ms * 1e-3), "unit": UNIT, "steps": Kd,
-            "setup_s": setup_s, "api": "TZDDPCEnsemble -> tz_closed_loop_step_set (one launch per step, one program per data set)",
+            "setup_s": setup_s, "gain": "tz_gain_synthesis (one launch, a robust LQR gain per data set)",
+            "gain_iterations_max": int(ens.theta_info["iterations"].max()), "rho_max": float(ens.theta_info["rho"].max()), "api": "TZDDPCEnsemble -> tz_closed_loop_step_set (one launch per step, one program per data set)",
             "status_ok_frac": float(1.0 - (tot[3] + tot[4] + tot[6]) / max(tot[7], 1.0)), "iters_mean": float(tot[5] / max(tot[7], 1.0))}
 
 

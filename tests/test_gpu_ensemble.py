@@ -154,3 +154,30 @@ def test_packed_tube_scatters_to_the_dense_tube(cuda_lib, name):
     np.testing.assert_array_equal(tube.Z.value, tube2.Z.value)
     assert tube.Z.value.shape == (n, 1 + g1)
     np.testing.assert_array_equal(tube.device_tensor.cpu().numpy(), tube2.device_tensor.cpu().numpy())
+
+
+def test_from_datasets_batches_identification_and_gain_synthesis(cuda_lib):
+    """from_datasets (one identify / gain-synthesis launch for all data sets) builds the controllers the per-data-set route builds."""
+    import tzddpc_b200 as tz
+    cfg = configs.CONFIGS["fivedim"]()
+    D, per = 4, 32
+    data = [tz.Data(*common.dataset(cfg, seed=cfg.seed + 101 * d)) for d in range(D)]
+    Z = tz.Zonotope
+    zon = tz.SystemZonotopes(Z(*cfg.X0), Z(*cfg.U), Z(*cfg.X), Z(*cfg.W))
+    ens = tz.TZDDPCEnsemble.from_datasets(data, zon, cfg.horizon, tz.StageCost(**cfg.cost), tz.BoxConstraint(**cfg.box),
+                                          scenarios_per_dataset=per, num_initial_points=3, accuracy=0.05, confidence=1e-2)
+    assert ens.theta_info["robust"].all() and ens.K.shape == (D, cfg.m, cfg.n)
+    x0 = np.tile(np.asarray(cfg.X0[0], dtype=np.float64), (D * per, 1))
+    r = ens.simulate(cfg.A, cfg.B, x0, steps=6, seed=3, restart=True)
+    for d in range(D):
+        c = tz.TZDDPC(data[d])
+        c.verbose = False
+        c.build_zonotopes_theta(zon, K=ens.K[d])
+        c.build_problem(cfg.horizon, tz.StageCost(**cfg.cost), tz.BoxConstraint(**cfg.box))
+        for a, b in ((c.Mdata, ens.controllers[d].Mdata), (c.MdataK, ens.controllers[d].MdataK), (c.Mdelta, ens.controllers[d].Mdelta)):
+            np.testing.assert_allclose(a.center, b.center, rtol=1e-12, atol=1e-14)
+            np.testing.assert_allclose(a.generators, b.generators, rtol=1e-12, atol=1e-14)
+        sl = slice(d * per, (d + 1) * per)
+        rd = c.simulate(cfg.A, cfg.B, x0[sl], steps=6, seed=3, restart=True, scenario_offset=d * per)
+        for k in ("x", "u", "cost", "status"):
+            np.testing.assert_allclose(r[k][:, sl], rd[k], rtol=1e-9, atol=1e-9, err_msg=k)

@@ -15,6 +15,7 @@ import numpy as np
 import torch
 
 from . import _abi, ops
+from .objects import Data, SystemZonotopes
 from .ops import SolverOptions
 from .tzddpc import TZDDPC
 
@@ -53,6 +54,54 @@ class TZDDPCEnsemble(object):
         self.dim_x, self.dim_u, self.horizon, self._dims = c0.dim_x, c0.dim_u, c0.horizon, list(c0._dims)
         self.zonotopes = c0.zonotopes
         self.num_scenarios = int(self.begin[-1])
+
+    @classmethod
+    def from_datasets(cls, datasets: Sequence[Data], zonotopes: SystemZonotopes, horizon: int, build_loss, build_constraints=None,
+                      scenarios_per_dataset: Union[int, Sequence[int]] = 16, K: Optional[np.ndarray] = None, k0: Optional[int] = None,
+                      device=None, tol: float = 1e-5, num_max_iterations: int = 20, num_initial_points: int = 10,
+                      accuracy: float = 1e-2, confidence: float = 1e-5, seed: int = 25) -> "TZDDPCEnsemble":
+        """What the reference does once per data set -- TZDDPC(data), build_zonotopes_theta, build_problem
+        (examples/2.pulley_sim.py:59-75) -- for D data sets of equal length, with the device work batched over the data sets:
+        ONE tz_identify launch (model + pseudo-inverse), ONE tz_gain_synthesis launch (a gain per data set; or `K`, (m, n)
+        shared / (D, m, n) per data set), ONE tz_identify launch for the boxes of M_K; then the host canonicalisation and
+        tz_program_create per data set."""
+        import torch
+        ctls = [TZDDPC(d, device=device) for d in datasets]
+        c0 = ctls[0]
+        D, n, m = len(ctls), c0.dim_x, c0.dim_u
+        for c in ctls:
+            c.verbose = False
+            assert (c.dim_x, c.dim_u, c.num_samples) == (n, m, c0.num_samples), "data sets must have the same shape"
+        X = torch.stack([c0._t(d.x) for d in datasets]).contiguous()
+        U = torch.stack([c0._t(d.u) for d in datasets]).contiguous()
+        WZ = c0._t(zonotopes.W.Z)
+        AB, dAB, _, Pinv, status = ops.identify(X, U, WZ, None, True)
+        if int((status != 0).sum().item()) != 0:
+            raise Exception('Identification failed: [X0; U0] does not have full row rank')
+        info = None
+        if K is None:
+            Kd, dA, dB, rho, robust, iters, st = ops.gain_synthesis(AB, Pinv, WZ, tol, num_max_iterations, num_initial_points,
+                                                                    accuracy, confidence, seed, 0)
+            if int((st != 0).sum().item()) != 0:
+                raise Exception('Gain synthesis failed: a Riccati iteration did not converge')
+            assert bool(robust.bool().all().item()), f'K is not robust with accuracy-confidence of {accuracy, 1 - confidence}'
+            info = {"rho": rho.cpu().numpy(), "iterations": iters.cpu().numpy(), "robust": robust.cpu().numpy().astype(bool)}
+            dA_h, dB_h = dA.cpu().numpy(), dB.cpu().numpy()
+        else:
+            Kh = np.asarray(K, dtype=np.float64)
+            Kd = c0._t(np.broadcast_to(Kh.reshape((-1, m, n)) if Kh.ndim == 3 else Kh.reshape(1, m, n), (D, m, n)))
+            dA_h, dB_h = np.zeros((D, n, n)), np.zeros((D, n, m))
+        _, _, dK, _, _ = ops.identify(X, U, WZ, Kd.contiguous(), False)
+        AB_h, dAB_h, dK_h, K_h = AB.cpu().numpy(), dAB.cpu().numpy(), dK.cpu().numpy(), Kd.cpu().numpy()
+        from .objects import Theta
+        for d, c in enumerate(ctls):
+            theta = Theta(K_h[d].copy(), dA_h[d], dB_h[d])
+            if not c._adopt_model(zonotopes, AB_h[d], dAB_h[d], dK_h[d], theta):
+                c.build_zonotopes_theta(zonotopes, K=K_h[d])
+            c._build(int(horizon), build_loss, build_constraints, k0)
+        ens = cls(ctls, scenarios_per_dataset)
+        ens.theta_info = info
+        return ens
 
     @property
     def num_datasets(self) -> int:

@@ -219,6 +219,22 @@ class TZDDPC(object):
             self.Mdata, self.MdataK, self.Mdelta = self.Mdata.reduce(1), MK.reduce(1), Mdelta.reduce(1)
         return self.theta, self.Mdata
 
+    def _adopt_model(self, zonotopes: SystemZonotopes, AB: np.ndarray, dAB: np.ndarray, dK: np.ndarray, theta: Theta) -> bool:
+        """Takes an identified model computed elsewhere (TZDDPCEnsemble.from_datasets: one batched launch for all data sets)
+        in place of build_zonotopes_theta.  Only for the boxed branch (order-1 reduction boxes every generator); returns False
+        when the data set is so short that reduce(1) is a no-op and the caller must use build_zonotopes_theta."""
+        n, m = self.dim_x, self.dim_u
+        if zonotopes.W.num_generators * (self.num_samples - 1) <= n * (n + m):
+            return False
+        self.optimization_problem, self._program = None, None
+        self.zonotopes, self.theta = zonotopes, theta
+        self._AB, self._dAB, self._Pinv = AB, dAB, None
+        centreK = MatrixZonotope(AB, np.zeros((0, n, n + m))) * np.vstack([np.eye(n), theta.K])
+        self.MdataK = MatrixZonotope(centreK.center, boxed_generators(dK))                      # tzddpc/tzddpc.py:119,127
+        self.Mdelta = MatrixZonotope(np.zeros((n, n + m)), boxed_generators(dAB))               # :122-123,128
+        self.Mdata = MatrixZonotope(AB, boxed_generators(dAB))                                  # :126
+        return True
+
     # ---- tzddpc/tzddpc.py:132-241 / 243-355 -------------------------------------------------
     def _model(self) -> TubeModel:
         X, U = self.zonotopes.X.interval, self.zonotopes.U.interval
