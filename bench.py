@@ -580,7 +580,7 @@ def main():
     ap.add_argument("--eps", type=float, default=1e-6)
     ap.add_argument("--polish", type=int, default=3, help="augmented-Lagrangian iterations of the certificate / polish")
     ap.add_argument("--e2e-steps", type=int, default=20)
-    ap.add_argument("--e2e-chunks", type=int, default=4)
+    ap.add_argument("--e2e-chunks", type=int, default=2)
     ap.add_argument("--datasets", type=int, default=64, help="data sets of the data-set-axis leg (0 = skip)")
     ap.add_argument("--cpu-steps", type=int, default=1500)
     ap.add_argument("--cpu-cores", type=int, default=0, help="processes of the CPU baseline (0 = all host cores)")

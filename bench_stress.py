@@ -50,8 +50,9 @@ for order in (10, 20, 30):
     # stand-alone kernels at the same size
     Sz = min(S, 8192)
     Zin = torch.rand((Sz, n, 1 + gcap), dtype=torch.float64, device="cuda") - 0.5
-    t_reach = ev(lambda: torch.ops.tzddpc.reach_step(f(A), f(GK), Zin, None))
-    pre = torch.ops.tzddpc.reach_step(f(A), f(GK), Zin, None)
+    dA_, dGK_ = f(A), f(GK)          # (uploaded once: the timed region holds the kernel only)
+    t_reach = ev(lambda: torch.ops.tzddpc.reach_step(dA_, dGK_, Zin, None))
+    pre = torch.ops.tzddpc.reach_step(dA_, dGK_, Zin, None)
     bytes_reach = 8 * n * Sz * ((1 + gcap) + pre.shape[2])
     t_gir = ev(lambda: torch.ops.tzddpc.girard_reduce(pre, float(order), 0, gcap))
     bytes_gir = 8 * n * Sz * (pre.shape[2] + 1 + gcap)

@@ -35,6 +35,9 @@
 
 namespace tz {
 
+#ifndef TZ_SPO_MIN
+#define TZ_SPO_MIN 16      // scenarios per output tile (>= 16: full 128-byte lines of every SoA row)
+#endif
 template <int NZ_, int N2_, int NU_, int NL_, int G_, int NPAR_, int NAG_, int NCHK_, int MINB_>
 struct Bucket {
   static constexpr int NZ = NZ_, N2 = N2_, NU = NU_, NL = NL_, G = G_, NPAR = NPAR_, NAG = NAG_, NCHK = NCHK_;
@@ -47,7 +50,7 @@ struct Bucket {
   static constexpr int TPB = 128;
   static constexpr int WPB = TPB / 32;                // warps per CTA
   static constexpr int SPW = 32 / G;                  // scenarios per solve tile of a warp
-  static constexpr int TPO = (SPW >= 16) ? 1 : 16 / SPW;   // solve tiles per output tile: the output phase always covers
+  static constexpr int TPO = (SPW >= TZ_SPO_MIN) ? 1 : TZ_SPO_MIN / SPW;   // solve tiles per output tile: the output phase always covers
   static constexpr int SPO = SPW * TPO;               //   >= 16 consecutive scenarios = full 128-byte lines of every SoA row
   // layout of the per-scenario vector om = [1 | v (NZ) | xbar0 (HP) | e0 (HP) | centre of Ze[1] (HP) | x+ (HP)], HP = NPAR/2 >= dim_x
   static constexpr int HP = NPAR / 2;

@@ -85,11 +85,94 @@ __global__ void __launch_bounds__(256) reach_kernel(int n, int p, int N, int g, 
   }
 }
 
+// Fast path for the dimensions of the shipped systems (NN = n, PP = p exactly): the generic kernel above spends ~370 warp
+// instructions per output column (predicated NMAX-wide loops, one scalar shared load per FMA, an integer division per
+// column) and is ISSUE-bound at 64 % (profiles/r2_reach_girard_ncu.txt).  Here a thread owns column j of Z, keeps its PP
+// entries in registers and walks over the blocks b = 0..N: per output column NN*PP FMAs, NN*PP/2 16-byte broadcast loads
+// of the transposed, padded matrices and NN streaming stores -- the kernel becomes what it should be, a stream of writes.
+// Threads are arranged (column, block group) so that short zonotopes (1+g < 256) still fill the CTA.
+template <int NN, int PP>
+__global__ void __launch_bounds__(256) reach_kernel_fast(int N, int g, int gW, const double* __restrict__ C,
+                                                         const double* __restrict__ Gm, int per_scenario,
+                                                         const double* __restrict__ Z, const double* __restrict__ W,
+                                                         double* __restrict__ Zout, int jthreads) {
+  constexpr int NNP = NN + (NN & 1);               // padded row count: 16-byte aligned pairs
+  constexpr int MS = PP * NNP;                     // doubles per staged matrix, layout [k][r]
+  extern __shared__ __align__(16) double smf[];    // (N+1) * MS
+  const int64_t s = blockIdx.x;
+  const double* Cs = C + (per_scenario ? s * (int64_t)(NN * PP) : 0);
+  const double* Gs = Gm + (per_scenario ? s * (int64_t)N * (NN * PP) : 0);
+  for (int i = threadIdx.x; i < (N + 1) * MS; i += blockDim.x) {
+    const int b = i / MS, e = i - b * MS, k = e / NNP, r = e - k * NNP;
+    double v = 0.0;
+    if (r < NN) v = b == 0 ? Cs[r * PP + k] : Gs[(int64_t)(b - 1) * (NN * PP) + r * PP + k];
+    smf[i] = v;
+  }
+  __syncthreads();
+  const int ldz = 1 + g;
+  const int64_t ldo = (int64_t)(N + 1) * ldz + gW;
+  const double* Zs = Z + s * (int64_t)PP * ldz;
+  double* Os = Zout + s * (int64_t)NN * ldo;
+  const int tj = threadIdx.x % jthreads, tb = threadIdx.x / jthreads, bgroups = blockDim.x / jthreads;
+  for (int j = tj; j < ldz; j += jthreads) {
+    double z[PP];
+#pragma unroll
+    for (int k = 0; k < PP; ++k) z[k] = __ldg(Zs + (int64_t)k * ldz + j);
+    for (int b = tb; b <= N; b += bgroups) {
+      const double2* M2 = reinterpret_cast<const double2*>(smf + (size_t)b * MS);
+      double acc[NNP];
+#pragma unroll
+      for (int r = 0; r < NNP; ++r) acc[r] = 0.0;
+#pragma unroll
+      for (int k = 0; k < PP; ++k) {
+#pragma unroll
+        for (int r2 = 0; r2 < NNP / 2; ++r2) {
+          const double2 mv = M2[k * (NNP / 2) + r2];
+          acc[2 * r2] = fma(mv.x, z[k], acc[2 * r2]);
+          acc[2 * r2 + 1] = fma(mv.y, z[k], acc[2 * r2 + 1]);
+        }
+      }
+      if (b == 0 && j == 0 && W != nullptr) {
+#pragma unroll
+        for (int r = 0; r < NN; ++r) acc[r] += W[(int64_t)r * (1 + gW)];
+      }
+      double* o = Os + (int64_t)b * ldz + j;
+#pragma unroll
+      for (int r = 0; r < NN; ++r) __stcs(o + (int64_t)r * ldo, acc[r]);
+    }
+  }
+  for (int t = threadIdx.x; t < gW * NN; t += blockDim.x) {
+    const int r = t / gW, c = t - r * gW;
+    Os[(int64_t)r * ldo + (int64_t)(N + 1) * ldz + c] = W[(int64_t)r * (1 + gW) + 1 + c];
+  }
+}
+
+template <int NN, int PP>
+static int launch_reach_fast(int64_t S, int N, int g, int gW, const double* C, const double* Gm, int per_scenario,
+                             const double* Z, const double* W, double* Zout, cudaStream_t st) {
+  constexpr int NNP = NN + (NN & 1);
+  const size_t smem = (size_t)(N + 1) * PP * NNP * sizeof(double);
+  TZ_REQUIRE(smem <= 200 * 1024, "matrix zonotope too large for shared memory");
+  if (smem + 8192 > 48 * 1024)
+    TZ_CUDA(cudaFuncSetAttribute(reach_kernel_fast<NN, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int jthreads = 32;
+  while (jthreads < 256 && jthreads < 1 + g) jthreads *= 2;       // a power of two >= 1+g (capped): column threads
+  reach_kernel_fast<NN, PP><<<(unsigned)S, 256, smem, st>>>(N, g, gW, C, Gm, per_scenario, Z, W, Zout, jthreads);
+  TZ_CUDA(cudaGetLastError());
+  return TZ_OK;
+}
+
 // ---------------------------------------------------------------------------------------
 // Girard reduction: one CTA per zonotope, generator block in shared memory.
 //   metric per column -> 64-bit radix select of the nReduced smallest (ties: lowest index)
 //   -> box of the selected columns -> stable compaction of the kept columns + diag(d).
 // ---------------------------------------------------------------------------------------
+#ifndef TZ_GIRARD_AGG
+#define TZ_GIRARD_AGG 0
+#endif
+#ifndef TZ_GIRARD_BATCH
+#define TZ_GIRARD_BATCH 2
+#endif
 constexpr int kGirardThreads = 256;
 constexpr int kGirardMaxDim = 128;    // vectorised matrix zonotopes reach n*(n+m) = 96
 
@@ -135,21 +218,48 @@ __device__ int girard_block(int n, int g, double order, int metric, const double
   const int per = (g + kGirardThreads - 1) / kGirardThreads;       // columns per thread (contiguous range)
   const int j0 = min(tid * per, g), j1 = min(j0 + per, g);
   // metric (rows accumulated r = 0..n-1, exactly as oracle/zono.py:_girard_metric) and zero filter
+  // Two columns x eight rows of loads are issued before any of them is consumed: with one dependent load per thread in
+  // flight the pass was latency-bound at ~1.5 TB/s (Little's law: 1,024 threads x 8 bytes per SM; profiles/r2_reach_girard_ncu.txt).
+  // Rows beyond n read as 0, which changes neither the sums nor the maximum (bit-exact against the row-by-row loop).
   int nnz_local = 0;
-  for (int j = tid; j < g; j += kGirardThreads) {
-    double sum = 0.0, mx = 0.0;
-    bool nzc = false;
-    for (int r = 0; r < n; ++r) {
-      const double a = fabs(G[(int64_t)r * ldg + j]);
-      nzc = nzc || (a != 0.0);
-      if (metric == 2) sum = __dadd_rn(sum, __dmul_rn(a, a));      // no FMA contraction: selection must match the oracle bit for bit
-      else sum += a;
-      mx = fmax(mx, a);
+  for (int ja = tid; ja < g; ja += TZ_GIRARD_BATCH * kGirardThreads) {
+    const int jc = ja + kGirardThreads;
+    const bool hc = TZ_GIRARD_BATCH == 2 && jc < g;
+    double sumA = 0.0, mxA = 0.0, sumC = 0.0, mxC = 0.0;
+    bool nzA = false, nzC = false;
+    for (int r0 = 0; r0 < n; r0 += 8) {
+      double a[8], c[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const bool in = r0 + i < n;
+        a[i] = in ? fabs(G[(int64_t)(r0 + i) * ldg + ja]) : 0.0;
+        c[i] = (in && hc) ? fabs(G[(int64_t)(r0 + i) * ldg + jc]) : 0.0;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        nzA = nzA || (a[i] != 0.0);
+        nzC = nzC || (c[i] != 0.0);
+        if (metric == 2) {       // no FMA contraction: selection must match the oracle bit for bit
+          sumA = __dadd_rn(sumA, __dmul_rn(a[i], a[i]));
+          sumC = __dadd_rn(sumC, __dmul_rn(c[i], c[i]));
+        } else {
+          sumA += a[i];
+          sumC += c[i];
+        }
+        mxA = fmax(mxA, a[i]);
+        mxC = fmax(mxC, c[i]);
+      }
     }
-    const double h = (metric == 0) ? (sum - mx) : sum;
-    key[j] = (unsigned long long)__double_as_longlong(h);      // h >= 0: bit pattern is order-preserving
-    flag[j] = nzc ? 1 : 0;
-    nnz_local += nzc ? 1 : 0;
+    const double hA = (metric == 0) ? (sumA - mxA) : sumA;
+    key[ja] = (unsigned long long)__double_as_longlong(hA);    // h >= 0: bit pattern is order-preserving
+    flag[ja] = nzA ? 1 : 0;
+    nnz_local += nzA ? 1 : 0;
+    if (hc) {
+      const double hC = (metric == 0) ? (sumC - mxC) : sumC;
+      key[jc] = (unsigned long long)__double_as_longlong(hC);
+      flag[jc] = nzC ? 1 : 0;
+      nnz_local += nzC ? 1 : 0;
+    }
   }
   int gnz;
   (void)block_exclusive_scan(nnz_local, warp_tot, gnz);
@@ -168,8 +278,21 @@ __device__ int girard_block(int n, int g, double order, int metric, const double
       __syncthreads();
       const unsigned long long prefix = sel_prefix;
       const unsigned long long himask = (pass == 7) ? 0ull : (~0ull << ((pass + 1) * 8));
+      // warp-aggregated histogram: the lanes holding the same digit elect one of them to add their count.  (The
+      // generator norms of one zonotope share their exponent bits, so in the leading passes EVERY key falls into the same
+      // bin: one shared-memory atomic per key serialised thousands of same-address updates per pass.)
+#if TZ_GIRARD_AGG
+      for (int jb = 0; jb < g; jb += kGirardThreads) {
+        const int j = jb + tid;
+        const bool act = j < g && flag[j] && ((key[j] & himask) == prefix);
+        const unsigned digit = act ? (unsigned)((key[j] >> (pass * 8)) & 0xffull) : 256u;
+        const unsigned peers = __match_any_sync(0xffffffffu, digit);
+        if (act && lane == __ffs(peers) - 1) atomicAdd(&hist[digit], __popc(peers));
+      }
+#else
       for (int j = tid; j < g; j += kGirardThreads)
         if (flag[j] && ((key[j] & himask) == prefix)) atomicAdd(&hist[(int)((key[j] >> (pass * 8)) & 0xffull)], 1);
+#endif
       __syncthreads();
       if (wid == 0) {        // warp 0 finds the digit: lane l owns bins 8l .. 8l+7
         int loc[8], tot = 0;
@@ -230,12 +353,19 @@ __device__ int girard_block(int n, int g, double order, int metric, const double
       double acc[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] = 0.0;
-      for (int j = tid; j < g; j += kGirardThreads)
-        if (flag[j] == 2) {
+      for (int ja = tid; ja < g; ja += TZ_GIRARD_BATCH * kGirardThreads) {       // two columns of loads in flight, same summation order
+        const int jc = ja + kGirardThreads;
+        const bool fa = flag[ja] == 2, fc = TZ_GIRARD_BATCH == 2 && jc < g && flag[jc] == 2;
+        double a[8], c[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (r0 + i < n) acc[i] += fabs(G[(int64_t)(r0 + i) * ldg + j]);
+        for (int i = 0; i < 8; ++i) {
+          const bool in = r0 + i < n;
+          a[i] = (fa && in) ? fabs(G[(int64_t)(r0 + i) * ldg + ja]) : 0.0;
+          c[i] = (fc && in) ? fabs(G[(int64_t)(r0 + i) * ldg + jc]) : 0.0;
         }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { acc[i] += a[i]; acc[i] += c[i]; }
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const double v = warp_sum(acc[i]);
@@ -584,6 +714,11 @@ extern "C" int tz_reach_step(int64_t S, int32_t n, int32_t p, int32_t N, int32_t
   const size_t smem = (size_t)(N + 1) * n * p * sizeof(double);
   TZ_REQUIRE(smem <= 200 * 1024, "matrix zonotope too large for shared memory");
   cudaStream_t st = (cudaStream_t)stream;
+  // exact-dimension fast paths: M_K (p = n) and M_Delta (p = n + 1) of the double integrator, the pulley and the 5-dim system
+#define TZ_FAST(NN, PP) \
+  if (n == NN && p == PP) return launch_reach_fast<NN, PP>(S, N, g, gW, C, Gm, per_scenario_model, Z, gW ? W : nullptr, Zout, st);
+  TZ_FAST(2, 2) TZ_FAST(2, 3) TZ_FAST(4, 4) TZ_FAST(4, 5) TZ_FAST(5, 5) TZ_FAST(5, 6)
+#undef TZ_FAST
   if (n <= 8) {
     if (smem + 8192 > 48 * 1024) TZ_CUDA(cudaFuncSetAttribute(reach_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     reach_kernel<8><<<(unsigned)S, 256, smem, st>>>(n, p, N, g, gW, C, Gm, per_scenario_model, Z, gW ? W : nullptr, Zout);
