@@ -181,3 +181,39 @@ def test_from_datasets_batches_identification_and_gain_synthesis(cuda_lib):
         rd = c.simulate(cfg.A, cfg.B, x0[sl], steps=6, seed=3, restart=True, scenario_offset=d * per)
         for k in ("x", "u", "cost", "status"):
             np.testing.assert_allclose(r[k][:, sl], rd[k], rtol=1e-9, atol=1e-9, err_msg=k)
+
+
+@pytest.mark.parametrize("horizon,k0", [(3, None), (4, None), (5, None), (4, 2)])
+def test_program_sets_on_the_larger_buckets(cuda_lib, horizon, k0):
+    """Longer horizons / the simplified variant use the kernel buckets B1-B3: a program set over three data sets of the
+    complexity-sweep system equals the three single-program solves, packed and dense tube alike."""
+    import tzddpc_b200 as tz
+    from tzddpc_b200 import _abi
+    cfg = configs.sweep()
+    ctls = []
+    for d in range(3):
+        u, x = common.dataset(cfg, seed=cfg.seed + 31 * d)
+        o, K = common.make_oracle(cfg, u, x, horizon=horizon, k0=k0)
+        ctls.append(common.make_product(cfg, u, x, K, horizon=horizon, k0=k0))
+    assert not ctls[0]._program.bucket.startswith("B0")
+    counts = [16, 32, 9]
+    ens = tz.TZDDPCEnsemble(ctls, counts)
+    S = sum(counts)
+    rng = np.random.default_rng(horizon)
+    Xi = o.zonotopes.X.interval
+    xb = Xi.left_limit + (Xi.right_limit - Xi.left_limit) * rng.uniform(0.3, 0.7, (S, cfg.n))
+    ee = rng.uniform(-0.01, 0.01, (S, cfg.n))
+    dev = ens.device
+    xbt, eet = torch.tensor(xb.T.copy(), device=dev), torch.tensor(ee.T.copy(), device=dev)
+    for packed in (0, 1):
+        opts = tz.SolverOptions(tube_packed=packed)
+        r = ens.solve_batch(xbt, eet, options=opts)
+        b = 0
+        for c, cnt in zip(ctls, counts):
+            rd = c.solve_batch(xbt[:, b:b + cnt].contiguous(), eet[:, b:b + cnt].contiguous(), options=opts)
+            assert torch.equal(rd.status, r.status[b:b + cnt])
+            for name in ("cost", "v", "xbar"):
+                assert torch.equal(torch.nan_to_num(getattr(rd, name), nan=-7.0), torch.nan_to_num(getattr(r, name)[..., b:b + cnt], nan=-7.0)), name
+            np.testing.assert_array_equal(rd.tube.Z.value, r.tube.Z.value[b:b + cnt])
+            b += cnt
+        assert int((r.status == 0).sum()) >= S // 2

@@ -25,30 +25,53 @@ constexpr int kMaxGW = 4;
 constexpr int kSquarings = 30;
 constexpr int kNN = kMaxN * kMaxN;
 
-__device__ double spectral_radius_sq(const double* M, int n) {
-  double X[kNN], Y[kNN];
-  for (int i = 0; i < n * n; ++i) X[i] = M[i];
+template <int N>
+__device__ double spectral_radius_n(const double* M) {
+  double X[N * N], Y[N * N];
+#pragma unroll
+  for (int i = 0; i < N * N; ++i) X[i] = M[i];
   double logr = 0.0, w = 1.0;
   for (int it = 0; it <= kSquarings; ++it) {
     double s2 = 0.0;
-    for (int i = 0; i < n * n; ++i) s2 = fma(X[i], X[i], s2);
+#pragma unroll
+    for (int i = 0; i < N * N; ++i) s2 = fma(X[i], X[i], s2);
     const double s = sqrt(s2);
     if (!(s < INFINITY)) return INFINITY;
     if (s == 0.0) return 0.0;
     logr = fma(w, log(s), logr);
     if (it == kSquarings) break;
     const double inv = 1.0 / s;
-    for (int i = 0; i < n * n; ++i) X[i] *= inv;
-    for (int i = 0; i < n; ++i)
-      for (int j = 0; j < n; ++j) {
+#pragma unroll
+    for (int i = 0; i < N * N; ++i) X[i] *= inv;
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
         double acc = 0.0;
-        for (int k = 0; k < n; ++k) acc = fma(X[i * n + k], X[k * n + j], acc);
-        Y[i * n + j] = acc;
+#pragma unroll
+        for (int k = 0; k < N; ++k) acc = fma(X[i * N + k], X[k * N + j], acc);
+        Y[i * N + j] = acc;
       }
-    for (int i = 0; i < n * n; ++i) X[i] = Y[i];
+#pragma unroll
+    for (int i = 0; i < N * N; ++i) X[i] = Y[i];
     w *= 0.5;
   }
   return exp(logr);
+}
+
+// rho(M) by repeated squaring; the matrix lives in registers (the size is a template parameter: with a run-time n the
+// two n x n arrays sat in local memory and their loads were 40 % of the kernel's stall samples, profiles/r1_gain_kernel_ncu.txt)
+__device__ double spectral_radius_sq(const double* M, int n) {
+  switch (n) {
+    case 1: return fabs(M[0]);
+    case 2: return spectral_radius_n<2>(M);
+    case 3: return spectral_radius_n<3>(M);
+    case 4: return spectral_radius_n<4>(M);
+    case 5: return spectral_radius_n<5>(M);
+    case 6: return spectral_radius_n<6>(M);
+    case 7: return spectral_radius_n<7>(M);
+    default: return spectral_radius_n<8>(M);
+  }
 }
 
 // C (p x r) = A (p x q) B (q x r)
