@@ -6,6 +6,8 @@
 // All three are HBM-bound (1-2 flop per byte): a warp / CTA owns one zonotope, rows are
 // contiguous so every global access is a full-line coalesced access, the generator block is
 // staged once in shared memory and never re-read from HBM.
+#include <cstdlib>
+
 #include "tz_common.cuh"
 
 namespace tz {
@@ -214,6 +216,7 @@ __device__ int girard_block(int n, int g, double order, int metric, const double
   __shared__ int sel_remaining, sel_done;
   __shared__ double dbox[kGirardMaxDim];
   __shared__ double red[kGirardThreads / 32][8];
+  __shared__ unsigned bits[kGirardThreads / 32][4];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int per = (g + kGirardThreads - 1) / kGirardThreads;       // columns per thread (contiguous range)
   const int j0 = min(tid * per, g), j1 = min(j0 + per, g);
@@ -222,6 +225,7 @@ __device__ int girard_block(int n, int g, double order, int metric, const double
   // flight the pass was latency-bound at ~1.5 TB/s (Little's law: 1,024 threads x 8 bytes per SM; profiles/r2_reach_girard_ncu.txt).
   // Rows beyond n read as 0, which changes neither the sums nor the maximum (bit-exact against the row-by-row loop).
   int nnz_local = 0;
+  unsigned long long kand = ~0ull, kor = 0ull;
   for (int ja = tid; ja < g; ja += TZ_GIRARD_BATCH * kGirardThreads) {
     const int jc = ja + kGirardThreads;
     const bool hc = TZ_GIRARD_BATCH == 2 && jc < g;
@@ -251,15 +255,22 @@ __device__ int girard_block(int n, int g, double order, int metric, const double
       }
     }
     const double hA = (metric == 0) ? (sumA - mxA) : sumA;
-    key[ja] = (unsigned long long)__double_as_longlong(hA);    // h >= 0: bit pattern is order-preserving
+    const unsigned long long kA = (unsigned long long)__double_as_longlong(hA);    // h >= 0: bit pattern is order-preserving
+    key[ja] = kA;
     flag[ja] = nzA ? 1 : 0;
-    nnz_local += nzA ? 1 : 0;
+    if (nzA) { ++nnz_local; kand &= kA; kor |= kA; }
     if (hc) {
       const double hC = (metric == 0) ? (sumC - mxC) : sumC;
-      key[jc] = (unsigned long long)__double_as_longlong(hC);
+      const unsigned long long kC = (unsigned long long)__double_as_longlong(hC);
+      key[jc] = kC;
       flag[jc] = nzC ? 1 : 0;
-      nnz_local += nzC ? 1 : 0;
+      if (nzC) { ++nnz_local; kand &= kC; kor |= kC; }
     }
+  }
+  {  // bits shared by all active keys of the zonotope (block-wide AND / OR): the select skips the passes over them
+    const unsigned ah = __reduce_and_sync(0xffffffffu, (unsigned)(kand >> 32)), al = __reduce_and_sync(0xffffffffu, (unsigned)kand);
+    const unsigned oh = __reduce_or_sync(0xffffffffu, (unsigned)(kor >> 32)), ol = __reduce_or_sync(0xffffffffu, (unsigned)kor);
+    if (lane == 0) { bits[wid][0] = ah; bits[wid][1] = al; bits[wid][2] = oh; bits[wid][3] = ol; }
   }
   int gnz;
   (void)block_exclusive_scan(nnz_local, warp_tot, gnz);
@@ -270,9 +281,23 @@ __device__ int girard_block(int n, int g, double order, int metric, const double
     if (n_unred < 0) n_unred = 0;
     n_red = gnz - n_unred;
     // ---- radix select (MSB first, 8 bits per pass) of the n_red-th smallest key among non-zero columns
-    if (tid == 0) { sel_prefix = 0ull; sel_remaining = n_red; sel_done = 0; }
+    // The generator norms of one zonotope share their sign / exponent bits: the passes over the bytes in which ALL active
+    // keys agree would put every key into one bin.  Start at the byte of the highest differing bit instead.
+    // (bits[][] was written before the barriers of the block scan above)
+    unsigned long long all_and = ~0ull, all_or = 0ull;
+#pragma unroll
+    for (int w = 0; w < kGirardThreads / 32; ++w) {
+      all_and &= ((unsigned long long)bits[w][0] << 32) | bits[w][1];
+      all_or |= ((unsigned long long)bits[w][2] << 32) | bits[w][3];
+    }
+    const unsigned long long kdiff = all_and ^ all_or;
+    int pass = kdiff == 0ull ? -1 : ((63 - __clzll((long long)kdiff)) >> 3);       // -1: all keys equal, only ties to rank
+    if (tid == 0) {
+      sel_prefix = pass >= 7 ? 0ull : (pass < 0 ? all_or : (all_or & (~0ull << ((pass + 1) * 8))));
+      sel_remaining = n_red;
+      sel_done = 0;
+    }
     __syncthreads();
-    int pass = 7;
     for (; pass >= 0; --pass) {
       hist[tid] = 0;                                           // kGirardThreads == 256 bins
       __syncthreads();
@@ -425,6 +450,245 @@ __global__ void __launch_bounds__(kGirardThreads) girard_kernel(int n, int g, do
   for (int r = tid; r < n; r += kGirardThreads) Os[(int64_t)r * ldo] = Zs[(int64_t)r * ldz];
   const int written = girard_block(n, g, order, metric, Zs + 1, ldz, key, flag, Os + 1, ldo, gout_cap);
   if (tid == 0) gout[s] = written;
+}
+
+// ---------------------------------------------------------------------------------------
+// Girard reduction, ONE WARP PER ZONOTOPE (north_star: "a warp-per-zonotope segmented sort/top-k kernel does the order
+// reduction").  Same semantics as girard_block, but nothing in it is a CTA barrier: the CTA version spent 26 % of its
+// samples at barriers and serialised its phases (metric -> select -> box -> output), so that only the CTAs that happened to
+// be in the metric phase had loads in flight (profiles/r1_reach_girard_ncu.txt).  Here up to 32 independent warps per SM
+// are each in their own phase.  Lanes stride the columns (j = 32 i + lane: every access a 256-byte run), the keys, flags
+// and the 256-bin histogram live in the warp's slice of shared memory, ranks in column order come from ballots.
+//   metric -> [common leading bytes of the keys skipped] -> 8-bit MSB-first radix select of the n_red-th smallest key ->
+//   ties by lowest index -> box of the selected columns -> kept columns in original order, diag(d), zero padding.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+// (hi, lo) += x with the rounding error of the addition kept in lo (Neumaier): the box is computed as
+// "sum over all columns minus sum over the kept columns", so that the generator block is read from HBM exactly once;
+// the compensation keeps the difference accurate to an ulp of the reduced sum even when the kept columns carry
+// almost all of a row's mass, and when the reduced entries of a row are all zero both sums go through the same
+// additions in the same order and cancel exactly.
+__device__ __forceinline__ void csum(double& hi, double& lo, double x) {
+  const double s = hi + x;
+  const double bb = s - hi;
+  lo += (hi - (s - bb)) + (x - bb);
+  hi = s;
+}
+__device__ __forceinline__ void cwarp(double& hi, double& lo) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double oh = __shfl_xor_sync(0xffffffffu, hi, o), ol = __shfl_xor_sync(0xffffffffu, lo, o);
+    // (both partners must arrive at the same bits: add the smaller-lane value to the larger-lane one in a fixed order)
+    const bool low = (threadIdx.x & o) == 0;
+    double h = low ? hi : oh, l = low ? lo : ol;
+    const double xh = low ? oh : hi, xl = low ? ol : lo;
+    csum(h, l, xh);
+    l += xl;
+    hi = h; lo = l;
+  }
+}
+
+__global__ void __launch_bounds__(32) girard_warp_kernel(int n, int g, double order, int metric, const double* __restrict__ Z,
+                                                         int gout_cap, double* __restrict__ Zout, int32_t* __restrict__ gout) {
+  extern __shared__ __align__(16) unsigned char smw[];
+  unsigned long long* key = reinterpret_cast<unsigned long long*>(smw);      // g
+  int* hist = reinterpret_cast<int*>(key + g);                                // 256
+  unsigned char* flag = reinterpret_cast<unsigned char*>(hist + 256);         // g: 0 zero, 1 keep, 2 reduce
+  const int lane = threadIdx.x;
+  const int64_t s = blockIdx.x;
+  const int ldz = 1 + g, ldo = 1 + gout_cap;
+  const double* G = Z + s * (int64_t)n * ldz + 1;
+  double* Os = Zout + s * (int64_t)n * ldo;
+  double* out = Os + 1;
+  const int64_t ldg = ldz;
+  for (int r = lane; r < n; r += 32) Os[(int64_t)r * ldo] = G[(int64_t)r * ldg - 1];      // centre
+  // ---- metric (rows accumulated r = 0..n-1, exactly as oracle/zono.py:_girard_metric), zero filter, row sums of |G|
+  int nnz_local = 0;
+  unsigned long long kand = ~0ull, kor = 0ull;
+  double bh[8], bl[8];                                         // n <= 8: sum_j |G[r][j]| over this lane's columns
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { bh[i] = 0.0; bl[i] = 0.0; }
+  for (int ja = lane; ja < g; ja += 64) {
+    const int jc = ja + 32;
+    const bool hc = jc < g;
+    double a[8], c[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const bool in = i < n;
+      a[i] = in ? fabs(__ldcs(G + (int64_t)i * ldg + ja)) : 0.0;
+      c[i] = (in && hc) ? fabs(__ldcs(G + (int64_t)i * ldg + jc)) : 0.0;
+    }
+    double sumA = 0.0, mxA = 0.0, sumC = 0.0, mxC = 0.0;
+    bool nzA = false, nzC = false;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      nzA = nzA || (a[i] != 0.0);
+      nzC = nzC || (c[i] != 0.0);
+      if (metric == 2) {       // no FMA contraction: selection must match the oracle bit for bit
+        sumA = __dadd_rn(sumA, __dmul_rn(a[i], a[i]));
+        sumC = __dadd_rn(sumC, __dmul_rn(c[i], c[i]));
+      } else {
+        sumA += a[i];
+        sumC += c[i];
+      }
+      mxA = fmax(mxA, a[i]);
+      mxC = fmax(mxC, c[i]);
+      csum(bh[i], bl[i], a[i]);
+      csum(bh[i], bl[i], c[i]);
+    }
+    const unsigned long long kA = (unsigned long long)__double_as_longlong((metric == 0) ? (sumA - mxA) : sumA);
+    key[ja] = kA;                                              // h >= 0: the bit pattern is order-preserving
+    flag[ja] = nzA ? 1 : 0;
+    if (nzA) { ++nnz_local; kand &= kA; kor |= kA; }
+    if (hc) {
+      const unsigned long long kC = (unsigned long long)__double_as_longlong((metric == 0) ? (sumC - mxC) : sumC);
+      key[jc] = kC;
+      flag[jc] = nzC ? 1 : 0;
+      if (nzC) { ++nnz_local; kand &= kC; kor |= kC; }
+    }
+  }
+  const int gnz = __reduce_add_sync(0xffffffffu, nnz_local);
+  __syncwarp();
+  const bool do_reduce = (double)gnz > order * (double)n;
+  if (do_reduce) {
+    int n_unred = (int)floor((double)n * (order - 1.0));
+    if (n_unred < 0) n_unred = 0;
+    const int n_red = gnz - n_unred;
+    // bits shared by every active key need no pass: start at the byte of the highest differing bit
+    const unsigned and_hi = __reduce_and_sync(0xffffffffu, (unsigned)(kand >> 32)), and_lo = __reduce_and_sync(0xffffffffu, (unsigned)kand);
+    const unsigned or_hi = __reduce_or_sync(0xffffffffu, (unsigned)(kor >> 32)), or_lo = __reduce_or_sync(0xffffffffu, (unsigned)kor);
+    const unsigned long long all_and = ((unsigned long long)and_hi << 32) | and_lo, all_or = ((unsigned long long)or_hi << 32) | or_lo;
+    const unsigned long long diff = all_and ^ all_or;
+    unsigned long long thr;
+    bool whole = false;
+    int ties_needed = n_red;
+    if (diff == 0ull) {
+      thr = all_or;                                            // all active keys are equal: the first n_red of them are reduced
+    } else {
+      int pass = (63 - __clzll((long long)diff)) >> 3;
+      unsigned long long prefix = pass == 7 ? 0ull : (all_or & (~0ull << ((pass + 1) * 8)));
+      int remaining = n_red;
+      for (; pass >= 0; --pass) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) hist[lane * 8 + i] = 0;
+        __syncwarp();
+        const unsigned long long himask = (pass == 7) ? 0ull : (~0ull << ((pass + 1) * 8));
+        for (int j = lane; j < g; j += 32)
+          if (flag[j] && ((key[j] & himask) == prefix)) atomicAdd(&hist[(int)((key[j] >> (pass * 8)) & 0xffull)], 1);
+        __syncwarp();
+        int tot = 0;                                           // lane l owns bins 8l .. 8l+7
+        int loc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { loc[i] = hist[lane * 8 + i]; tot += loc[i]; }
+        int inc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += t;
+        }
+        const int before = inc - tot;                          // keys in the bins of lower lanes
+        const bool mine = before < remaining && remaining <= inc;      // the remaining-th smallest lies in one of my bins
+        int acc = before, d = 0, cnt = 0;
+        bool found = false;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (!found) {
+            if (acc + loc[i] >= remaining) { d = i; cnt = loc[i]; found = true; }
+            else acc += loc[i];
+          }
+        }
+        const int owner = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;      // exactly one lane
+        const int o_acc = __shfl_sync(0xffffffffu, acc, owner), o_d = __shfl_sync(0xffffffffu, d, owner);
+        const int o_cnt = __shfl_sync(0xffffffffu, cnt, owner);
+        const unsigned long long digit = (unsigned long long)(owner * 8 + o_d);
+        __syncwarp();
+        if (o_acc + o_cnt == remaining) {
+          // the bucket is consumed whole: every key with this prefix and digit is reduced, no need to refine
+          const unsigned long long low = pass == 0 ? 0ull : ((1ull << (pass * 8)) - 1ull);
+          prefix = prefix | (digit << (pass * 8)) | low;
+          remaining = 0;
+          whole = true;
+          break;
+        }
+        prefix = prefix | (digit << (pass * 8));
+        remaining -= o_acc;
+      }
+      thr = prefix;
+      ties_needed = remaining;
+    }
+    // keys < thr are reduced; among keys == thr the first `ties_needed` in column order (whole: all keys <= thr)
+    int taken = 0;
+    for (int j0 = 0; j0 < g; j0 += 32) {
+      const int j = j0 + lane;
+      const bool act = j < g && flag[j] != 0;
+      const unsigned long long k = act ? key[j] : 0ull;
+      const bool tie = act && !whole && k == thr;
+      const unsigned tb = __ballot_sync(0xffffffffu, tie);
+      const int rank = taken + __popc(tb & lanemask_lt());
+      if (act) {
+        if (whole) { if (k <= thr) flag[j] = 2; }
+        else if (k < thr) flag[j] = 2;
+        else if (tie && rank < ties_needed) flag[j] = 2;
+      }
+      taken += __popc(tb);
+    }
+    __syncwarp();
+  }
+  // ---- output: kept columns in original order (their |.| row sums are taken off the totals), then diag(d), zero padding
+  double kh[8], kl[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { kh[i] = 0.0; kl[i] = 0.0; }
+  int written = 0;
+  for (int j0 = 0; j0 < g; j0 += 32) {
+    const int j = j0 + lane;
+    const bool keep = j < g && flag[j] == 1;
+    const unsigned kb = __ballot_sync(0xffffffffu, keep);
+    const int pos = written + __popc(kb & lanemask_lt());
+    if (keep) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (i < n) {
+          const double v = G[(int64_t)i * ldg + j];
+          if (pos < gout_cap) out[(int64_t)i * ldo + pos] = v;
+          csum(kh[i], kl[i], fabs(v));
+        }
+      }
+    }
+    written += __popc(kb);
+  }
+  if (do_reduce) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      cwarp(bh[i], bl[i]);
+      cwarp(kh[i], kl[i]);
+      // d_r = (total - kept), never negative
+      const double dh = bh[i] - kh[i];
+      const double bb = dh - bh[i];
+      const double err = (bh[i] - (dh - bb)) + (-kh[i] - bb);
+      bh[i] = fmax(dh + (err + (bl[i] - kl[i])), 0.0);
+    }
+    for (int i = lane; i < n * n; i += 32) {
+      const int r = i / n, c = i - r * n;
+      double dv = 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) dv = (q == r) ? bh[q] : dv;
+      if (written + c < gout_cap) out[(int64_t)r * ldo + written + c] = (r == c) ? dv : 0.0;
+    }
+    written += n;
+  }
+  if (written > gout_cap) written = -written;          // signals "gout_cap too small"
+  const int wpos = written < 0 ? gout_cap : written;
+  const int padc = gout_cap - wpos;
+  for (int i = lane; i < n * padc; i += 32) {
+    const int r = i / padc, c = i - r * padc;
+    out[(int64_t)r * ldo + wpos + c] = 0.0;
+  }
+  if (lane == 0) gout[s] = written;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -736,6 +1000,20 @@ extern "C" int tz_girard_reduce(int64_t S, int32_t n, int32_t g, double order, i
   TZ_REQUIRE(metric >= 0 && metric <= 2, "metric must be 0 (l1-linf), 1 (l1) or 2 (l2)");
   if (S == 0) return TZ_OK;
   TZ_REQUIRE(Z && Zout && gout, "null pointer");
+  {  // Short zonotopes (the tubes Ze[1] of the examples: 24 / 75 / 113 generators): one warp per zonotope, a 256-thread CTA
+     // would idle.  Measured on B200 (n = 5, order 3, scratch/girard_small.py): warp kernel 2.0x / 1.7x / 1.1x faster at
+     // g = 32 / 64 / 113, CTA kernel 1.2x / 1.6x / 1.7x faster at g = 256 / 512 / 1024 and 1.4-2.6x at the stress sizes.
+    const size_t smw = (size_t)g * 9 + 256 * sizeof(int) + 32;
+    static const char* force = getenv("TZ_GIRARD_KERNEL");                 // "cta" / "warp": A/B switch for the benches
+    const bool want_warp = force ? (force[0] == 'w') : (g <= 128);
+    if (want_warp && n <= 8 && smw <= 56 * 1024) {
+      if (smw + 8192 > 48 * 1024)
+        TZ_CUDA(cudaFuncSetAttribute(girard_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw));
+      girard_warp_kernel<<<(unsigned)S, 32, smw, (cudaStream_t)stream>>>(n, g, order, metric, Z, gout_cap, Zout, gout);
+      TZ_CUDA(cudaGetLastError());
+      return TZ_OK;
+    }
+  }
   const size_t smem = (size_t)g * sizeof(unsigned long long) + (size_t)g + 16;
   TZ_REQUIRE(smem <= 200 * 1024, "too many generators (g=%d) for the shared-memory key table", g);
   if (smem + 8192 > 48 * 1024) TZ_CUDA(cudaFuncSetAttribute(girard_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
