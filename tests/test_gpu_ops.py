@@ -81,6 +81,28 @@ def test_girard_reduce(T, metric, n, g, order):
         assert not np.any(out[s, :, 1 + gout[s]:])
 
 
+@pytest.mark.parametrize("g", [40, 400])          # warp-per-zonotope kernel / CTA kernel
+def test_girard_reduce_row_carried_by_the_kept_generators(T, g):
+    """Row 0 is non-zero only in the three generators of largest metric (kept at order 2, n = 3): its box entry is exactly 0
+    (the warp kernel computes the box as total minus kept row sums: they must cancel exactly here)."""
+    rng = np.random.default_rng(g)
+    n, order = 3, 2.0
+    Z = np.zeros((2, n, 1 + g))
+    Z[:, 1:, 1:] = 0.01 * rng.normal(size=(2, n - 1, g))
+    big = [5, g // 2, g - 2]
+    for j in big:
+        Z[:, :, 1 + j] = [[7.0 + j, 1.0 + 0.1 * j, -2.0 - 0.01 * j]] * 2
+    Z[1, 1, 1:] += 0.3                                  # second zonotope: another row with heavy cancellation (not exact)
+    out, gout = T.ops.tzddpc.girard_reduce(_gpu(T, Z), order, 0, 2 * n)
+    out, gout = out.cpu().numpy(), gout.cpu().numpy()
+    for s in range(2):
+        ref = girard_reduce_generators(Z[s, :, 1:], order)
+        assert gout[s] == ref.shape[1] == 2 * n
+        np.testing.assert_array_equal(out[s, :, 1:1 + n], ref[:, :n])
+        np.testing.assert_allclose(out[s, :, 1 + n:], ref[:, n:], rtol=common.GEN_RTOL, atol=1e-300)
+        assert out[s, 0, 1 + n] == 0.0
+
+
 def test_girard_reduce_matrix_zonotope_order_one(T):
     """MatrixZonotope.reduce(1) of tzddpc/tzddpc.py:126-128 on the vectorised generators (dimension n(n+m) = 30)."""
     cfg = configs.fivedim()
