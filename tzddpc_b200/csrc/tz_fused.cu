@@ -487,12 +487,28 @@ extern "C" int tz_closed_loop_step_host(const TzProgram* prog, const TzSolverOpt
   int32_t* dst = reinterpret_cast<int32_t*>(dze + nent * S);
   double* dwarm = dze + nent * S + S;      // behind the status words (S int32 <= S doubles)
   const bool use_warm = opts && opts->warm_start != 0;
-  cudaStream_t streams[16];
-  for (int c = 0; c < nchunks; ++c) TZ_CUDA(cudaStreamCreateWithFlags(&streams[c], cudaStreamNonBlocking));
+  // the chunk streams are created once per host thread and device and reused by later calls (creating and destroying
+  // them cost tens of microseconds of every call)
+  struct StreamPool {
+    cudaStream_t s[16];
+    cudaEvent_t plant = nullptr;      // A_true / B_true uploaded (on s[0]); the other chunk streams wait for it
+    int n = 0, dev = -1;
+  };
+  static thread_local StreamPool pool;
+  int cur_dev = 0;
+  TZ_CUDA(cudaGetDevice(&cur_dev));
+  if (pool.dev != cur_dev) { pool.n = 0; pool.dev = cur_dev; pool.plant = nullptr; }      // (streams of another device stay alive, unused)
+  if (!pool.plant) TZ_CUDA(cudaEventCreateWithFlags(&pool.plant, cudaEventDisableTiming));
+  while (pool.n < nchunks) {
+    TZ_CUDA(cudaStreamCreateWithFlags(&pool.s[pool.n], cudaStreamNonBlocking));
+    ++pool.n;
+  }
+  cudaStream_t* streams = pool.s;
   int rc = TZ_OK;
   cudaError_t err = cudaMemcpyAsync(dA, A_true_host, n * n * sizeof(double), cudaMemcpyHostToDevice, streams[0]);
   if (err == cudaSuccess) err = cudaMemcpyAsync(dB, B_true_host, n * m * sizeof(double), cudaMemcpyHostToDevice, streams[0]);
-  if (err == cudaSuccess) err = cudaStreamSynchronize(streams[0]);
+  if (err == cudaSuccess) err = cudaEventRecord(pool.plant, streams[0]);
+  for (int c = 1; c < nchunks && err == cudaSuccess; ++c) err = cudaStreamWaitEvent(streams[c], pool.plant, 0);
   int64_t per = (S + nchunks - 1) / nchunks;
   per = (per + 15) & ~(int64_t)15;          // whole tiles, 16-byte aligned chunk starts
   // The device arrays are SoA with leading dimension S; a chunk [s0, s1) of a d x S array is d strided
@@ -540,7 +556,6 @@ extern "C" int tz_closed_loop_step_host(const TzProgram* prog, const TzSolverOpt
   for (int c = 0; c < nchunks; ++c) {
     cudaError_t e2 = cudaStreamSynchronize(streams[c]);
     if (err == cudaSuccess) err = e2;
-    cudaStreamDestroy(streams[c]);
   }
   if (rc != TZ_OK) return rc;
   if (err != cudaSuccess) return fail(TZ_ECUDA, "closed_loop_step_host: %s", cudaGetErrorString(err));

@@ -169,12 +169,6 @@ static int launch_reach_fast(int64_t S, int N, int g, int gW, const double* C, c
 //   metric per column -> 64-bit radix select of the nReduced smallest (ties: lowest index)
 //   -> box of the selected columns -> stable compaction of the kept columns + diag(d).
 // ---------------------------------------------------------------------------------------
-#ifndef TZ_GIRARD_AGG
-#define TZ_GIRARD_AGG 0
-#endif
-#ifndef TZ_GIRARD_BATCH
-#define TZ_GIRARD_BATCH 2
-#endif
 constexpr int kGirardThreads = 256;
 constexpr int kGirardMaxDim = 128;    // vectorised matrix zonotopes reach n*(n+m) = 96
 
@@ -226,9 +220,9 @@ __device__ int girard_block(int n, int g, double order, int metric, const double
   // Rows beyond n read as 0, which changes neither the sums nor the maximum (bit-exact against the row-by-row loop).
   int nnz_local = 0;
   unsigned long long kand = ~0ull, kor = 0ull;
-  for (int ja = tid; ja < g; ja += TZ_GIRARD_BATCH * kGirardThreads) {
+  for (int ja = tid; ja < g; ja += 2 * kGirardThreads) {
     const int jc = ja + kGirardThreads;
-    const bool hc = TZ_GIRARD_BATCH == 2 && jc < g;
+    const bool hc = jc < g;
     double sumA = 0.0, mxA = 0.0, sumC = 0.0, mxC = 0.0;
     bool nzA = false, nzC = false;
     for (int r0 = 0; r0 < n; r0 += 8) {
@@ -303,21 +297,9 @@ __device__ int girard_block(int n, int g, double order, int metric, const double
       __syncthreads();
       const unsigned long long prefix = sel_prefix;
       const unsigned long long himask = (pass == 7) ? 0ull : (~0ull << ((pass + 1) * 8));
-      // warp-aggregated histogram: the lanes holding the same digit elect one of them to add their count.  (The
-      // generator norms of one zonotope share their exponent bits, so in the leading passes EVERY key falls into the same
-      // bin: one shared-memory atomic per key serialised thousands of same-address updates per pass.)
-#if TZ_GIRARD_AGG
-      for (int jb = 0; jb < g; jb += kGirardThreads) {
-        const int j = jb + tid;
-        const bool act = j < g && flag[j] && ((key[j] & himask) == prefix);
-        const unsigned digit = act ? (unsigned)((key[j] >> (pass * 8)) & 0xffull) : 256u;
-        const unsigned peers = __match_any_sync(0xffffffffu, digit);
-        if (act && lane == __ffs(peers) - 1) atomicAdd(&hist[digit], __popc(peers));
-      }
-#else
+      // (a warp-aggregated histogram via __match_any_sync was slower than these plain shared-memory atomics: DESIGN.md 5d)
       for (int j = tid; j < g; j += kGirardThreads)
         if (flag[j] && ((key[j] & himask) == prefix)) atomicAdd(&hist[(int)((key[j] >> (pass * 8)) & 0xffull)], 1);
-#endif
       __syncthreads();
       if (wid == 0) {        // warp 0 finds the digit: lane l owns bins 8l .. 8l+7
         int loc[8], tot = 0;
@@ -378,9 +360,9 @@ __device__ int girard_block(int n, int g, double order, int metric, const double
       double acc[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] = 0.0;
-      for (int ja = tid; ja < g; ja += TZ_GIRARD_BATCH * kGirardThreads) {       // two columns of loads in flight, same summation order
+      for (int ja = tid; ja < g; ja += 2 * kGirardThreads) {       // two columns of loads in flight, same summation order
         const int jc = ja + kGirardThreads;
-        const bool fa = flag[ja] == 2, fc = TZ_GIRARD_BATCH == 2 && jc < g && flag[jc] == 2;
+        const bool fa = flag[ja] == 2, fc = jc < g && flag[jc] == 2;
         double a[8], c[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
