@@ -338,7 +338,7 @@ struct TzProgramSet {
   std::vector<const TzProgram*> progs;
   std::vector<int64_t> begin;          // nprog + 1
   tz::SetEntry* entries_dev = nullptr;
-  int64_t max_scen = 0;
+  int64_t max_scen = 0, total_tiles = 0;
 };
 
 extern "C" int tz_program_set_create(const TzProgram* const* progs, int32_t nprog, const int64_t* begin, TzProgramSet** out) {
@@ -347,7 +347,7 @@ extern "C" int tz_program_set_create(const TzProgram* const* progs, int32_t npro
   TZ_REQUIRE(p0 != nullptr, "null program 0");
   TZ_REQUIRE(begin[0] == 0, "begin[0] must be 0");
   std::vector<tz::SetEntry> ent((size_t)nprog);
-  int64_t mx = 0;
+  int64_t mx = 0, tiles = 0;
   for (int j = 0; j < nprog; ++j) {
     const TzProgram* p = progs[j];
     TZ_REQUIRE(p != nullptr, "null program %d", j);
@@ -363,7 +363,8 @@ extern "C" int tz_program_set_create(const TzProgram* const* progs, int32_t npro
     TZ_REQUIRE(cnt >= 0, "begin[] must be non-decreasing");
     TZ_REQUIRE(begin[j] % 16 == 0, "begin[%d] = %lld: the scenarios of a program must start on a multiple of 16", j,
                (long long)begin[j]);
-    ent[j] = tz::SetEntry{p->packed_dev, a.tab, begin[j], begin[j + 1]};
+    ent[j] = tz::SetEntry{p->packed_dev, a.tab, begin[j], begin[j + 1], tiles};
+    tiles += (cnt + TZ_SPO_MIN - 1) / TZ_SPO_MIN;             // (every bucket has output tiles of TZ_SPO_MIN scenarios)
     if (cnt > mx) mx = cnt;
   }
   TzProgramSet* s = new (std::nothrow) TzProgramSet();
@@ -371,6 +372,7 @@ extern "C" int tz_program_set_create(const TzProgram* const* progs, int32_t npro
   s->progs.assign(progs, progs + nprog);
   s->begin.assign(begin, begin + nprog + 1);
   s->max_scen = mx;
+  s->total_tiles = tiles;
   cudaError_t err = cudaMalloc(&s->entries_dev, ent.size() * sizeof(tz::SetEntry));
   if (err == cudaSuccess) err = cudaMemcpy(s->entries_dev, ent.data(), ent.size() * sizeof(tz::SetEntry), cudaMemcpyHostToDevice);
   if (err != cudaSuccess) {
@@ -406,10 +408,10 @@ static int launch_set(const TzProgramSet* s, const TzSolverOpts* o, const StepAr
   const TzProgram* p0 = s->progs[0];
   const int np = (int)s->progs.size();
   switch (p0->bucket) {
-    case 0: return launch_bucket_set<B0>(p0, s->entries_dev, np, s->max_scen, sp, a, st);
-    case 1: return launch_bucket_set<B1>(p0, s->entries_dev, np, s->max_scen, sp, a, st);
-    case 2: return launch_bucket_set<B2>(p0, s->entries_dev, np, s->max_scen, sp, a, st);
-    case 3: return launch_bucket_set<B3>(p0, s->entries_dev, np, s->max_scen, sp, a, st);
+    case 0: return launch_bucket_set<B0>(p0, s->entries_dev, np, s->total_tiles, sp, a, st);
+    case 1: return launch_bucket_set<B1>(p0, s->entries_dev, np, s->total_tiles, sp, a, st);
+    case 2: return launch_bucket_set<B2>(p0, s->entries_dev, np, s->total_tiles, sp, a, st);
+    case 3: return launch_bucket_set<B3>(p0, s->entries_dev, np, s->total_tiles, sp, a, st);
   }
   return fail(TZ_EINVAL, "corrupt program handle");
 }

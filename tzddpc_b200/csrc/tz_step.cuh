@@ -336,12 +336,15 @@ __device__ __forceinline__ void output_phase(WarpBuf<BK>& wb, const double (*pre
 // no CTA barrier after the program has been staged (a CTA barrier made fast warps wait for the
 // slowest ADMM solve of the CTA: 8 % of the samples in profiles/r1_v2_*).
 //
-// run_program: the work of one CTA on one program -- CTA share `vcta` of `ncta` over the scenarios [0, a.S) of that program.
-// step_kernel calls it once (its block index, its grid size); step_kernel_set (data-set axis: many programs in one launch)
-// calls it once per (program, share) job of the CTA.
+// run_program: the work of one CTA on one program.  Warp w of the CTA takes the output tiles tile_first + w,
+// tile_first + w + tile_stride, ... below tile_limit of that program's scenarios [0, a.S).
+// step_kernel calls it once (tiles strided over the whole grid); step_kernel_set (data-set axis: many programs in one
+// launch) calls it once per program that intersects the CTA's contiguous range of tiles.
 template <class BK>
 __device__ __forceinline__ void run_program(unsigned char* smem_raw, const QpProg<BK>* __restrict__ gpg, const Aux& ax,
-                                            const SolverParams& sp, const StepArgs& a, const unsigned vcta, const unsigned ncta) {
+                                            const SolverParams& sp, const StepArgs& a, const int64_t tile_first,
+                                            const int64_t tile_stride, const int64_t tile_limit, const unsigned zseed,
+                                            const bool stage = true) {
   constexpr int NZ = BK::NZ, NCL = BK::NCL, N2 = BK::N2, NU = BK::NU, NPAR = BK::NPAR, NAG = BK::NAG, NCHL = BK::NCHL,
                 NCOL = BK::NCOL, TPB = BK::TPB, G = BK::G, SPW = BK::SPW, NW = BK::NW, HP = BK::NPAR / 2;
   Smem<BK>& sm = *reinterpret_cast<Smem<BK>*>(smem_raw);
@@ -352,13 +355,13 @@ __device__ __forceinline__ void run_program(unsigned char* smem_raw, const QpPro
   const int lane = tid & 31, wib = tid >> 5;
   WarpBuf<BK>& wb = sm.wb[wib];
   const bool explicit_qp = a.q_in != nullptr;
-  const int64_t ntiles = (a.S + BK::SPO - 1) / BK::SPO;
-  const int64_t nwarps = (int64_t)ncta * BK::WPB;
-  const int64_t otile0 = (int64_t)vcta * BK::WPB + wib;
+  const int64_t ntiles = tile_limit;
+  const int64_t nwarps = tile_stride;
+  const int64_t otile0 = tile_first + wib;
   const double* hintp = (sp.warm == 2 && !explicit_qp) ? a.warm : nullptr;
   // inputs of this warp's first output tile: in flight while the program is staged (cp.async group 0)
   if (!explicit_qp && otile0 < ntiles) prefetch_inputs<BK>(wb.pre[0], a, hintp, n, otile0, lane);
-  {  // stage the program and its tables once per CTA (persistent kernel: amortised over all tiles of this CTA): 16-byte
+  if (stage) {  // stage the program and its tables once per CTA (persistent kernel: amortised over all tiles of this CTA): 16-byte
      // cp.async copies, all in flight at once (a load/store loop serialised ~10 dependent round trips to L2 per thread)
     const char* src = reinterpret_cast<const char*>(gpg);
     char* dst = reinterpret_cast<char*>(&sm.pg);
@@ -375,10 +378,10 @@ __device__ __forceinline__ void run_program(unsigned char* smem_raw, const QpPro
     for (int i = tid; i < ax.n_int; i += TPB) tabi[i] = gi[i];
     cp_async_commit();
     cp_async_wait<0>();
+    __syncthreads();
+    for (int i = tid; i < BK::NC * NZ; i += TPB) (&sm.Aa[0][0])[i] = sp.alpha * (&sm.pg.A[0][0])[i];
+    __syncthreads();
   }
-  __syncthreads();
-  for (int i = tid; i < BK::NC * NZ; i += TPB) (&sm.Aa[0][0])[i] = sp.alpha * (&sm.pg.A[0][0])[i];
-  __syncthreads();
   const QpProg<BK>& pg = sm.pg;
   const int g = lane % G;                 // lane within the scenario's group
   const int sl = lane / G;                // scenario within the warp's tile (solve-phase mapping)
@@ -401,7 +404,7 @@ __device__ __forceinline__ void run_program(unsigned char* smem_raw, const QpPro
     }
     const double (*pre)[BK::SPO] = wb.pre[buf];
     // zero-fill slot of this warp: before solve tile 0, .., before solve tile TPO-1, or (== TPO) in the output phase
-    const int zslot = (!explicit_qp && a.ze1 != nullptr && !sp.tube_packed) ? (int)((vcta * BK::WPB + wib) % (BK::TPO + 1)) : BK::TPO;
+    const int zslot = (!explicit_qp && a.ze1 != nullptr && !sp.tube_packed) ? (int)((zseed + wib) % (BK::TPO + 1)) : BK::TPO;
    #pragma unroll 1
    for (int half = 0; half < BK::TPO; ++half) {
     if (half == zslot) {
@@ -719,17 +722,23 @@ template <class BK>
 __global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel(const QpProg<BK>* __restrict__ gpg, const Aux ax,
                                                                 const SolverParams sp, const StepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  run_program<BK>(smem_raw, gpg, ax, sp, a, blockIdx.x, gridDim.x);
+  run_program<BK>(smem_raw, gpg, ax, sp, a, (int64_t)blockIdx.x * BK::WPB, (int64_t)gridDim.x * BK::WPB,
+                  (a.S + BK::SPO - 1) / BK::SPO, blockIdx.x * BK::WPB);
 }
 
 // Data-set axis (BASELINE.json north_star: scenarios = noise realisations x initial states x DATA SETS): `nprog` programs
 // of identical structure -- the same problem built from different data sets, hence different (P, A, R, ...) -- in ONE
-// launch.  Scenarios [e.begin, e.end) of the batch belong to program e; every program gets `cps` CTA shares, job =
-// (program, share), and a CTA walks over its jobs re-staging the program in shared memory between them.
+// launch.  Scenarios [e.begin, e.end) of the batch belong to program e.  The output tiles of all programs are numbered
+// consecutively (e.tile_begin) and dealt out exactly as step_kernel deals out the tiles of one program: in round k the
+// WPB warps of CTA b take the tiles (b + k * gridDim.x) * WPB + w.  At any moment the grid therefore writes one contiguous
+// window of scenarios (DRAM page locality: giving every CTA its own contiguous range of tiles cost 12 %), the load is
+// balanced whatever the number and the sizes of the programs, and a CTA re-stages the program image in shared memory
+// only when its next tiles belong to another program (every round once the programs are smaller than a wave).
 struct SetEntry {
   const void* pg;         // QpProg<bucket> image on the device
   const double* tab;      // run-time tables (Aux::tab) of this program
   int64_t begin, end;     // its scenarios
+  int64_t tile_begin;     // number of output tiles of the programs before it
 };
 
 __device__ __forceinline__ StepArgs shift_args(const StepArgs& a, int64_t b, int64_t cnt) {
@@ -744,18 +753,46 @@ __device__ __forceinline__ StepArgs shift_args(const StepArgs& a, int64_t b, int
 
 template <class BK>
 __global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel_set(const SetEntry* __restrict__ entries, const int nprog,
-                                                                    const int cps, const Aux ax0, const SolverParams sp,
-                                                                    const StepArgs a0) {
+                                                                    const int64_t total_tiles, const Aux ax0,
+                                                                    const SolverParams sp, const StepArgs a0) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int64_t njobs = (int64_t)nprog * cps;
-  for (int64_t job = blockIdx.x; job < njobs; job += gridDim.x) {
-    const int pj = (int)(job / cps), share = (int)(job - (int64_t)pj * cps);
-    const SetEntry en = entries[pj];
+  if (nprog == 1) {                                // one program: exactly step_kernel (tiles strided over the grid, prefetch across rounds)
+    const SetEntry en = entries[0];
     Aux ax = ax0;
     ax.tab = en.tab;
     const StepArgs a = shift_args(a0, en.begin, en.end - en.begin);
-    __syncthreads();                     // every warp is done with the previous job's program image
-    run_program<BK>(smem_raw, reinterpret_cast<const QpProg<BK>*>(en.pg), ax, sp, a, (unsigned)share, (unsigned)cps);
+    run_program<BK>(smem_raw, reinterpret_cast<const QpProg<BK>*>(en.pg), ax, sp, a, (int64_t)blockIdx.x * BK::WPB,
+                    (int64_t)gridDim.x * BK::WPB, total_tiles, blockIdx.x * BK::WPB);
+    return;
+  }
+  int staged = -1;                                 // program whose image is in shared memory
+  int lo = 0;
+  // round k: the CTA's WPB warps take the consecutive tiles [base, base + WPB) of the global numbering
+  for (int64_t base = (int64_t)blockIdx.x * BK::WPB; base < total_tiles; base += (int64_t)gridDim.x * BK::WPB) {
+    const int64_t t1 = base + BK::WPB < total_tiles ? base + BK::WPB : total_tiles;
+    int hi = nprog - 1;                            // last program with tile_begin <= base (programs are visited in order)
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (entries[mid].tile_begin <= base) lo = mid;
+      else hi = mid - 1;
+    }
+    int j = lo;
+    for (int64_t t = base; t < t1 && j < nprog; ++j) {
+      const SetEntry en = entries[j];
+      const int64_t ntl = (en.end - en.begin + BK::SPO - 1) / BK::SPO;
+      const int64_t tend = en.tile_begin + ntl < t1 ? en.tile_begin + ntl : t1;
+      if (tend <= t) continue;                     // (an empty program)
+      Aux ax = ax0;
+      ax.tab = en.tab;
+      const StepArgs a = shift_args(a0, en.begin, en.end - en.begin);
+      const bool stage = staged != j;
+      if (stage && staged >= 0) __syncthreads();   // every warp is done with the previous program's image
+      staged = j;
+      // warp w takes tile (t + w) of the round when it belongs to this program (tile_stride: beyond the limit)
+      run_program<BK>(smem_raw, reinterpret_cast<const QpProg<BK>*>(en.pg), ax, sp, a, t - en.tile_begin, BK::WPB,
+                      tend - en.tile_begin, (unsigned)(base % 1024), stage);
+      t = tend;
+    }
   }
 }
 
@@ -809,7 +846,7 @@ int launch_bucket(const TzProgram* p, const SolverParams& sp, const StepArgs& a,
 
 // data-set axis: one launch over `nprog` programs (entries on the device); see step_kernel_set
 template <class BK>
-int launch_bucket_set(const TzProgram* p0, const SetEntry* entries_dev, int nprog, int64_t max_scen, const SolverParams& sp,
+int launch_bucket_set(const TzProgram* p0, const SetEntry* entries_dev, int nprog, int64_t total_tiles, const SolverParams& sp,
                       const StepArgs& a, cudaStream_t st) {
   const size_t smem = sizeof(Smem<BK>) + p0->smem_tab;
   static bool configured = false;     // benign race: the attribute is idempotent
@@ -818,20 +855,14 @@ int launch_bucket_set(const TzProgram* p0, const SetEntry* entries_dev, int npro
                                  (int)(sizeof(Smem<BK>) + kMaxTabBytes)));
     configured = true;
   }
-  // CTA shares per program: the wave split evenly (rounded down, so that all jobs run in one round when nprog <= wave),
-  // never more than the largest program has warp-tiles for
+  static_assert(BK::SPO == TZ_SPO_MIN, "tz_program_set_create counts output tiles of TZ_SPO_MIN scenarios");
+  // one wave of CTAs, each with an equal contiguous share of the tiles of all programs (at least one tile per warp)
   const int64_t wave = (int64_t)p0->num_sms * BK::MINB;
-  const int64_t ntiles = (max_scen + BK::SPO - 1) / BK::SPO;
-  const int64_t need = (ntiles + BK::WPB - 1) / BK::WPB;
-  int64_t cps = wave / nprog;
-  if (cps < 1) cps = 1;
-  if (cps > need) cps = need;
-  const int64_t njobs = cps * nprog;
-  const unsigned grid = (unsigned)(njobs < wave ? njobs : wave);
-  step_kernel_set<BK><<<grid, BK::TPB, smem, st>>>(entries_dev, nprog, (int)cps, p0->aux, sp, a);
+  const int64_t need = (total_tiles + BK::WPB - 1) / BK::WPB;
+  const unsigned grid = (unsigned)(need < wave ? need : wave);
+  step_kernel_set<BK><<<grid, BK::TPB, smem, st>>>(entries_dev, nprog, total_tiles, p0->aux, sp, a);
   TZ_CUDA(cudaGetLastError());
   return TZ_OK;
 }
-
 
 }  // namespace tz
