@@ -217,3 +217,21 @@ def test_program_sets_on_the_larger_buckets(cuda_lib, horizon, k0):
             np.testing.assert_array_equal(rd.tube.Z.value, r.tube.Z.value[b:b + cnt])
             b += cnt
         assert int((r.status == 0).sum()) >= S // 2
+
+
+def test_program_set_with_an_empty_data_set(cuda_lib):
+    """A data set without scenarios in the middle of the set is skipped; its neighbours are unaffected."""
+    import tzddpc_b200 as tz
+    cfg = configs.CONFIGS["pulley"]()
+    ctls, _ = _controllers(cfg, 3)
+    counts = [16, 0, 40]
+    ens = tz.TZDDPCEnsemble(ctls, counts)
+    S = sum(counts)
+    rng = np.random.default_rng(2)
+    x0 = np.tile(np.asarray(cfg.X0[0], dtype=np.float64), (S, 1))
+    noise = common.noise_for(cfg, 4, S, rng)
+    r = ens.simulate(cfg.A, cfg.B, x0, noise=noise, keep_tubes=True)
+    for c, sl in ((ctls[0], slice(0, 16)), (ctls[2], slice(16, 56))):
+        rd = c.simulate(cfg.A, cfg.B, x0[sl], noise=noise[:, sl], keep_tubes=True)
+        for k in ("x", "u", "cost", "status", "tubes"):
+            np.testing.assert_array_equal(r[k][:, sl], rd[k], err_msg=k)
