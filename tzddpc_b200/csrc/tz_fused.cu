@@ -404,9 +404,10 @@ static int launch_set(const TzProgramSet* s, const TzSolverOpts* o, const StepAr
   const SolverParams sp = to_params(o);
   TZ_REQUIRE(sp.max_iter >= 1 && sp.rho > 0 && sp.rho_act > 0 && sp.rho_inact > 0 && sp.alpha > 0 && sp.alpha < 2,
              "bad solver options");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const TzProgram* p0 = s->progs[0];
   const int np = (int)s->progs.size();
+  if (np == 1) return launch(p0, o, a_in, stream);       // one program: exactly step_kernel (tiles strided over the grid)
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (p0->bucket) {
     case 0: return launch_bucket_set<B0>(p0, s->entries_dev, np, s->total_tiles, sp, a, st);
     case 1: return launch_bucket_set<B1>(p0, s->entries_dev, np, s->total_tiles, sp, a, st);

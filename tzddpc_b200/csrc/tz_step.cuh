@@ -8,6 +8,14 @@
 
 #include "tz_admm.cuh"
 
+#ifndef TZ_NO_HINTS
+#define TZ_LIKELY(x) __builtin_expect(!!(x), 1)
+#define TZ_UNLIKELY(x) __builtin_expect(!!(x), 0)
+#else
+#define TZ_LIKELY(x) (x)
+#define TZ_UNLIKELY(x) (x)
+#endif
+
 namespace tz {
 
 // Run-time sized tables of a program, one device blob staged into shared memory by every CTA:
@@ -288,7 +296,7 @@ __device__ __forceinline__ void output_phase(WarpBuf<BK>& wb, const double (*pre
 #pragma unroll
         for (int j = 0; j < NW; ++j) xb1 = vfma(row[j], om(j), xb1);
         V en = vsub(acc, xb1);                                                 // e+ = x+ - xbar+
-        if (!all_good) {
+        if (TZ_UNLIKELY(!all_good)) {
           // a scenario whose step failed keeps its state, or -- the reference raises and the run ends
           // (tzddpc/tzddpc.py:374-375) -- starts a new run from x_restart: x = xbar = x_restart, e = 0
           const V xo = vld(&pre[2 * n + i][sc0], vt);
@@ -545,7 +553,7 @@ __device__ __forceinline__ void run_program(unsigned char* smem_raw, const QpPro
     // ---- ADMM (+ certificate / polish)
     LaneState<BK> st;
     bool warm = false;
-    if (sp.warm == 1 && a.warm != nullptr && live) {
+    if (TZ_UNLIKELY(sp.warm == 1 && a.warm != nullptr && live)) {
       // layout: [x (NZ) | y (NC, slot-indexed) | activity words (G) | valid flag] x LD
       warm = (a.warm[(int64_t)(NZ + BK::NC + G) * LD + s] == 1.0);
       if (warm) {
@@ -591,7 +599,7 @@ __device__ __forceinline__ void run_program(unsigned char* smem_raw, const QpPro
         }
       }
     }
-    if (!__all_sync(0xffffffffu, hint_ok || !solve_it)) {
+    if (TZ_UNLIKELY(!__all_sync(0xffffffffu, hint_ok || !solve_it))) {
       // no (valid) hint: is the program infeasible outright?  (singleton presolve, exact; saves the ADMM iterations and
       // the failed certificate an infeasible scenario would otherwise need before the same test inside admm_solve)
       const bool inf = singleton_infeasible<BK>(qp);
@@ -633,9 +641,9 @@ __device__ __forceinline__ void run_program(unsigned char* smem_raw, const QpPro
       a.warm[(int64_t)(NZ + BK::NC + g) * LD + s] = __longlong_as_double((long long)st.act);
     }
     // residual exits are polished; certified exits already are an exact KKT point
-    if (sp.polish && __any_sync(0xffffffffu, good && !certified)) (void)admm_polish<BK>(qp, inv_alpha, st, good && !certified, sp.polish);
+    if (TZ_UNLIKELY(sp.polish && __any_sync(0xffffffffu, good && !certified))) (void)admm_polish<BK>(qp, inv_alpha, st, good && !certified, sp.polish);
 
-    if (explicit_qp) {
+    if (TZ_UNLIKELY(explicit_qp)) {
       if (live) {
         if (g == 0) {
           a.status[s] = status;
@@ -702,7 +710,7 @@ __device__ __forceinline__ void run_program(unsigned char* smem_raw, const QpPro
    }     // solve tiles of this output tile
     if (explicit_qp) continue;
     __syncwarp();
-    if (a.vec2) output_phase<BK, 2>(wb, pre, ax, a, tabd, tabi, otile, lane, zslot < BK::TPO, sp.tube_packed != 0);
+    if (TZ_LIKELY(a.vec2)) output_phase<BK, 2>(wb, pre, ax, a, tabd, tabi, otile, lane, zslot < BK::TPO, sp.tube_packed != 0);
     else output_phase<BK, 1>(wb, pre, ax, a, tabd, tabi, otile, lane, zslot < BK::TPO, sp.tube_packed != 0);
     __syncwarp();     // wb is rewritten by the next tile
   }
@@ -756,15 +764,6 @@ __global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel_set(const SetEn
                                                                     const int64_t total_tiles, const Aux ax0,
                                                                     const SolverParams sp, const StepArgs a0) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  if (nprog == 1) {                                // one program: exactly step_kernel (tiles strided over the grid, prefetch across rounds)
-    const SetEntry en = entries[0];
-    Aux ax = ax0;
-    ax.tab = en.tab;
-    const StepArgs a = shift_args(a0, en.begin, en.end - en.begin);
-    run_program<BK>(smem_raw, reinterpret_cast<const QpProg<BK>*>(en.pg), ax, sp, a, (int64_t)blockIdx.x * BK::WPB,
-                    (int64_t)gridDim.x * BK::WPB, total_tiles, blockIdx.x * BK::WPB);
-    return;
-  }
   int staged = -1;                                 // program whose image is in shared memory
   int lo = 0;
   // round k: the CTA's WPB warps take the consecutive tiles [base, base + WPB) of the global numbering
