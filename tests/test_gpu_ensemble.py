@@ -235,3 +235,25 @@ def test_program_set_with_an_empty_data_set(cuda_lib):
         rd = c.simulate(cfg.A, cfg.B, x0[sl], noise=noise[:, sl], keep_tubes=True)
         for k in ("x", "u", "cost", "status", "tubes"):
             np.testing.assert_array_equal(r[k][:, sl], rd[k], err_msg=k)
+
+
+@pytest.mark.parametrize("per", [8192, 8208])       # 512 tiles per data set (rounds never straddle) / 513 (they do)
+def test_program_set_over_several_rounds(cuda_lib, per):
+    """More tiles than one wave of warps (1,776): every CTA works through several rounds, re-stages programs between them
+    and prefetches the next round's inputs -- still bit-equal to the per-data-set controllers, step after step."""
+    import tzddpc_b200 as tz
+    cfg = configs.CONFIGS["fivedim"]()
+    D, steps = 5, 4
+    ctls, _ = _controllers(cfg, D)
+    ens = tz.TZDDPCEnsemble(ctls, per)
+    S = D * per
+    x0 = np.tile(np.asarray(cfg.X0[0], dtype=np.float64), (S, 1))
+    x0 += 0.01 * np.random.default_rng(8).standard_normal(x0.shape)
+    opts = tz.SolverOptions(warm_start=2)
+    r = ens.simulate(cfg.A, cfg.B, x0, steps=steps, seed=11, options=opts, restart=True, keep_tubes=False)
+    for d, c in enumerate(ctls):
+        sl = slice(d * per, (d + 1) * per)
+        rd = c.simulate(cfg.A, cfg.B, x0[sl], steps=steps, seed=11, options=opts, restart=True, scenario_offset=d * per)
+        for k in ("x", "xbar", "e", "u", "v", "cost", "status"):
+            np.testing.assert_array_equal(r[k][:, sl], rd[k], err_msg=f"{k}, data set {d}")
+    assert (r["status"] == 0).mean() > 0.9
