@@ -14,8 +14,9 @@
  *     `_host`; the library allocates nothing on the device except inside
  *     tz_program_create (freed by tz_program_destroy);
  *   - all work is enqueued on `stream` (a cudaStream_t passed as void*), no implicit sync;
- *   - thread-safe: no mutable globals; per-scenario failures go to `status[S]`
- *     (TZ_STATUS_*), never to the return code;
+ *   - thread-safe: the only process-wide state is a cache of "dynamic shared-memory attribute already set for kernel k
+ *     on device d" bits (idempotent, atomic) and the per-thread stream pool of tz_closed_loop_step_host; per-scenario
+ *     failures go to `status[S]` (TZ_STATUS_*), never to the return code;
  *   - arithmetic is IEEE fp64 throughout.
  *
  * Layouts
@@ -96,6 +97,10 @@ int tz_program_bucket(const TzProgram* prog, char* buf, size_t cap);
 /* rows of the `warm` scratch array (rows x S doubles) that tz_solve / tz_closed_loop_step accept */
 int tz_program_warm_rows(const TzProgram* prog);
 
+/* Array sizes of a program, for bindings that validate caller buffers:
+ * out8 = [n, m, N*m, (N+1)*n, n*(1+g1), n_nz (packed tube rows), tz_program_warm_rows, CUDA device of the program]. */
+int tz_program_dims(const TzProgram* prog, int32_t* out8);
+
 /* Sparsity pattern of Ze[1].Z: returns n_nz, the number of entries that are not structurally zero, and (when
  * entries_host != NULL, cap >= n_nz) writes their row-major indices r*(1+g1)+j into entries_host.  Centre column included. */
 int tz_program_tube_pattern(const TzProgram* prog, int32_t* entries_host, int32_t cap);
@@ -120,6 +125,10 @@ typedef struct TzSolverOpts {
                         1: `ze1` is n_nz x S -- row i holds entry tz_program_tube_pattern()[i] of Ze[1].Z; the other
                         entries are zero for EVERY (xbar0, e0) (boxed M_K / M_Delta: 88 % of the 5-dim tube) and are
                         neither written to HBM nor copied to the host                  default 0 */
+  int32_t hot_path;  /* 1: with warm_start == 2, programs with two decision variables (horizon 2, one input: every shipped
+                        example) run fast_step_kernel -- one thread per scenario, closed-form KKT certificate of the hinted
+                        active set -- and only the 16-scenario tiles it cannot decide go through the ADMM kernel.
+                        0: the ADMM kernel for everything (same results bit for bit)      default 1 */
 } TzSolverOpts;
 
 void tz_solver_opts_default(TzSolverOpts* o);
@@ -175,6 +184,7 @@ typedef struct TzProgramSet TzProgramSet;   /* opaque */
 int tz_program_set_create(const TzProgram* const* progs, int32_t nprog, const int64_t* begin, TzProgramSet** out);
 void tz_program_set_destroy(TzProgramSet* set);
 int64_t tz_program_set_scenarios(const TzProgramSet* set);
+int tz_program_set_dims(const TzProgramSet* set, int32_t* out8);      /* as tz_program_dims (the programs share them) */
 int tz_solve_set(const TzProgramSet* set, const TzSolverOpts* opts, int64_t S,
                  const double* xbar0, const double* e0,
                  double* cost, double* v, double* xbar_traj, double* ze1,
@@ -198,6 +208,20 @@ int tz_closed_loop_step_host(const TzProgram* prog, const TzSolverOpts* opts, in
                              const double* A_true_host, const double* B_true_host,
                              double* cost_host, double* v_host, double* xbar_traj_host, double* ze1_host,
                              int32_t* status_host, void* dev_scratch, int32_t nchunks);
+
+/* The closed loop with the state RESIDENT on the device: (x, xbar, e), x_restart, the plant matrices and the active-set
+ * hints live in `dev_scratch` (same size query as above) from one call to the next, as the reference keeps them in its
+ * Python lists between calls of `solve` (examples/2.pulley_sim.py:81-96).
+ *   flags & 1   upload x, xbar, e (and x_restart when non-NULL: an infeasible scenario starts a new run from it), A_true,
+ *               B_true before the step -- the first call of a run (zero dev_scratch once before it);
+ *   flags & 2   download xbar and e after the step, too (x always comes down).
+ * Per call only the step's noise goes up and x+ and the non-NULL outputs (cost, v, xbar_traj, ze1, u = K e + v[0], status)
+ * come down.  x_restart_host is only read with flags & 1. */
+int tz_closed_loop_run_host(const TzProgram* prog, const TzSolverOpts* opts, int64_t S, int32_t flags,
+                            double* x_host, double* xbar_host, double* e_host, const double* x_restart_host,
+                            const double* noise_host, const double* A_true_host, const double* B_true_host,
+                            double* cost_host, double* v_host, double* xbar_traj_host, double* ze1_host, double* u_host,
+                            int32_t* status_host, void* dev_scratch, int32_t nchunks);
 
 /* ------------------------------------------------------------------------------------
  * Stand-alone zonotope ops (AoS batches).
@@ -272,6 +296,13 @@ int tz_gain_synthesis(int64_t D, int32_t T, int32_t n, int32_t m, int32_t gW, co
                       const double* WZ, double tol, int32_t max_iter, int32_t num_init, double accuracy, double confidence,
                       uint64_t seed, int64_t dataset_offset, double* K, double* dA, double* dB, double* rho,
                       int32_t* robust, int32_t* iters, int32_t* status, void* stream);
+/* compute_A_B and is_gain_robust (tzddpc/utils.py:13-41, 105-129) for a GIVEN gain K (D x m x n): the adversarial pair
+ * (A0 + dA, B0 + dB) of M_Sigma for that gain -- one pass of the convex-concave iteration above from the centre and
+ * num_init-1 Philox starts -- and the Monte-Carlo check.  rho: D x 3 as tz_gain_synthesis. */
+int tz_gain_adversary(int64_t D, int32_t T, int32_t n, int32_t m, int32_t gW, const double* AB, const double* Pinv,
+                      const double* WZ, const double* K, int32_t num_init, double accuracy, double confidence,
+                      uint64_t seed, int64_t dataset_offset, double* dA, double* dB, double* rho,
+                      int32_t* robust, int32_t* status, void* stream);
 /* N of the robustness check (utils.py:120), or -1 for arguments outside (0, 1) */
 int32_t tz_gain_robust_samples(double accuracy, double confidence);
 

@@ -54,7 +54,7 @@ def test_host_only_entry_points(cuda_lib):
 def test_struct_layouts_match_the_header(cuda_lib):
     """ctypes mirrors of TzProgramDesc / TzSolverOpts: field order and sizes as in include/tzddpc.h."""
     from tzddpc_b200 import _abi
-    assert C.sizeof(_abi.TzSolverOpts) == 80          # 7 doubles + 5 int32, padded to 8
+    assert C.sizeof(_abi.TzSolverOpts) == 88          # 7 doubles + 7 int32, padded to 8
     names = [f[0] for f in _abi.TzProgramDesc._fields_]
     src = open(HEADER).read()
     body = src[src.index("typedef struct TzProgramDesc {"):src.index("} TzProgramDesc;")]
@@ -98,3 +98,7 @@ def test_public_names_mirror_the_reference_package():
         assert hasattr(tz.TZDDPC, meth)
     assert tz.Data._fields == ("u", "x") and tz.SystemZonotopes._fields == ("X0", "U", "X", "W")
     assert tz.Theta._fields == ("K", "deltaA", "deltaB")
+    for name in ("compute_theta", "compute_A_B", "compute_control_gain", "spectral_radius"):      # tzddpc/__init__.py:2-7
+        assert callable(getattr(tz, name))
+    import numpy as np
+    assert tz.spectral_radius(np.array([[0.5, 1.0], [0.0, -0.8]])) == 0.8

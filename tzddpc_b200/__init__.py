@@ -11,6 +11,7 @@ from .program import BoxConstraint, StageCost  # noqa: F401
 from .tzddpc import TZDDPC, TubeHandle  # noqa: F401
 from .ensemble import TZDDPCEnsemble  # noqa: F401
 from .zonotope import Interval, MatrixZonotope, Zonotope, concatenate_zonotope  # noqa: F401
+from .utils import compute_theta, compute_A_B, compute_control_gain, is_gain_robust, spectral_radius  # noqa: F401
 
 __version__ = "0.1.0"
 __reference__ = "https://github.com/rssalessio/TZDDPC (0.0.3)"

@@ -28,7 +28,7 @@ class TzProgramDesc(C.Structure):
 
 class TzSolverOpts(C.Structure):
     _fields_ = [(k, C.c_double) for k in ("rho", "rho_active", "rho_inactive", "sigma", "alpha", "eps_abs", "eps_rel")] + \
-               [(k, C.c_int32) for k in ("max_iter", "check_every", "polish", "warm_start", "cert_first", "tube_packed")]
+               [(k, C.c_int32) for k in ("max_iter", "check_every", "polish", "warm_start", "cert_first", "tube_packed", "hot_path")]
 
 
 class TzddpcLibraryMissing(RuntimeError):
@@ -43,7 +43,8 @@ EXPORTS = ["tz_version", "tz_last_error", "tz_device_cc", "tz_program_create", "
            "tz_closed_loop_step_host", "tz_interval_hull", "tz_reach_step", "tz_girard_reduce", "tz_tube_rollout",
            "tz_identify", "tz_qp_solve", "tz_philox4x32_10_host", "tz_sample_noise", "tz_generate_trajectories",
            "tz_program_tube_pattern", "tz_program_set_create", "tz_program_set_destroy", "tz_program_set_scenarios",
-           "tz_solve_set", "tz_closed_loop_step_set", "tz_gain_synthesis", "tz_gain_robust_samples"]
+           "tz_solve_set", "tz_closed_loop_step_set", "tz_gain_synthesis", "tz_gain_robust_samples", "tz_gain_adversary", "tz_program_dims",
+           "tz_program_set_dims", "tz_closed_loop_run_host"]
 
 
 def lib() -> C.CDLL:
@@ -74,6 +75,10 @@ def lib() -> C.CDLL:
     L.tz_solve.argtypes = [vp, C.POINTER(TzSolverOpts), i64] + [vp] * 10
     L.tz_closed_loop_step.restype = C.c_int
     L.tz_closed_loop_step.argtypes = [vp, C.POINTER(TzSolverOpts), i64] + [vp] * 17
+    L.tz_program_dims.restype = C.c_int
+    L.tz_program_dims.argtypes = [vp, vp]
+    L.tz_program_set_dims.restype = C.c_int
+    L.tz_program_set_dims.argtypes = [vp, vp]
     L.tz_program_tube_pattern.restype = C.c_int
     L.tz_program_tube_pattern.argtypes = [vp, vp, i32]
     L.tz_program_set_create.restype = C.c_int
@@ -90,6 +95,8 @@ def lib() -> C.CDLL:
     L.tz_closed_loop_step_host_scratch_bytes.argtypes = [vp, i64]
     L.tz_closed_loop_step_host.restype = C.c_int
     L.tz_closed_loop_step_host.argtypes = [vp, C.POINTER(TzSolverOpts), i64] + [vp] * 12 + [i32]
+    L.tz_closed_loop_run_host.restype = C.c_int
+    L.tz_closed_loop_run_host.argtypes = [vp, C.POINTER(TzSolverOpts), i64, i32] + [vp] * 14 + [i32]
     L.tz_interval_hull.restype = C.c_int
     L.tz_interval_hull.argtypes = [i64, i32, i32, vp, vp, vp, vp]
     L.tz_reach_step.restype = C.c_int
@@ -109,12 +116,22 @@ def lib() -> C.CDLL:
     L.tz_identify.argtypes = [i64, i32, i32, i32, i32] + [vp] * 10
     L.tz_gain_synthesis.restype = C.c_int
     L.tz_gain_synthesis.argtypes = [i64, i32, i32, i32, i32, vp, vp, vp, dbl, i32, i32, dbl, dbl, u64, i64] + [vp] * 8
+    L.tz_gain_adversary.restype = C.c_int
+    L.tz_gain_adversary.argtypes = [i64, i32, i32, i32, i32, vp, vp, vp, vp, i32, dbl, dbl, u64, i64] + [vp] * 6
     L.tz_gain_robust_samples.restype = i32
     L.tz_gain_robust_samples.argtypes = [dbl, dbl]
     L.tz_qp_solve.restype = C.c_int
     L.tz_qp_solve.argtypes = [vp, C.POINTER(TzSolverOpts), i64] + [vp] * 8
     _lib = L
     return L
+
+
+def program_dims(handle: int, is_set: bool = False):
+    """(n, m, nv, (N+1)n, n(1+g1), n_nz, warm_rows) of a program / program set handle."""
+    out = (C.c_int32 * 8)()
+    L = lib()
+    check((L.tz_program_set_dims if is_set else L.tz_program_dims)(C.c_void_p(handle), out), "tz_program_dims")
+    return tuple(int(v) for v in out[:7])
 
 
 def last_error() -> str:

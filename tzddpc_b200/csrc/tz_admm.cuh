@@ -71,12 +71,14 @@ struct QpProg {
   double A[BK::NC][BK::NZ];            // E A D (NOT multiplied by alpha)
   double l0[BK::NC], u0[BK::NC];
   double kink0[BK::NK], wabs[BK::NK];
-  double R[BK::NC][BK::NCOLP];
+  double R[BK::NC][BK::NCOLP];         // UNSCALED shift rows (rows of one tube constraint share them up to a sign, see grp_*)
+  double Rs[BK::NC];                   // row scaling E_i:  r_i(p) = Rs_i * (R_i . w)
   double q0[BK::NZ];
   double Qp[BK::NZ][BK::NPAR];
   double Bt[BK::NAG][BK::NPAR];        // general atoms |Bt p + gam| (the unit atoms |p_c| are implicit)
   double gam[BK::NAG];
   double Rchk[BK::NCHK][BK::NCOLP];
+  double chk_tol[BK::NCHK];            // 1e-9 max(1, |Rchk[i][0]|)
   double cc[BK::NCOL];
   double CC2[BK::NPAR][BK::NPAR];
   double D[BK::NZ];
@@ -85,12 +87,18 @@ struct QpProg {
   double cinv;                          // 1 / cost scaling
   int sing_var[BK::NC];                 // ... and j, else -1 (singleton presolve: such rows are bounds on x_j)
   int row_of_slot[BK::NC];              // original row index of a slot, -1 for padding
+  // fast_step_kernel's order of the rows: rows that share their shift row R_i up to the sign of its constant / |.| part
+  // (the four rows a tube constraint expands into: upper / lower bound x the two signs of its |v| atom) are adjacent, the
+  // first of a group computes (L, A) = (linear part, constant + |.| part) of R_i . w and the others reuse it as L +- A
+  int grp_order[BK::NC];               // t -> row slot
+  int grp_new[BK::NC];                 // t -> 1: first row of a group
+  double grp_sgn[BK::NC];              // t -> sign of A relative to the group's first row
   int nz, nc, npar, nag, nchk, has_cc2, has_qp;
 };
 
 struct SolverParams {     // TzSolverOpts, device side
   double rho, rho_act, rho_inact, sigma, alpha, eps_abs, eps_rel;
-  int max_iter, check_every, polish, warm, cert_first, tube_packed;
+  int max_iter, check_every, polish, warm, cert_first, tube_packed, hot;
 };
 
 // compare-select min/max: 3 instructions instead of the ~8 of IEEE fmin/fmax (no NaN quieting needed:
@@ -307,6 +315,7 @@ __device__ __forceinline__ bool admm_certify(const LaneQp<BK>& qp, double inv_al
   constexpr int NZ = BK::NZ, NCL = BK::NCL, N2 = BK::N2, G = BK::G;
   const double delta = 1e-9, mu = 1e6, alpha = 1.0 / inv_alpha;
   double L[NZ][NZ], qt[NZ], tgt[NCL];
+  double sgs[N2], rlx[N2];               // |.| rows: subgradient of the assumed side; slack of the sign test when bound == kink
   uint32_t am = 0u;                      // active rows (on a bound / on the kink / equality)
   auto cof = [&](int k) { return (unsigned)(code >> (3 * k)) & 7u; };
 #pragma unroll
@@ -323,13 +332,24 @@ __device__ __forceinline__ bool admm_certify(const LaneQp<BK>& qp, double inv_al
     const bool ia = (c >= 1u && c <= 3u) || c == 6u;
     double b = (c == 2u) ? qp.upper(k) : qp.lower(k);
     if (k < N2) {
-      if (c == 3u) b = qp.kink[k < N2 ? k : 0];
-      if (c == 4u || c == 5u) {
-        const double wgt = qp.wk[(k < N2 ? k : 0) * G];
-        const double sg = (c == 4u ? wgt : -wgt) * inv_alpha;
-#pragma unroll
-        for (int a = 0; a < NZ; ++a) qt[a] = fma(sg, qp.Aa[k][a], qt[a]);
+      const double kk = qp.kink[k < N2 ? k : 0];
+      const double wgt = qp.wk[(k < N2 ? k : 0) * G];
+      if (c == 3u) b = kk;
+      // a |.| row off its kink -- free (codes 4 / 5) or resting on a finite bound away from the kink -- contributes the
+      // linear cost of its side; when the bound coincides with the kink the whole interval [-w, w] is available
+      double sg = 0.0, rl = 0.0;
+      if (c == 4u) sg = wgt;
+      else if (c == 5u) sg = -wgt;
+      else if (wgt > 0.0 && (c == 1u || c == 2u || c == 6u)) {
+        if (b > kk) sg = wgt;
+        else if (b < kk) sg = -wgt;
+        else rl = wgt;
       }
+      sgs[k < N2 ? k : 0] = sg;
+      rlx[k < N2 ? k : 0] = rl;
+      const double sga = sg * inv_alpha;
+#pragma unroll
+      for (int a = 0; a < NZ; ++a) qt[a] = fma(sga, qp.Aa[k][a], qt[a]);
     }
     tgt[k] = ia ? b * alpha : 0.0;
     am |= ia ? (1u << k) : 0u;
@@ -349,11 +369,14 @@ __device__ __forceinline__ bool admm_certify(const LaneQp<BK>& qp, double inv_al
     for (int b = 0; b <= a; ++b) L[a][b] = gsum<G>(L[a][b]) + qp.P[a][b] + (a == b ? delta : 0.0);
   }
   chol_factor<NZ>(L);
+  double xprev[NZ];
+#pragma unroll
+  for (int a = 0; a < NZ; ++a) xprev[a] = xk[a];
 #pragma unroll 1
   for (int it = 0; it < n_iter; ++it) {
     double rhs[NZ];
 #pragma unroll
-    for (int a = 0; a < NZ; ++a) rhs[a] = 0.0;
+    for (int a = 0; a < NZ; ++a) { rhs[a] = 0.0; xprev[a] = xk[a]; }
 #pragma unroll
     for (int k = 0; k < NCL; ++k) {
       const double t = ((am >> k) & 1u) ? fma(mu, tgt[k], -lam[k]) : 0.0;
@@ -395,11 +418,13 @@ __device__ __forceinline__ bool admm_certify(const LaneQp<BK>& qp, double inv_al
     const unsigned c = cof(k);
     bad |= (qp.lower(k) - ax > ptol) || (ax - qp.upper(k) > ptol);                 // primal feasibility
     if ((am >> k) & 1u) {
+      const double rl = k < N2 ? rlx[k < N2 ? k : 0] * inv_alpha : 0.0;
       bad |= fabs(ax - tgt[k] * inv_alpha) > etol;                                // active rows on their bound
-      bad |= (c == 2u) && (lam[k] < -ltol);                                       // multiplier signs
-      bad |= (c == 1u) && (lam[k] > ltol);
+      bad |= (c == 2u) && (lam[k] < -ltol - rl);                                  // multiplier signs
+      bad |= (c == 1u) && (lam[k] > ltol + rl);
       if (k < N2) bad |= (c == 3u) && (fabs(lam[k]) * alpha > qp.wk[(k < N2 ? k : 0) * G] * (1.0 + 1e-9));
       lam[k] *= alpha;                                                            // y
+      if (k < N2) lam[k] += sgs[k < N2 ? k : 0];                                  // ... of the row: bound multiplier + cost subgradient
     } else if (k < N2 && (c == 4u || c == 5u)) {
       const double kk = qp.kink[k < N2 ? k : 0];
       const double wgt = qp.wk[(k < N2 ? k : 0) * G];
@@ -407,6 +432,14 @@ __device__ __forceinline__ bool admm_certify(const LaneQp<BK>& qp, double inv_al
       lam[k] = (c == 4u) ? wgt : -wgt;
     }
   }
+  // stationarity: P x + qt + B'lam = delta (x_prev - x) by construction of the sweeps, so the residual is the last
+  // proximal step -- small at a KKT point, but NOT when the active set leaves a direction in which the cost is linear
+  // and non-zero (an LP with fewer active rows than variables): the iterate then runs away along it
+  double qs = lscale;
+#pragma unroll
+  for (int a = 0; a < NZ; ++a) qs = fmax(qs, fabs(qt[a]));
+#pragma unroll
+  for (int a = 0; a < NZ; ++a) bad |= !(delta * fabs(xprev[a] - xk[a]) <= 1e-9 * qs);
 #pragma unroll
   for (int a = 0; a < NZ; ++a) bad |= !(xk[a] == xk[a]);
   return gor<G>(bad) == 0;
@@ -669,6 +702,7 @@ __device__ bool admm_polish(const LaneQp<BK>& qp, double inv_alpha, LaneState<BK
   constexpr int NZ = BK::NZ, NCL = BK::NCL, N2 = BK::N2, G = BK::G;
   const double delta = 1e-9, mu = 1e6;
   double L[NZ][NZ], qt[NZ], xk[NZ], tgt[NCL];
+  double psg[N2];                  // cost subgradient of a |.| row that rests on a bound away from its kink
   uint32_t act = 0u;
 #pragma unroll
   for (int a = 0; a < NZ; ++a) {
@@ -681,13 +715,23 @@ __device__ bool admm_polish(const LaneQp<BK>& qp, double inv_alpha, LaneState<BK
   for (int k = 0; k < NCL; ++k) {
     bool ia = false;
     double b = 0.0;
-    if (st.z[k] <= qp.lower(k)) { b = qp.lower(k); ia = true; }
-    else if (st.z[k] >= qp.upper(k)) { b = qp.upper(k); ia = true; }
+    bool onb = false;
+    if (st.z[k] <= qp.lower(k)) { b = qp.lower(k); ia = true; onb = true; }
+    else if (st.z[k] >= qp.upper(k)) { b = qp.upper(k); ia = true; onb = true; }
     else if (k < N2) {
       const double kk = qp.kink[k < N2 ? k : 0];
       if (qp.wk[(k < N2 ? k : 0) * G] > 0.0 && st.z[k] == kk) { b = kk; ia = true; }
     }
     tgt[k] = b * (1.0 / inv_alpha);          // compare against Aa x = alpha (A x)
+    if (k < N2 && onb) {                     // a |.| row resting on a bound away from its kink: the linear cost of that side
+      const double wgt = qp.wk[(k < N2 ? k : 0) * G];
+      const double kk = qp.kink[k < N2 ? k : 0];
+      const double sg = (wgt > 0.0 && b != kk) ? (b > kk ? wgt : -wgt) : 0.0;
+      psg[k < N2 ? k : 0] = sg;
+      if (ia) st.w[k] -= sg;                 // the bound's own multiplier
+#pragma unroll
+      for (int a = 0; a < NZ; ++a) qt[a] = fma(sg * inv_alpha, qp.Aa[k][a], qt[a]);
+    } else if (k < N2) psg[k < N2 ? k : 0] = 0.0;
     if (ia) {
       act |= 1u << k;
 #pragma unroll
@@ -750,7 +794,7 @@ __device__ bool admm_polish(const LaneQp<BK>& qp, double inv_alpha, LaneState<BK
   }
 #pragma unroll
   for (int k = 0; k < NCL; ++k)
-    if ((act >> k) & 1u) st.w[k] *= (1.0 / inv_alpha);      // back to y
+    if ((act >> k) & 1u) st.w[k] = fma(st.w[k], 1.0 / inv_alpha, k < N2 ? psg[k < N2 ? k : 0] : 0.0);      // back to y (+ the cost subgradient)
   // accept only a feasible polished point
   double viol = 0.0, scale = 1.0;
 #pragma unroll

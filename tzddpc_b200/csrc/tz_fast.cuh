@@ -1,0 +1,357 @@
+// fast_step_kernel: the closed-loop step of the two-variable programs (bucket B0) with ONE THREAD PER SCENARIO.
+//
+// Replaces, per closed-loop step, tzddpc/tzddpc.py:357-377 (solve) and examples/2.pulley_sim.py:90-96 (update), as
+// step_kernel does -- for the scenarios whose active-set hint (the optimal active set of their previous step) still
+// certifies.  In a running closed loop that is all but a fraction of a percent of the scenario-steps, and for them
+// the solve is the closed-form KKT test of tz_cert2.cuh: no ADMM iteration, no lane group, no shuffle.
+//
+// Why a second kernel (profiles/r1_v12_*): step_kernel needs 168 registers (3 CTAs = 12 warps per SM) because it
+// carries the whole ADMM machinery, issues 29.5 M warp instructions per 65,536 scenarios (replicated x / factor /
+// certificate in the 4 lanes of a group, 12 % of them shuffles) and sits on dependent-issue latency at IPC 1.
+// Here a warp owns 32 consecutive scenarios, lane = scenario:
+//   * every load / store of the scenario-fastest arrays is one fully coalesced 256-byte access per row, straight from /
+//     to registers (no exchange buffer, no re-mapping between solve and output phase);
+//   * program coefficients (R, A, XB, ...) are read from shared memory at warp-uniform addresses: one broadcast load
+//     serves 32 scenarios;
+//   * the code is kept COMPACT (row loops are real loops): a warp runs through the kernel once, so straight-line code is
+//     fetched from L2 by every warp -- the first, fully unrolled version spent 3-4 stall cycles per issued instruction
+//     waiting for instructions (profiles/r2_fast_v0_*: no_instruction);
+//   * the dense Ze[1].Z (88 % structural zeros, but dense by the reference's contract) is written once: the zero runs
+//     between the term table's entries as plain streaming stores -- odd warps before they solve, even warps behind, so
+//     that the stores of one half drain while the other half computes -- and the other entries from the table.
+//     (Measured and dropped: zero-filling the CTA's [entries x scenarios] block with cp.async.bulk.tensor stores of a
+//     shared-memory tile of zeros, UTMASTG.2D through a tensor map over the caller's array.  The entries that are not
+//     structurally zero can only be stored once the bulk group has completed, and with one tile per CTA nothing is left
+//     to overlap that wait with: 8 barrier-stall cycles per issued instruction, 0.0784 ms per step against 0.0705 with
+//     plain stores -- profiles/r2_fast_v1_tma_*.)
+// Scenarios the hint cannot decide (no hint yet, active set changed) are DEFERRED in units of 16-scenario output
+// tiles: the tile index goes to a list in the caller's warm-start scratch and step_kernel, launched right behind on
+// the same stream, solves exactly those tiles (ADMM + certificate).  Both kernels use the same closed-form function
+// for hint-certified scenarios, so a scenario's result does not depend on which kernel handled its tile.
+#pragma once
+#include <cstdlib>
+
+#include "tz_step.cuh"
+
+namespace tz {
+
+template <class BK, int TPB>
+struct alignas(16) FastSmem {
+  QpProg<BK> pg;
+  double om[BK::KOM][TPB];                 // per-scenario vector [1 | v | xbar0 | e0 | centre of Ze[1]] for the term table's dynamic index
+};
+
+constexpr int kDeferTile = TZ_SPO_MIN;     // scenarios per deferred tile = output tile of step_kernel
+
+template <class BK, int TPB>
+__global__ void __launch_bounds__(TPB, 512 / TPB) fast_step_kernel(const QpProg<BK>* __restrict__ gpg, const Aux ax,
+                                                                  const SolverParams sp, const StepArgs a) {
+  constexpr int NZ = BK::NZ, NPAR = BK::NPAR, HP = BK::NPAR / 2, NCOL = BK::NCOL, NW = BK::NW, G = BK::G;
+  static_assert(kDeferTile == 16 && BK::SPO == 16, "deferred tiles are the 16-scenario output tiles of step_kernel");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FastSmem<BK, TPB>& sm = *reinterpret_cast<FastSmem<BK, TPB>*>(smem_raw);
+  double* tabd = reinterpret_cast<double*>(smem_raw + sizeof(FastSmem<BK, TPB>));
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int n = ax.n, m = ax.m, nv = ax.nv;
+  const bool closed = a.x != nullptr;
+  const int64_t LD = a.ld;
+  const bool dense = a.ze1 != nullptr && !sp.tube_packed;
+  // ---- stage the program and its tables (cp.async, all in flight at once)
+  {
+    const char* src = reinterpret_cast<const char*>(gpg);
+    char* dst = reinterpret_cast<char*>(&sm.pg);
+    constexpr int NCH = (int)(sizeof(QpProg<BK>) / 16);
+    for (int i = tid; i < NCH; i += TPB) cp_async16(dst + 16 * i, src + 16 * i);
+    if (tid == 0 && (sizeof(QpProg<BK>) % 16) != 0) cp_async8(dst + 16 * NCH, src + 16 * NCH);
+    for (int i = tid; i < ax.n_dbl; i += TPB) cp_async8(tabd + i, ax.tab + i);
+    if (closed) {
+      for (int i = tid; i < n * n; i += TPB) cp_async8(tabd + ax.n_dbl + i, a.A_true + i);
+      for (int i = tid; i < n * m; i += TPB) cp_async8(tabd + ax.n_dbl + n * n + i, a.B_true + i);
+    }
+    cp_async_commit();
+  }
+  bool staged = false;
+  const QpProg<BK>& pg = sm.pg;
+  const double* sXB = tabd + ax.o_XB;
+  const double* sCZ = tabd + ax.o_CZ;
+  const double* sK = tabd + ax.o_K;
+  const double* sA = tabd + ax.n_dbl;
+  const double* sB = sA + n * n;
+  const double2* tt = reinterpret_cast<const double2*>(tabd + ax.o_tt);      // term table: (coef, idx | ent << 32)
+  const int* zs = reinterpret_cast<const int*>(tabd + ax.o_zrun);           // zero runs: (first row, length) pairs
+  const unsigned long long* hint = reinterpret_cast<const unsigned long long*>(a.warm);
+  unsigned long long* hint_w = reinterpret_cast<unsigned long long*>(a.warm);
+  const unsigned half_mask = lane < 16 ? 0x0000ffffu : 0xffff0000u;
+  const double* omc = &sm.om[0][tid];                                       // this thread's column of om
+
+  const int64_t nblk = (a.S + TPB - 1) / TPB;
+  for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    const int64_t s = blk * TPB + tid;
+    const bool live = s < a.S;
+    const int64_t sc = live ? s : a.S - 1;                 // dead lanes shadow the last scenario and write nothing
+    // ---- inputs: parameters p = [xbar0 | e0] and the hint words (coalesced: lane = scenario)
+    double w[2 * BK::NCOL2];                               // w = [1 | p | |p| | general atoms] (+ a zero pad)
+    w[0] = 1.0;
+    if constexpr (2 * BK::NCOL2 > NCOL) w[2 * BK::NCOL2 - 1] = 0.0;
+    unsigned long long hw[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) hw[g] = hint[(int64_t)g * LD + sc];
+    bool finite = true;
+#pragma unroll
+    for (int j = 0; j < HP; ++j) {
+      double xv = 0.0, ev = 0.0;
+      if (j < n) { xv = a.xbar0[(int64_t)j * LD + sc]; ev = a.e0[(int64_t)j * LD + sc]; }
+      w[1 + j] = xv;
+      w[1 + HP + j] = ev;
+      w[1 + NPAR + j] = fabs(xv);
+      w[1 + NPAR + HP + j] = fabs(ev);
+      finite = finite && (fabs(xv) < 1e300) && (fabs(ev) < 1e300);
+    }
+    if (!staged) {
+      cp_async_wait<0>();
+      __syncthreads();
+      staged = true;
+    }
+    // ---- zero runs of the dense tube: odd warps before the solve, even warps behind it
+    auto zero_runs = [&]() {
+      double* base = a.ze1 + s;
+#pragma unroll 1
+      for (int r = 0; r < ax.n_zrun; ++r) {
+        double* ptr = base + (int64_t)zs[2 * r] * LD;
+#pragma unroll 4
+        for (int c = zs[2 * r + 1]; c > 0; --c, ptr += LD) __stcs(ptr, 0.0);
+      }
+    };
+    const bool zero_first = dense && (((tid >> 5) + (int)blk) & 1);
+    if (zero_first && live) zero_runs();
+
+    eval_atoms<BK>(pg, w);
+    double q[NZ];
+    eval_q<BK>(pg, w, q);
+    bool param_ok = true;
+#pragma unroll 1
+    for (int i = 0; i < pg.nchk; ++i) param_ok = param_ok && !param_row_violated<BK>(pg, i, w);
+    const double c0 = cost_const<BK>(pg, w);
+
+    bool valid = true;
+#pragma unroll
+    for (int g = 0; g < G; ++g) valid = valid && (hw[g] & kCodeValid);
+    const bool fresh = !(hw[0] & kCodeValid) || (hw[0] & kCodeFresh);
+    unsigned long long code[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) code[g] = hw[g] & ~(kCodeValid | kCodeFresh);
+    enum { kDefer = -2 };
+    int status = kDefer;
+    if (!finite) status = TZ_STATUS_NONFINITE;
+    else if (!param_ok) status = TZ_STATUS_INFEASIBLE;
+    Cert2Result res;
+    res.x[0] = res.x[1] = 0.0;
+    res.obj = 0.0;
+    res.verdict = kCertUndecided;
+    if (__any_sync(0xffffffffu, status == kDefer && valid)) {
+      res = certify2<BK>(pg, w, q, code);
+      if (status == kDefer && valid && res.verdict == kCertOk) status = TZ_STATUS_OK;
+    }
+    // a hint that does not certify: is the program infeasible outright (singleton presolve, exact)?  Otherwise defer.
+    if (__any_sync(0xffffffffu, status == kDefer && valid)) {
+      const bool inf = singleton_infeasible2<BK>(pg, w);
+      if (status == kDefer && valid && inf) status = TZ_STATUS_INFEASIBLE;
+    }
+    // ---- deferral, per 16-scenario tile
+    const unsigned dmask = __ballot_sync(0xffffffffu, live && status == kDefer);
+    const bool deferred = (dmask & half_mask) != 0u;
+    if (deferred && (lane & 15) == 0 && live) {
+      const int slot = atomicAdd(a.defer, 1);
+      if (slot >= 0 && slot < (a.S + kDeferTile - 1) / kDeferTile) a.defer_list[slot] = (int32_t)(s / kDeferTile);
+    }
+    const bool emit = live && !deferred;
+    const bool good = status == TZ_STATUS_OK;
+    double nrm2 = 0.0, cost = NAN;
+    if (emit) {
+      // ---- hints: rows [0, G) the active set for the next step, rows [G, 2G) the active set of the run's first step
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        unsigned long long wnext = 0ull;
+        if (good) {
+          wnext = code[g] | kCodeValid;
+          if (fresh) hint_w[(int64_t)(G + g) * LD + s] = wnext;
+        } else if (a.x_restart != nullptr) {
+          const unsigned long long h0 = hint[(int64_t)(G + g) * LD + s];
+          wnext = (h0 & kCodeValid) ? (h0 | kCodeFresh) : 0ull;
+        }
+        hint_w[(int64_t)g * LD + s] = wnext;
+      }
+      // ---- om = [1 | v | p | centre of Ze[1]]
+      double omr[NW];
+      omr[0] = 1.0;
+#pragma unroll
+      for (int j = 0; j < NZ; ++j) omr[BK::OM_V + j] = (j < nv) ? (good ? pg.D[j] * res.x[j] : NAN) : 0.0;
+#pragma unroll
+      for (int j = 0; j < NPAR; ++j) omr[BK::OM_P + j] = w[1 + j];
+      if (good) cost = fma(res.obj, pg.cinv, c0);
+      else if (status == TZ_STATUS_INFEASIBLE) cost = INFINITY;      // cvxpy returns +inf for an infeasible Minimize (:374)
+#pragma unroll
+      for (int j = 0; j < NW; ++j) sm.om[j][tid] = omr[j];
+#pragma unroll 1
+      for (int r = 0; r < n; ++r) {
+        const double* row = sCZ + r * NW;
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < NW; ++j) acc = fma(row[j], omr[j], acc);
+        sm.om[BK::OM_C + r][tid] = acc;
+      }
+      // (sm.om columns are thread-private: no barrier)
+      // ---- Ze[1].Z at the optimum (examples/2.pulley_sim.py:96): the entries of the term table
+      if (a.ze1 != nullptr) {
+        double* base = a.ze1 + s;
+        if (sp.tube_packed) {
+          double* ptr = base;
+#pragma unroll 4
+          for (int i = 0; i < ax.n_nz; ++i, ptr += LD) {
+            const double2 e = tt[i];
+            __stcs(ptr, e.x * omc[(int)(__double_as_longlong(e.y) & 0xffffffffll) * TPB]);
+          }
+        } else {
+          if (!zero_first) zero_runs();
+#pragma unroll 4
+          for (int i = 0; i < ax.n_nz; ++i) {
+            const double2 e = tt[i];
+            const long long ie = __double_as_longlong(e.y);
+            __stcs(base + (ie >> 32) * LD, e.x * omc[(int)(ie & 0xffffffffll) * TPB]);
+          }
+        }
+      }
+      // ---- nominal trajectory xbar_0..xbar_N = XB om  (tzddpc/tzddpc.py:166-170); xbar_1 is kept for the update
+      double xb1[HP];
+#pragma unroll
+      for (int i = 0; i < HP; ++i) xb1[i] = 0.0;
+      auto xb_row = [&](int i) {
+        const double* row = sXB + i * NW;
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < NW; ++j) acc = fma(row[j], omr[j], acc);
+        if (a.xbar_traj != nullptr) a.xbar_traj[(int64_t)i * LD + s] = acc;
+        return acc;
+      };
+      if (a.xbar_traj != nullptr) {
+#pragma unroll 1
+        for (int i = 0; i < n; ++i) (void)xb_row(i);
+      }
+      if (a.xbar_traj != nullptr || closed) {
+#pragma unroll
+        for (int k = 0; k < HP; ++k)
+          if (k < n) xb1[k] = xb_row(n + k);
+      }
+      if (a.xbar_traj != nullptr) {
+#pragma unroll 1
+        for (int i = 2 * n; i < (ax.N + 1) * n; ++i) (void)xb_row(i);
+      }
+      if (a.v != nullptr)
+        for (int j = 0; j < nv; ++j) a.v[(int64_t)j * LD + s] = omc[(BK::OM_V + j) * TPB];
+      if (a.status) a.status[s] = status;
+      if (a.iters) a.iters[s] = 0;
+      if (a.cost) a.cost[s] = cost;
+      // ---- closed-loop update (examples/2.pulley_sim.py:90-94)
+      if (closed) {
+        double us[kMaxM];
+#pragma unroll
+        for (int j = 0; j < kMaxM; ++j) {
+          double acc = 0.0;
+          if (j < m) {
+            acc = omr[BK::OM_V + (j < NZ ? j : 0)];                                  // v[0]
+#pragma unroll
+            for (int i = 0; i < HP; ++i)
+              if (i < n) acc = fma(sK[j * n + i], omr[BK::OM_P + HP + i], acc);
+            if (a.u_out) a.u_out[(int64_t)j * LD + s] = good ? acc : NAN;
+          }
+          us[j] = acc;                                                              // u = K e + v[0]
+        }
+        double xo[HP];
+#pragma unroll
+        for (int i = 0; i < HP; ++i) xo[i] = (i < n) ? a.x[(int64_t)i * LD + s] : 0.0;
+#pragma unroll
+        for (int i = 0; i < HP; ++i) {
+          if (i < n) {
+            double acc = a.noise ? a.noise[(int64_t)i * LD + s] : 0.0;
+#pragma unroll
+            for (int k = 0; k < HP; ++k)
+              if (k < n) acc = fma(sA[i * n + k], xo[k], acc);
+#pragma unroll
+            for (int k = 0; k < kMaxM; ++k)
+              if (k < m) acc = fma(sB[i * m + k], us[k], acc);
+            double xb = xb1[i];                                                      // xbar+ = xbar_traj[1]
+            double en = acc - xb;                                                    // e+ = x+ - xbar+
+            if (!good) {
+              // a scenario whose step failed keeps its state, or -- the reference raises and the run ends
+              // (tzddpc/tzddpc.py:374-375) -- starts a new run from x_restart: x = xbar = x_restart, e = 0
+              const double xr = a.x_restart ? a.x_restart[(int64_t)i * LD + s] : xo[i];
+              acc = xr;
+              xb = a.x_restart ? xr : omr[BK::OM_P + i];
+              en = a.x_restart ? 0.0 : omr[BK::OM_P + HP + i];
+            }
+            nrm2 = fma(acc, acc, nrm2);
+            a.x[(int64_t)i * LD + s] = acc;                                          // x+ = A x + B u + w
+            a.xbar[(int64_t)i * LD + s] = xb;
+            a.e[(int64_t)i * LD + s] = en;
+          }
+        }
+      }
+    }
+    // ---- closed-loop statistics: warp reduction, one atomic per statistic and warp
+    if (a.stats != nullptr && closed) {
+      const bool eg = emit && good;
+      double s0 = eg ? sqrt(nrm2) : 0.0, s1 = eg ? nrm2 : 0.0, s2 = eg ? cost : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      const unsigned binf = __ballot_sync(0xffffffffu, emit && status == TZ_STATUS_INFEASIBLE);
+      const unsigned bnf = __ballot_sync(0xffffffffu, emit && status == TZ_STATUS_NONFINITE);
+      const unsigned bem = __ballot_sync(0xffffffffu, emit);
+      if (lane == 0 && bem) {
+        if (s0 != 0.0) atomicAdd(a.stats + 0, s0);
+        if (s1 != 0.0) atomicAdd(a.stats + 1, s1);
+        if (s2 != 0.0) atomicAdd(a.stats + 2, s2);
+        if (binf) atomicAdd(a.stats + 3, (double)__popc(binf));
+        if (bnf) atomicAdd(a.stats + 6, (double)__popc(bnf));
+        atomicAdd(a.stats + 7, (double)__popc(bem));
+      }
+    }
+  }
+  if (!staged) cp_async_wait<0>();
+}
+
+template <class BK, int TPB>
+int launch_fast_tpb(const TzProgram* p, const SolverParams& sp, const StepArgs& a, cudaStream_t st) {
+  const size_t smem = sizeof(FastSmem<BK, TPB>) + p->smem_tab;
+  static std::atomic<unsigned long long> configured{0ull};
+  if (const int rc = ensure_dynamic_smem(fast_step_kernel<BK, TPB>, (int)(sizeof(FastSmem<BK, TPB>) + kMaxTabBytes), p->device,
+                                         configured))
+    return rc;
+  const int64_t nblk = (a.S + TPB - 1) / TPB;
+  const int64_t wave = (int64_t)p->num_sms * (512 / TPB);
+  const unsigned grid = (unsigned)(nblk < wave ? nblk : wave);
+  fast_step_kernel<BK, TPB><<<grid, TPB, smem, st>>>(reinterpret_cast<const QpProg<BK>*>(p->packed_dev), p->aux, sp, a);
+  TZ_CUDA(cudaGetLastError());
+  return TZ_OK;
+}
+
+// CTA size by batch size: big CTAs amortise the program staging (128 threads: 0.072 ms per 65,536-scenario step against
+// 0.079 / 0.097 with 64 / 32), small ones keep every SM busy when the batch is a fraction of a wave (strong scaling:
+// 8,192 scenarios per GPU are 256 warps on 148 SMs)
+template <class BK>
+int launch_fast(const TzProgram* p, const SolverParams& sp, const StepArgs& a, cudaStream_t st) {
+  if (const char* e = getenv("TZDDPC_FAST_TPB")) {      // tuning knob (read per launch, no state): force the CTA size
+    const int t = atoi(e);
+    if (t == 128) return launch_fast_tpb<BK, 128>(p, sp, a, st);
+    if (t == 64) return launch_fast_tpb<BK, 64>(p, sp, a, st);
+    if (t == 32) return launch_fast_tpb<BK, 32>(p, sp, a, st);
+  }
+  if (a.S >= (int64_t)p->num_sms * 128 * 2) return launch_fast_tpb<BK, 128>(p, sp, a, st);
+  if (a.S >= (int64_t)p->num_sms * 64 * 2) return launch_fast_tpb<BK, 64>(p, sp, a, st);
+  return launch_fast_tpb<BK, 32>(p, sp, a, st);
+}
+
+}  // namespace tz

@@ -18,6 +18,10 @@
 namespace tz {
 
 // the larger buckets are compiled in tz_bucket1.cu / tz_bucket2.cu / tz_bucket3.cu
+// fast_step_kernel (tz_fast.cuh) is compiled in tz_fast.cu
+template <class BK>
+int launch_fast(const TzProgram* p, const SolverParams& sp, const StepArgs& a, cudaStream_t st);
+extern template int launch_fast<B0>(const TzProgram*, const SolverParams&, const StepArgs&, cudaStream_t);
 extern template int launch_bucket<B1>(const TzProgram*, const SolverParams&, const StepArgs&, cudaStream_t);
 extern template int launch_bucket<B2>(const TzProgram*, const SolverParams&, const StepArgs&, cudaStream_t);
 extern template int launch_bucket<B3>(const TzProgram*, const SolverParams&, const StepArgs&, cudaStream_t);
@@ -107,7 +111,8 @@ void pack(const TzProgramDesc& d, QpProg<BK>& g) {
     if (nnz == 1) { g.sing_var[s] = where; g.sing_inv[s] = 1.0 / g.A[s][where]; }     // a bound on one variable
     g.l0[s] = E * d.l0[i];
     g.u0[s] = E * d.u0[i];
-    for (int j = 0; j < ncol; ++j) g.R[s][colmap(j)] += E * d.R[i * ncol + j];
+    g.Rs[s] = E;
+    for (int j = 0; j < ncol; ++j) g.R[s][colmap(j)] += d.R[i * ncol + j];
     if (cls[i] == 0) {
       g.kink0[s] = E * d.kink0[i];
       g.wabs[s] = d.wabs[i] > 0.0 ? d.c * d.wabs[i] / E : 0.0;
@@ -118,11 +123,44 @@ void pack(const TzProgramDesc& d, QpProg<BK>& g) {
     g.gam[amap[i]] = d.gam[i];
     for (int k = 0; k < npar; ++k) g.Bt[amap[i]][pk(k)] = d.Bt[i * npar + k];
   }
-  for (int i = 0; i < d.nchk; ++i)
+  for (int i = 0; i < d.nchk; ++i) {
     for (int j = 0; j < ncol; ++j) g.Rchk[i][colmap(j)] += d.Rchk[i * ncol + j];
+    g.chk_tol[i] = 1e-9 * std::fmax(1.0, std::fabs(d.Rchk[i * ncol]));
+  }
   for (int j = 0; j < ncol; ++j) g.cc[colmap(j)] += d.cc[j];
   for (int a = 0; a < npar; ++a)
     for (int b = 0; b < npar; ++b) g.CC2[pk(a)][pk(b)] = d.CC2[a * npar + b];
+  // ---- groups of rows that share their shift row up to the sign of its constant / |.| part (see QpProg::grp_*)
+  {
+    auto in_L = [&](int c) { return c >= 1 && c <= BK::NPAR; };
+    std::vector<int> rep_of;                         // group -> slot of its first row
+    std::vector<std::vector<std::pair<int, double>>> members;
+    for (int s = 0; s < BK::NC; ++s) {
+      if (g.row_of_slot[s] < 0) continue;            // padding
+      int found = -1;
+      double sgn = 1.0;
+      for (size_t q = 0; q < rep_of.size() && found < 0; ++q) {
+        const int r0 = rep_of[q];
+        bool same_L = true, same_A = true, neg_A = true;
+        for (int c = 0; c < BK::NCOLP; ++c) {
+          const double a = g.R[s][c], b = g.R[r0][c];
+          if (in_L(c)) same_L = same_L && (a == b);
+          else { same_A = same_A && (a == b); neg_A = neg_A && (a == -b); }
+        }
+        if (same_L && (same_A || neg_A)) { found = (int)q; sgn = same_A ? 1.0 : -1.0; }
+      }
+      if (found < 0) { rep_of.push_back(s); members.emplace_back(); found = (int)rep_of.size() - 1; }
+      members[found].push_back({s, sgn});
+    }
+    int t = 0;
+    for (auto& mem : members)
+      for (size_t k = 0; k < mem.size(); ++k, ++t) {
+        g.grp_order[t] = mem[k].first;
+        g.grp_new[t] = k == 0 ? 1 : 0;
+        g.grp_sgn[t] = mem[k].second;
+      }
+    for (; t < BK::NC; ++t) { g.grp_order[t] = 0; g.grp_new[t] = 0; g.grp_sgn[t] = 1.0; }
+  }
   g.cinv = 1.0 / d.c;
   g.nz = nz; g.nc = nc; g.npar = npar; g.nag = nag; g.nchk = d.nchk;
   g.has_cc2 = 0;
@@ -144,6 +182,7 @@ static int create_bucket(const TzProgramDesc& d, TzProgram* p, int id) {
   p->NW = BK::NW; p->OM_V = BK::OM_V; p->OM_P = BK::OM_P; p->OM_C = BK::OM_C; p->HP = BK::NPAR / 2;
   int dev = 0;
   TZ_CUDA(cudaGetDevice(&dev));
+  p->device = dev;
   TZ_CUDA(cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, dev));
   TZ_CUDA(cudaMalloc(&p->packed_dev, sizeof(QpProg<BK>)));
   TZ_CUDA(cudaMemcpy(p->packed_dev, packed.data(), sizeof(QpProg<BK>), cudaMemcpyHostToDevice));
@@ -155,6 +194,12 @@ extern "C" int tz_program_create(const TzProgramDesc* d, TzProgram** out) {
   TZ_REQUIRE(d->n >= 1 && d->n <= kMaxN && d->m >= 1 && d->m <= kMaxM, "dim_x must be 1..%d and dim_u 1..%d", kMaxN, kMaxM);
   TZ_REQUIRE(d->npar == 2 * d->n, "npar must be 2*dim_x");
   TZ_REQUIRE(d->nv == d->horizon * d->m && d->nv <= 16 && d->nz >= d->nv, "bad nv/nz");
+  TZ_REQUIRE(d->nc >= 0 && d->na >= 0 && d->nchk >= 0 && d->g1 >= 0 && d->nterms >= 0 && d->nkink >= 0 && d->nkink <= d->nc,
+             "negative size in the program descriptor");
+  TZ_REQUIRE(d->ze1_ptr && d->ze1_ptr[0] == 0, "ze1_ptr[0] must be 0");
+  for (int e = 0; e < d->n * (1 + d->g1); ++e)
+    TZ_REQUIRE(d->ze1_ptr[e + 1] >= d->ze1_ptr[e], "ze1_ptr must be non-decreasing (entry %d)", e);
+  TZ_REQUIRE(d->ze1_ptr[d->n * (1 + d->g1)] == d->nterms, "ze1_ptr[n(1+g1)] must equal nterms");
   TzProgram* p = new (std::nothrow) TzProgram();
   if (!p) return fail(TZ_ENOMEM, "out of host memory");
   int rc = TZ_ERANGE;
@@ -163,7 +208,7 @@ extern "C" int tz_program_create(const TzProgramDesc* d, TzProgram** out) {
   TZ_TRY(B0, 0) TZ_TRY(B1, 1) TZ_TRY(B2, 2) TZ_TRY(B3, 3)
 #undef TZ_TRY
   if (rc != TZ_OK) {
-    delete p;
+    tz_program_destroy(p);              // (frees the device image when the upload failed half-way)
     if (rc == TZ_ERANGE) {
       const RowClasses c = classify(*d, nullptr);
       return fail(TZ_ERANGE, "program (nz=%d rows: %d two-sided, %d upper, %d lower; npar=%d general atoms=%d nchk=%d) "
@@ -189,7 +234,7 @@ extern "C" int tz_program_create(const TzProgramDesc* d, TzProgram** out) {
   for (int e = 0; e < nent; ++e) {
     const int t0 = d->ze1_ptr[e], t1 = d->ze1_ptr[e + 1];
     for (int t = t0; t < t1; ++t)
-      if (d->ze1_idx[t] < 0 || d->ze1_idx[t] >= nwc) { delete p; return fail(TZ_EINVAL, "ze1_idx[%d] out of range", t); }
+      if (d->ze1_idx[t] < 0 || d->ze1_idx[t] >= nwc) { tz_program_destroy(p); return fail(TZ_EINVAL, "ze1_idx[%d] out of range", t); }
     const int r = e / ld1, j = e % ld1;
     if (j == 0) {                        // centre column: its (possibly many) terms become om[OM_C + r]
       for (int t = t0; t < t1; ++t) CZ[(size_t)r * NW + omidx(d->ze1_idx[t])] += d->ze1_val[t];
@@ -197,16 +242,30 @@ extern "C" int tz_program_create(const TzProgramDesc* d, TzProgram** out) {
     } else if (t1 - t0 == 1) {
       ent.push_back(e); idx.push_back(omidx(d->ze1_idx[t0])); coef.push_back(d->ze1_val[t0]);
     } else if (t1 - t0 > 1) {
-      delete p;
+      tz_program_destroy(p);
       return fail(TZ_EINVAL, "generator entry %d of Ze[1] has %d terms: only single-term generator entries are supported "
                   "(boxed M_K / M_Delta)", e, t1 - t0);
     }
   }
+  // zero runs of the dense Ze[1].Z: the rows between consecutive non-zero entries (fast_step_kernel writes each row once)
+  std::vector<int32_t> zstart, zlen;
+  {
+    int next = 0;
+    for (size_t i = 0; i <= ent.size(); ++i) {
+      const int stop = i < ent.size() ? ent[i] : nent;
+      if (stop > next) { zstart.push_back(next); zlen.push_back(stop - next); }
+      next = stop + 1;
+    }
+  }
   const size_t nXB = XB.size(), nCZ = CZ.size(), nK = (size_t)d->m * n, nco = coef.size();
-  const size_t ndbl = nXB + nCZ + nK + nco, nint = ent.size() + idx.size();
+  // fast_step_kernel's tables, in the double part: the term table as 16-byte pairs (coef, idx | ent << 32) on an even offset,
+  // then the zero runs as int32 pairs
+  const size_t o_tt = (nXB + nCZ + nK + nco + 1) & ~(size_t)1;
+  const size_t o_zrun = o_tt + 2 * nco;
+  const size_t ndbl = o_zrun + zstart.size(), nint = ent.size() + idx.size();
   const size_t smem_tab = (ndbl + (size_t)n * n + (size_t)n * d->m) * sizeof(double) + nint * sizeof(int32_t);
   if (smem_tab > kMaxTabBytes) {
-    delete p;
+    tz_program_destroy(p);
     return fail(TZ_ERANGE, "program tables need %zu bytes of shared memory (limit %d)", smem_tab, kMaxTabBytes);
   }
   std::vector<unsigned char> host(ndbl * sizeof(double) + nint * sizeof(int32_t) + 16);
@@ -218,6 +277,15 @@ extern "C" int tz_program_create(const TzProgramDesc* d, TzProgram** out) {
   int32_t* hi = reinterpret_cast<int32_t*>(hd + ndbl);
   if (!ent.empty()) std::memcpy(hi, ent.data(), ent.size() * sizeof(int32_t));
   if (!idx.empty()) std::memcpy(hi + ent.size(), idx.data(), idx.size() * sizeof(int32_t));
+  for (size_t i = 0; i < nco; ++i) {
+    hd[o_tt + 2 * i] = coef[i];
+    const long long bits = (long long)(uint32_t)idx[i] | ((long long)ent[i] << 32);
+    std::memcpy(&hd[o_tt + 2 * i + 1], &bits, sizeof(bits));
+  }
+  for (size_t i = 0; i < zstart.size(); ++i) {
+    const int32_t pr[2] = {zstart[i], zlen[i]};
+    std::memcpy(&hd[o_zrun + i], pr, sizeof(pr));
+  }
   cudaError_t err = cudaMalloc(&p->aux_dev, host.size());
   if (err == cudaSuccess) err = cudaMemcpy(p->aux_dev, host.data(), host.size(), cudaMemcpyHostToDevice);
   if (err != cudaSuccess) {
@@ -229,6 +297,7 @@ extern "C" int tz_program_create(const TzProgramDesc* d, TzProgram** out) {
   ax.n_dbl = (int)ndbl; ax.n_int = (int)nint;
   ax.o_XB = 0; ax.o_CZ = (int)nXB; ax.o_K = (int)(nXB + nCZ); ax.o_coef = (int)(nXB + nCZ + nK);
   ax.o_ent = 0; ax.o_idx = (int)ent.size();
+  ax.o_tt = (int)o_tt; ax.o_zrun = (int)o_zrun; ax.n_zrun = (int)zstart.size();
   ax.n_nz = (int)ent.size();
   p->tube_ent = ent;
   ax.n = n; ax.m = d->m; ax.N = d->horizon; ax.nv = d->nv; ax.g1 = d->g1;
@@ -255,12 +324,24 @@ extern "C" int tz_program_warm_rows(const TzProgram* p) {
   return p->NZ + p->NC + p->G + 1;        // x | y | activity words | valid flag
 }
 
+static void program_dims(const TzProgram* p, int32_t* out) {
+  out[0] = p->n; out[1] = p->m; out[2] = p->nv; out[3] = (p->N + 1) * p->n; out[4] = p->n * (1 + p->g1); out[5] = p->aux.n_nz;
+  out[6] = tz_program_warm_rows(p); out[7] = p->device;
+}
+
+extern "C" int tz_program_dims(const TzProgram* p, int32_t* out8) {
+  TZ_REQUIRE(p && out8, "null argument");
+  program_dims(p, out8);
+  return TZ_OK;
+}
+
 extern "C" void tz_solver_opts_default(TzSolverOpts* o) {
   if (!o) return;
   o->rho = 0.1; o->rho_active = 100.0; o->rho_inactive = 0.1; o->sigma = 1e-6; o->alpha = 1.6;
   o->eps_abs = 1e-6; o->eps_rel = 1e-6; o->max_iter = 4000; o->check_every = 8; o->polish = 3; o->warm_start = 0;
   o->cert_first = 3;
   o->tube_packed = 0;
+  o->hot_path = 1;
 }
 
 static SolverParams to_params(const TzSolverOpts* o) {
@@ -268,7 +349,8 @@ static SolverParams to_params(const TzSolverOpts* o) {
   tz_solver_opts_default(&d);
   if (o) d = *o;
   return SolverParams{d.rho, d.rho_active, d.rho_inactive, d.sigma, d.alpha, d.eps_abs, d.eps_rel,
-                      d.max_iter, d.check_every, d.polish, d.warm_start, d.cert_first, d.tube_packed != 0 ? 1 : 0};
+                      d.max_iter, d.check_every, d.polish, d.warm_start, d.cert_first, d.tube_packed != 0 ? 1 : 0,
+                      d.hot_path != 0 ? 1 : 0};
 }
 
 // two scenarios per lane in the output phase need 16-byte aligned rows: S, ld even and aligned base pointers
@@ -284,12 +366,29 @@ static int launch(const TzProgram* p, const TzSolverOpts* o, const StepArgs& a_i
   TZ_REQUIRE(p != nullptr, "null program");
   TZ_REQUIRE(a_in.S >= 0, "negative batch");
   if (a_in.S == 0) return TZ_OK;
+  {
+    int cur = -1;
+    TZ_CUDA(cudaGetDevice(&cur));
+    TZ_REQUIRE(cur == p->device, "the program was created on CUDA device %d, the current device is %d", p->device, cur);
+  }
   StepArgs a = a_in;
   a.vec2 = vec2_ok(a);
   const SolverParams sp = to_params(o);
   TZ_REQUIRE(sp.max_iter >= 1 && sp.rho > 0 && sp.rho_act > 0 && sp.rho_inact > 0 && sp.alpha > 0 && sp.alpha < 2,
              "bad solver options");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (p->bucket == 0 && sp.hot && sp.warm == 2 && a.warm != nullptr && a.q_in == nullptr) {
+    // hint mode of the two-variable programs: fast_step_kernel (one thread per scenario, closed-form certificate) decides
+    // every scenario whose hint still holds; the 16-scenario tiles it defers are listed in the warm-start scratch (rows
+    // 2G: counters, 2G + 1: list) and solved by step_kernel right behind it
+    a.defer = reinterpret_cast<int32_t*>(a.warm + (int64_t)(2 * B0::G) * a.ld);
+    a.defer_list = reinterpret_cast<int32_t*>(a.warm + (int64_t)(2 * B0::G + 1) * a.ld);
+    a.list_mode = 0;
+    const int rc = launch_fast<B0>(p, sp, a, st);
+    if (rc != TZ_OK) return rc;
+    a.list_mode = 1;
+    return launch_bucket<B0>(p, sp, a, st);
+  }
   switch (p->bucket) {
     case 0: return launch_bucket<B0>(p, sp, a, st);
     case 1: return launch_bucket<B1>(p, sp, a, st);
@@ -356,7 +455,7 @@ extern "C" int tz_program_set_create(const TzProgram* const* progs, int32_t npro
     // horizon, cost and constraint structure) built from different data
     TZ_REQUIRE(p->bucket == p0->bucket && p->smem_tab == p0->smem_tab && a.n_dbl == b.n_dbl && a.n_int == b.n_int &&
                a.o_XB == b.o_XB && a.o_CZ == b.o_CZ && a.o_K == b.o_K && a.o_coef == b.o_coef && a.o_ent == b.o_ent &&
-               a.o_idx == b.o_idx && a.n_nz == b.n_nz && a.n == b.n && a.m == b.m && a.N == b.N && a.nv == b.nv && a.g1 == b.g1,
+               a.o_idx == b.o_idx && a.o_tt == b.o_tt && a.o_zrun == b.o_zrun && a.n_zrun == b.n_zrun && a.n_nz == b.n_nz && a.n == b.n && a.m == b.m && a.N == b.N && a.nv == b.nv && a.g1 == b.g1,
                "program %d does not have the structure of program 0 (bucket / table sizes differ)", j);
     TZ_REQUIRE(p->tube_ent == p0->tube_ent, "program %d: Ze[1] has a different sparsity pattern than program 0", j);
     const int64_t cnt = begin[j + 1] - begin[j];
@@ -391,6 +490,12 @@ extern "C" void tz_program_set_destroy(TzProgramSet* s) {
 }
 
 extern "C" int64_t tz_program_set_scenarios(const TzProgramSet* s) { return s ? s->begin.back() : -1; }
+
+extern "C" int tz_program_set_dims(const TzProgramSet* s, int32_t* out8) {
+  TZ_REQUIRE(s && out8 && !s->progs.empty(), "null argument");
+  program_dims(s->progs[0], out8);
+  return TZ_OK;
+}
 
 static int launch_set(const TzProgramSet* s, const TzSolverOpts* o, const StepArgs& a_in, void* stream) {
   TZ_REQUIRE(s != nullptr, "null program set");
@@ -452,12 +557,12 @@ extern "C" int tz_qp_solve(const TzProgram* prog, const TzSolverOpts* opts, int6
   return launch(prog, &o, a, stream);
 }
 
-// ---- host-buffer variant: chunked H2D -> kernel -> D2H pipeline ---------------------------------
+// ---- host-buffer variants: chunked H2D -> kernels -> D2H pipeline ---------------------------------
 static size_t host_scratch_doubles(const TzProgram* p, int64_t S) {
   const size_t n = p->n, nent = (size_t)p->n * (1 + p->g1), nt = (size_t)(p->N + 1) * p->n;
-  // x, xbar, e, noise | cost | v | xbar_traj | ze1 | status (as int32, rounded up) | A, B
-  // ... | warm rows (active-set hints / ADMM iterate carried between calls when opts->warm_start != 0)
-  return (size_t)S * (4 * n + 1 + p->nv + nt + nent + 1 + (size_t)tz_program_warm_rows(p)) + (size_t)(n * n + n * p->m) + 16;
+  // A, B | x, xbar, e, noise | cost | v | xbar_traj | ze1 | status (as int32, rounded up) | warm rows (active-set hints /
+  // ADMM iterate carried between calls when opts->warm_start != 0) | x_restart | u   (the last two: tz_closed_loop_run_host)
+  return (size_t)S * (4 * n + 1 + p->nv + nt + nent + 1 + (size_t)tz_program_warm_rows(p) + n + p->m) + (size_t)(n * n + n * p->m) + 16;
 }
 
 extern "C" size_t tz_closed_loop_step_host_scratch_bytes(const TzProgram* prog, int64_t S) {
@@ -465,16 +570,39 @@ extern "C" size_t tz_closed_loop_step_host_scratch_bytes(const TzProgram* prog, 
   return host_scratch_doubles(prog, S) * sizeof(double);
 }
 
-extern "C" int tz_closed_loop_step_host(const TzProgram* prog, const TzSolverOpts* opts, int64_t S, double* x_host,
-                                        double* xbar_host, double* e_host, const double* noise_host,
-                                        const double* A_true_host, const double* B_true_host, double* cost_host,
-                                        double* v_host, double* xbar_traj_host, double* ze1_host, int32_t* status_host,
-                                        void* dev_scratch, int32_t nchunks) {
-  TZ_REQUIRE(prog && dev_scratch, "null argument");
-  TZ_REQUIRE(S == 0 || (x_host && xbar_host && e_host && noise_host && A_true_host && B_true_host && status_host),
-             "x, xbar, e, noise, A_true, B_true, status are required");
-  if (S == 0) return TZ_OK;
-  const TzProgram* p = prog;
+namespace {
+// the chunk streams are created once per host thread and device and reused by later calls (creating and destroying them
+// cost tens of microseconds of every call); a thread that moves to another device gets that device's own pool
+struct StreamPool {
+  cudaStream_t s[16];
+  cudaEvent_t ready = nullptr;      // plant matrices (and, resident mode, the state) uploaded on s[0]; the other chunk streams wait for it
+  int n = 0;
+};
+constexpr int kMaxPoolDevices = 64;
+
+StreamPool* stream_pool(int device, int nchunks) {
+  static thread_local StreamPool pools[kMaxPoolDevices];
+  if (device < 0 || device >= kMaxPoolDevices) return nullptr;
+  StreamPool& pool = pools[device];
+  if (!pool.ready && cudaEventCreateWithFlags(&pool.ready, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  while (pool.n < nchunks) {
+    if (cudaStreamCreateWithFlags(&pool.s[pool.n], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    ++pool.n;
+  }
+  return &pool;
+}
+
+struct HostStep {
+  int resident = 0;          // 1: tz_closed_loop_run_host (state stays on the device between calls)
+  int upload_state = 1;      // copy x, xbar, e (and x_restart) up before the step
+  int download_state = 1;    // copy xbar and e down after the step (x always comes down)
+  double *x, *xbar, *e;
+  const double *x_restart, *noise, *A_true, *B_true;
+  double *cost, *v, *traj, *ze1, *u;
+  int32_t* status;
+};
+
+int closed_loop_host(const TzProgram* p, const TzSolverOpts* opts, int64_t S, const HostStep& hs, void* dev_scratch, int32_t nchunks) {
   const int64_t n = p->n, m = p->m, nent = (int64_t)p->n * (1 + p->g1), nt = (int64_t)(p->N + 1) * p->n, nv = p->nv;
   // packed tube (opts->tube_packed): only the entries of Ze[1].Z that are not structurally zero cross the bus
   const int64_t tube_rows = (opts && opts->tube_packed) ? (int64_t)p->aux.n_nz : nent;
@@ -489,29 +617,22 @@ extern "C" int tz_closed_loop_step_host(const TzProgram* prog, const TzSolverOpt
          *dtraj = dv + nv * S, *dze = dtraj + nt * S;
   int32_t* dst = reinterpret_cast<int32_t*>(dze + nent * S);
   double* dwarm = dze + nent * S + S;      // behind the status words (S int32 <= S doubles)
+  double* dxr = dwarm + (int64_t)tz_program_warm_rows(p) * S;
+  double* du = dxr + n * S;
   const bool use_warm = opts && opts->warm_start != 0;
-  // the chunk streams are created once per host thread and device and reused by later calls (creating and destroying
-  // them cost tens of microseconds of every call)
-  struct StreamPool {
-    cudaStream_t s[16];
-    cudaEvent_t plant = nullptr;      // A_true / B_true uploaded (on s[0]); the other chunk streams wait for it
-    int n = 0, dev = -1;
-  };
-  static thread_local StreamPool pool;
   int cur_dev = 0;
   TZ_CUDA(cudaGetDevice(&cur_dev));
-  if (pool.dev != cur_dev) { pool.n = 0; pool.dev = cur_dev; pool.plant = nullptr; }      // (streams of another device stay alive, unused)
-  if (!pool.plant) TZ_CUDA(cudaEventCreateWithFlags(&pool.plant, cudaEventDisableTiming));
-  while (pool.n < nchunks) {
-    TZ_CUDA(cudaStreamCreateWithFlags(&pool.s[pool.n], cudaStreamNonBlocking));
-    ++pool.n;
-  }
-  cudaStream_t* streams = pool.s;
+  StreamPool* pool = stream_pool(cur_dev, nchunks);
+  if (!pool) return fail(TZ_ECUDA, "closed_loop_host: cannot create the chunk streams on device %d", cur_dev);
+  cudaStream_t* streams = pool->s;
   int rc = TZ_OK;
-  cudaError_t err = cudaMemcpyAsync(dA, A_true_host, n * n * sizeof(double), cudaMemcpyHostToDevice, streams[0]);
-  if (err == cudaSuccess) err = cudaMemcpyAsync(dB, B_true_host, n * m * sizeof(double), cudaMemcpyHostToDevice, streams[0]);
-  if (err == cudaSuccess) err = cudaEventRecord(pool.plant, streams[0]);
-  for (int c = 1; c < nchunks && err == cudaSuccess; ++c) err = cudaStreamWaitEvent(streams[c], pool.plant, 0);
+  cudaError_t err = cudaSuccess;
+  if (hs.upload_state) {
+    err = cudaMemcpyAsync(dA, hs.A_true, n * n * sizeof(double), cudaMemcpyHostToDevice, streams[0]);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(dB, hs.B_true, n * m * sizeof(double), cudaMemcpyHostToDevice, streams[0]);
+  }
+  if (err == cudaSuccess) err = cudaEventRecord(pool->ready, streams[0]);
+  for (int c = 1; c < nchunks && err == cudaSuccess; ++c) err = cudaStreamWaitEvent(streams[c], pool->ready, 0);
   int64_t per = (S + nchunks - 1) / nchunks;
   per = (per + 15) & ~(int64_t)15;          // whole tiles, 16-byte aligned chunk starts
   // The device arrays are SoA with leading dimension S; a chunk [s0, s1) of a d x S array is d strided
@@ -528,39 +649,82 @@ extern "C" int tz_closed_loop_step_host(const TzProgram* prog, const TzSolverOpt
     const int64_t s0 = (int64_t)c * per, cnt = (s0 + per <= S ? per : S - s0);
     if (cnt <= 0) break;
     cudaStream_t st = streams[c];
-    err = h2d(dx, x_host, n, s0, cnt, st);
-    if (err == cudaSuccess) err = h2d(dxb, xbar_host, n, s0, cnt, st);
-    if (err == cudaSuccess) err = h2d(de, e_host, n, s0, cnt, st);
-    if (err == cudaSuccess) err = h2d(dw, noise_host, n, s0, cnt, st);
+    if (hs.upload_state) {
+      err = h2d(dx, hs.x, n, s0, cnt, st);
+      if (err == cudaSuccess) err = h2d(dxb, hs.xbar, n, s0, cnt, st);
+      if (err == cudaSuccess) err = h2d(de, hs.e, n, s0, cnt, st);
+      if (err == cudaSuccess && hs.resident && hs.x_restart) err = h2d(dxr, hs.x_restart, n, s0, cnt, st);
+    }
+    if (err == cudaSuccess) err = h2d(dw, hs.noise, n, s0, cnt, st);
     if (err != cudaSuccess) break;
     // the chunk is its own batch of `cnt` scenarios inside arrays of leading dimension S
     StepArgs a{};
     a.S = cnt; a.ld = S;
     a.xbar0 = dxb + s0; a.e0 = de + s0; a.x = dx + s0; a.xbar = dxb + s0; a.e = de + s0; a.noise = dw + s0;
+    a.x_restart = (hs.resident && hs.x_restart) ? dxr + s0 : nullptr;
     a.A_true = dA; a.B_true = dB;
-    a.cost = cost_host ? dcost + s0 : nullptr;
-    a.v = v_host ? dv + s0 : nullptr;
-    a.xbar_traj = xbar_traj_host ? dtraj + s0 : nullptr;
-    a.ze1 = ze1_host ? dze + s0 : nullptr;
+    a.cost = hs.cost ? dcost + s0 : nullptr;
+    a.v = hs.v ? dv + s0 : nullptr;
+    a.xbar_traj = hs.traj ? dtraj + s0 : nullptr;
+    a.ze1 = hs.ze1 ? dze + s0 : nullptr;
+    a.u_out = hs.u ? du + s0 : nullptr;
     a.status = dst + s0;
     a.warm = use_warm ? dwarm + s0 : nullptr;
     rc = launch(p, opts, a, st);
     if (rc != TZ_OK) break;
-    err = d2h(x_host, dx, n, s0, cnt, st);
-    if (err == cudaSuccess) err = d2h(xbar_host, dxb, n, s0, cnt, st);
-    if (err == cudaSuccess) err = d2h(e_host, de, n, s0, cnt, st);
-    if (err == cudaSuccess && cost_host) err = d2h(cost_host, dcost, 1, s0, cnt, st);
-    if (err == cudaSuccess && v_host) err = d2h(v_host, dv, nv, s0, cnt, st);
-    if (err == cudaSuccess && xbar_traj_host) err = d2h(xbar_traj_host, dtraj, nt, s0, cnt, st);
-    if (err == cudaSuccess && ze1_host) err = d2h(ze1_host, dze, tube_rows, s0, cnt, st);
+    err = d2h(hs.x, dx, n, s0, cnt, st);
+    if (err == cudaSuccess && hs.download_state) err = d2h(hs.xbar, dxb, n, s0, cnt, st);
+    if (err == cudaSuccess && hs.download_state) err = d2h(hs.e, de, n, s0, cnt, st);
+    if (err == cudaSuccess && hs.cost) err = d2h(hs.cost, dcost, 1, s0, cnt, st);
+    if (err == cudaSuccess && hs.v) err = d2h(hs.v, dv, nv, s0, cnt, st);
+    if (err == cudaSuccess && hs.traj) err = d2h(hs.traj, dtraj, nt, s0, cnt, st);
+    if (err == cudaSuccess && hs.ze1) err = d2h(hs.ze1, dze, tube_rows, s0, cnt, st);
+    if (err == cudaSuccess && hs.u) err = d2h(hs.u, du, m, s0, cnt, st);
     if (err == cudaSuccess)
-      err = cudaMemcpyAsync(status_host + s0, dst + s0, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+      err = cudaMemcpyAsync(hs.status + s0, dst + s0, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
   }
   for (int c = 0; c < nchunks; ++c) {
     cudaError_t e2 = cudaStreamSynchronize(streams[c]);
     if (err == cudaSuccess) err = e2;
   }
   if (rc != TZ_OK) return rc;
-  if (err != cudaSuccess) return fail(TZ_ECUDA, "closed_loop_step_host: %s", cudaGetErrorString(err));
+  if (err != cudaSuccess) return fail(TZ_ECUDA, "closed_loop_host: %s", cudaGetErrorString(err));
   return TZ_OK;
+}
+}  // namespace
+
+extern "C" int tz_closed_loop_step_host(const TzProgram* prog, const TzSolverOpts* opts, int64_t S, double* x_host,
+                                        double* xbar_host, double* e_host, const double* noise_host,
+                                        const double* A_true_host, const double* B_true_host, double* cost_host,
+                                        double* v_host, double* xbar_traj_host, double* ze1_host, int32_t* status_host,
+                                        void* dev_scratch, int32_t nchunks) {
+  TZ_REQUIRE(prog && dev_scratch, "null argument");
+  TZ_REQUIRE(S == 0 || (x_host && xbar_host && e_host && noise_host && A_true_host && B_true_host && status_host),
+             "x, xbar, e, noise, A_true, B_true, status are required");
+  if (S == 0) return TZ_OK;
+  HostStep hs;
+  hs.x = x_host; hs.xbar = xbar_host; hs.e = e_host; hs.x_restart = nullptr; hs.noise = noise_host; hs.A_true = A_true_host;
+  hs.B_true = B_true_host; hs.cost = cost_host; hs.v = v_host; hs.traj = xbar_traj_host; hs.ze1 = ze1_host; hs.u = nullptr;
+  hs.status = status_host;
+  return closed_loop_host(prog, opts, S, hs, dev_scratch, nchunks);
+}
+
+extern "C" int tz_closed_loop_run_host(const TzProgram* prog, const TzSolverOpts* opts, int64_t S, int32_t flags, double* x_host,
+                                       double* xbar_host, double* e_host, const double* x_restart_host, const double* noise_host,
+                                       const double* A_true_host, const double* B_true_host, double* cost_host, double* v_host,
+                                       double* xbar_traj_host, double* ze1_host, double* u_host, int32_t* status_host,
+                                       void* dev_scratch, int32_t nchunks) {
+  TZ_REQUIRE(prog && dev_scratch, "null argument");
+  const bool up = (flags & 1) != 0, down = (flags & 2) != 0;
+  TZ_REQUIRE(S == 0 || (x_host && noise_host && status_host), "x, noise, status are required");
+  TZ_REQUIRE(S == 0 || !up || (xbar_host && e_host && A_true_host && B_true_host),
+             "flags & 1 (upload the state): xbar, e, A_true, B_true are required");
+  TZ_REQUIRE(S == 0 || !down || (xbar_host && e_host), "flags & 2 (download xbar and e): xbar, e are required");
+  if (S == 0) return TZ_OK;
+  HostStep hs;
+  hs.resident = 1; hs.upload_state = up ? 1 : 0; hs.download_state = down ? 1 : 0;
+  hs.x = x_host; hs.xbar = xbar_host; hs.e = e_host; hs.x_restart = x_restart_host; hs.noise = noise_host; hs.A_true = A_true_host;
+  hs.B_true = B_true_host; hs.cost = cost_host; hs.v = v_host; hs.traj = xbar_traj_host; hs.ze1 = ze1_host; hs.u = u_host;
+  hs.status = status_host;
+  return closed_loop_host(prog, opts, S, hs, dev_scratch, nchunks);
 }

@@ -181,6 +181,7 @@ __device__ bool lqr_gain_sda(const double* A, const double* B, int n, int m, dou
 struct GainArgs {
   int T, n, m, gW;
   const double *AB, *Pinv, *WZ;
+  const double* K_fixed;          // tz_gain_adversary: the caller's gain (D x m x n); no synthesis, one adversary pass
   double tol;
   int max_iter, num_init, nsamp;
   uint64_t seed;
@@ -235,7 +236,12 @@ __global__ void __launch_bounds__(kGThreads) gain_kernel(const GainArgs a) {
     // ---- K = LQR gain of (An, Bn)
     if (tid == 0) {
       double Kl[kMaxM * kMaxN];
-      const bool ok = lqr_gain_sda(An, Bn, n, m, Kl);
+      bool ok = true;
+      if (a.K_fixed != nullptr) {
+        for (int i = 0; i < m * n; ++i) Kl[i] = a.K_fixed[ds * m * n + i];
+      } else {
+        ok = lqr_gain_sda(An, Bn, n, m, Kl);
+      }
       for (int i = 0; i < m * n; ++i) K[i] = Kl[i];
       if (!ok) s_ok = 0;
       double f0[kNN];
@@ -351,7 +357,7 @@ __global__ void __launch_bounds__(kGThreads) gain_kernel(const GainArgs a) {
         rho_adv = spectral_radius_sq(Fa, n);
         rho0 = spectral_radius_sq(F0, n);
         const double lam = fmax(rho_adv, rho0);
-        int stop = (fabs(lam - prev) < a.tol || lam < 1.0) ? 1 : 0;
+        int stop = (fabs(lam - prev) < a.tol || lam < 1.0 || a.K_fixed != nullptr) ? 1 : 0;
         if (!stop) {
           ++iteration;
           prev = lam;
@@ -392,14 +398,15 @@ __global__ void __launch_bounds__(kGThreads) gain_kernel(const GainArgs a) {
   __syncthreads();
   if (tid == 0) {
     for (int w = 1; w < kGThreads / 32; ++w) worst = fmax(worst, part[w][0]);
-    for (int i = 0; i < m * n; ++i) a.K[ds * m * n + i] = K[i];
+    if (a.K != nullptr)
+      for (int i = 0; i < m * n; ++i) a.K[ds * m * n + i] = K[i];
     for (int i = 0; i < n * n; ++i) a.dA[ds * n * n + i] = An[i] - A0[i];
     for (int i = 0; i < n * m; ++i) a.dB[ds * n * m + i] = Bn[i] - B0[i];
     a.rho[ds * 3 + 0] = ok ? rho0 : NAN;
     a.rho[ds * 3 + 1] = ok ? rho_adv : NAN;
     a.rho[ds * 3 + 2] = ok ? worst : NAN;
     a.robust[ds] = (ok && worst < 1.0) ? 1 : 0;
-    a.iters[ds] = iteration;
+    if (a.iters != nullptr) a.iters[ds] = iteration;
     a.status[ds] = ok ? TZ_STATUS_OK : TZ_STATUS_NONFINITE;
   }
 }
@@ -419,10 +426,38 @@ extern "C" int tz_gain_synthesis(int64_t D, int32_t T, int32_t n, int32_t m, int
   if (D == 0) return TZ_OK;
   TZ_REQUIRE(AB && Pinv && WZ && K && dA && dB && rho && robust && iters && status, "null pointer");
   GainArgs a;
+  a.K_fixed = nullptr;
   a.T = T; a.n = n; a.m = m; a.gW = gW; a.AB = AB; a.Pinv = Pinv; a.WZ = WZ; a.tol = tol; a.max_iter = max_iter;
   a.num_init = num_init; a.seed = seed; a.dataset_offset = dataset_offset;
   a.nsamp = (int)ceil(log(1.0 / confidence) / log(1.0 / (1.0 - accuracy)));      // utils.py:120
   a.K = K; a.dA = dA; a.dB = dB; a.rho = rho; a.robust = robust; a.iters = iters; a.status = status;
+  const size_t Tm = (size_t)T - 1;
+  size_t smem = Tm * (size_t)(n + m + n) * sizeof(double) + 4 * (size_t)gW * Tm + 16;
+  TZ_REQUIRE(smem <= 200 * 1024, "data set too long for the shared-memory staging (%zu bytes)", smem);
+  if (smem > 40 * 1024) TZ_CUDA(cudaFuncSetAttribute(gain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gain_kernel<<<(unsigned)D, kGThreads, smem, (cudaStream_t)stream>>>(a);
+  TZ_CUDA(cudaGetLastError());
+  return TZ_OK;
+}
+
+// compute_A_B + is_gain_robust for a GIVEN gain (tzddpc/utils.py:13-41,105-129): the adversarial pair of M_Sigma for K and
+// the Monte-Carlo robustness check, without the synthesis loop.
+extern "C" int tz_gain_adversary(int64_t D, int32_t T, int32_t n, int32_t m, int32_t gW, const double* AB, const double* Pinv,
+                                 const double* WZ, const double* K, int32_t num_init, double accuracy, double confidence,
+                                 uint64_t seed, int64_t dataset_offset, double* dA, double* dB, double* rho, int32_t* robust,
+                                 int32_t* status, void* stream) {
+  TZ_REQUIRE(D >= 0 && T >= 2 && n >= 1 && n <= kMaxN && m >= 1 && m <= kMaxM && gW >= 1 && gW <= kMaxGW, "bad shape");
+  TZ_REQUIRE(accuracy > 0 && accuracy < 1 && confidence > 0 && confidence < 1, "accuracy and confidence must be in (0, 1)");
+  TZ_REQUIRE(num_init >= 1, "bad iteration options");
+  TZ_REQUIRE((int64_t)2 * gW * (T - 1) < 131072, "too many generators for the draw counter");
+  if (D == 0) return TZ_OK;
+  TZ_REQUIRE(AB && Pinv && WZ && K && dA && dB && rho && robust && status, "null pointer");
+  GainArgs a;
+  a.K_fixed = K;
+  a.T = T; a.n = n; a.m = m; a.gW = gW; a.AB = AB; a.Pinv = Pinv; a.WZ = WZ; a.tol = 0.0; a.max_iter = 1;
+  a.num_init = num_init; a.seed = seed; a.dataset_offset = dataset_offset;
+  a.nsamp = (int)ceil(log(1.0 / confidence) / log(1.0 / (1.0 - accuracy)));      // utils.py:120
+  a.K = nullptr; a.dA = dA; a.dB = dB; a.rho = rho; a.robust = robust; a.iters = nullptr; a.status = status;
   const size_t Tm = (size_t)T - 1;
   size_t smem = Tm * (size_t)(n + m + n) * sizeof(double) + 4 * (size_t)gW * Tm + 16;
   TZ_REQUIRE(smem <= 200 * 1024, "data set too long for the shared-memory staging (%zu bytes)", smem);

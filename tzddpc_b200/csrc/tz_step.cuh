@@ -2,11 +2,14 @@
 // bucket is instantiated in its own translation unit (tz_fused.cu: B0, tz_bucket*.cu: the larger ones) so that they
 // compile in parallel.  See tz_fused.cu for the description of the kernel.
 #pragma once
+#include <atomic>
 #include <cmath>
 #include <new>
 #include <vector>
 
 #include "tz_admm.cuh"
+#include "tz_cert2.cuh"
+#include "tz_param.cuh"
 
 #ifndef TZ_NO_HINTS
 #define TZ_LIKELY(x) __builtin_expect(!!(x), 1)
@@ -27,6 +30,8 @@ struct Aux {
   int n_dbl, n_int;                // sizes of the two parts
   int o_XB, o_CZ, o_K, o_coef;     // offsets (doubles)
   int o_ent, o_idx;                // offsets (int32, from the start of the int part)
+  int o_tt;                        // (doubles, even) term table of fast_step_kernel: n_nz pairs (coef, bits of idx | ent << 32)
+  int o_zrun, n_zrun;              // (doubles) zero runs of the dense Ze[1].Z between its non-zero entries: int32 pairs (first row, length)
   int n_nz;                        // entries of Ze[1].Z that are not structurally zero (centre column included)
   int n, m, N, nv, g1;
 };
@@ -59,6 +64,11 @@ struct StepArgs {
   const double* u_in;
   double* z_out;
   double* y_out;
+  // deferred tiles (fast_step_kernel -> step_kernel): defer[0] = number of listed tiles, defer[1] = exit ticket of step_kernel's
+  // CTAs (the last one zeroes both); defer_list[i] = index of a 16-scenario output tile.  list_mode: step_kernel walks the list
+  int32_t* defer;
+  int32_t* defer_list;
+  int list_mode;
 };
 
 // Shared-memory image of one CTA: the program (read-only after staging) and, per warp, the
@@ -366,9 +376,16 @@ __device__ __forceinline__ void run_program(unsigned char* smem_raw, const QpPro
   const int64_t ntiles = tile_limit;
   const int64_t nwarps = tile_stride;
   const int64_t otile0 = tile_first + wib;
+  // list mode (the tiles fast_step_kernel deferred): iteration i works on output tile defer_list[i]
+  const int64_t tile_max = (a.S + BK::SPO - 1) / BK::SPO - 1;
+  auto tile_at = [&](int64_t i) {
+    if (!a.list_mode) return i;
+    const int64_t t = a.defer_list[i];
+    return t < 0 ? (int64_t)0 : (t > tile_max ? tile_max : t);
+  };
   const double* hintp = (sp.warm == 2 && !explicit_qp) ? a.warm : nullptr;
   // inputs of this warp's first output tile: in flight while the program is staged (cp.async group 0)
-  if (!explicit_qp && otile0 < ntiles) prefetch_inputs<BK>(wb.pre[0], a, hintp, n, otile0, lane);
+  if (!explicit_qp && otile0 < ntiles) prefetch_inputs<BK>(wb.pre[0], a, hintp, n, tile_at(otile0), lane);
   if (stage) {  // stage the program and its tables once per CTA (persistent kernel: amortised over all tiles of this CTA): 16-byte
      // cp.async copies, all in flight at once (a load/store loop serialised ~10 dependent round trips to L2 per thread)
     const char* src = reinterpret_cast<const char*>(gpg);
@@ -400,10 +417,11 @@ __device__ __forceinline__ void run_program(unsigned char* smem_raw, const QpPro
   __syncwarp();
 
   int buf = 0;
-  for (int64_t otile = otile0; otile < ntiles; otile += nwarps, buf ^= 1) {
+  for (int64_t it = otile0; it < ntiles; it += nwarps, buf ^= 1) {
+    const int64_t otile = tile_at(it);
     if (!explicit_qp) {        // inputs of the NEXT output tile stream in while this one is solved
-      if (otile + nwarps < ntiles) {
-        prefetch_inputs<BK>(wb.pre[buf ^ 1], a, hintp, n, otile + nwarps, lane);
+      if (it + nwarps < ntiles) {
+        prefetch_inputs<BK>(wb.pre[buf ^ 1], a, hintp, n, tile_at(it + nwarps), lane);
         cp_async_wait<1>();
       } else {
         cp_async_wait<0>();
@@ -425,10 +443,10 @@ __device__ __forceinline__ void run_program(unsigned char* smem_raw, const QpPro
     double c0 = 0.0;
     bool param_ok = true, finite = true;
     LaneQp<BK> qp;
+    double w[2 * BK::NCOL2];                 // w = [1 | p | |p| | general atoms |Bt p + gam|] (+ a zero pad)
 
     if (!explicit_qp) {
       // ---- parameters p = [xbar0 | e0] (every lane of the group loads them: same sectors)
-      double w[2 * BK::NCOL2];               // w = [1 | p | |p| | general atoms |Bt p + gam|] (+ a zero pad)
       w[0] = 1.0;
       if constexpr (2 * BK::NCOL2 > NCOL) w[2 * BK::NCOL2 - 1] = 0.0;
 #pragma unroll
@@ -442,31 +460,12 @@ __device__ __forceinline__ void run_program(unsigned char* smem_raw, const QpPro
         finite = finite && (fabs(xv) < 1e300) && (fabs(ev) < 1e300);
         if (g == 0) { wb.om[BK::OM_P + j][col] = xv; wb.om[BK::OM_P + HP + j][col] = ev; }   // kept for the output phase
       }
-#pragma unroll
-      for (int i = 0; i < NAG; ++i) w[1 + 2 * NPAR + i] = 0.0;
-      if (pg.nag > 0) {
-#pragma unroll
-        for (int i = 0; i < NAG; ++i) {
-          double acc = pg.gam[i];
-#pragma unroll
-          for (int j = 0; j < NPAR; ++j) acc = fma(pg.Bt[i][j], w[1 + j], acc);
-          w[1 + 2 * NPAR + i] = fabs(acc);
-        }
-      }
+      eval_atoms<BK>(pg, w);
       // ---- this lane's rows of the bounds: l = l0 + R w, u = u0 + R w (scaled), kinks
 #pragma unroll
       for (int k = 0; k < NCL; ++k) {
         const int i = k * G + g;
-        // (16-byte shared loads, two accumulation chains per row)
-        const double2* Rr = reinterpret_cast<const double2*>(&pg.R[i][0]);
-        double r = 0.0, r1 = 0.0;
-#pragma unroll
-        for (int j = 0; j < BK::NCOL2; ++j) {
-          const double2 c2 = Rr[j];
-          r = fma(c2.x, w[2 * j], r);
-          r1 = fma(c2.y, w[2 * j + 1], r1);
-        }
-        r += r1;
+        const double r = row_shift<BK>(pg, i, w);     // (16-byte shared loads, two accumulation chains per row)
         if (k < N2) {
           qp.lo[k < N2 ? k : 0] = pg.l0[i] + r;
           qp.hi[k < N2 ? k : 0] = pg.u0[i] + r;
@@ -477,50 +476,17 @@ __device__ __forceinline__ void run_program(unsigned char* smem_raw, const QpPro
           qp.lo[k - NU] = pg.l0[i] + r;
         }
       }
-#pragma unroll
-      for (int j = 0; j < NZ; ++j) {
-        double acc = pg.q0[j];
-        if (pg.has_qp) {
-#pragma unroll
-          for (int k = 0; k < NPAR; ++k) acc = fma(pg.Qp[j][k], w[1 + k], acc);
-        }
-        qp.q[j] = acc;
-      }
+      eval_q<BK>(pg, w, qp.q);
       // ---- parameter-only feasibility rows, split over the group:  sum_j R_j w_j <= 1e-9 max(1, sum_j |R_j| |w_j|)
       int bad = 0;
 #pragma unroll
       for (int k = 0; k < NCHL; ++k) {
         const int i = k * G + g;
-        if (i < pg.nchk) {
-          const double2* Rc = reinterpret_cast<const double2*>(&pg.Rchk[i % BK::NCHK][0]);
-          double r = 0.0, ra = 0.0;
-#pragma unroll
-          for (int j2 = 0; j2 < BK::NCOL2; ++j2) {
-            const double2 c2 = Rc[j2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int j = 2 * j2 + h;
-              const double c = h == 0 ? c2.x : c2.y;
-              r = fma(c, w[j], r);
-              ra = fma(fabs(c), (j >= 1 && j <= NPAR) ? w[j + NPAR] : w[j], ra);    // |w_j|: the |p| columns are already there
-            }
-          }
-          bad |= (r > 1e-9 * fmax(1.0, ra)) ? 1 : 0;
-        }
+        if (i < pg.nchk) bad |= param_row_violated<BK>(pg, i % BK::NCHK, w) ? 1 : 0;
       }
       param_ok = gor<G>(bad) == 0;
       // ---- cost constant c0(p)
-#pragma unroll
-      for (int j = 0; j < NCOL; ++j) c0 = fma(pg.cc[j], w[j], c0);
-      if (pg.has_cc2) {
-#pragma unroll
-        for (int i = 0; i < NPAR; ++i) {
-          double acc = 0.0;
-#pragma unroll
-          for (int j = 0; j < NPAR; ++j) acc = fma(pg.CC2[i][j], w[1 + j], acc);
-          c0 = fma(acc, w[1 + i], c0);
-        }
-      }
+      c0 = cost_const<BK>(pg, w);
     } else {
       // explicit instance: scale the caller's q, l, u  (qbar = c D q, lbar = E l)
 #pragma unroll
@@ -573,6 +539,7 @@ __device__ __forceinline__ void run_program(unsigned char* smem_raw, const QpPro
     // tried first; when its KKT certificate holds the step is solved exactly without a single ADMM iteration
     const bool use_hint = sp.warm == 2 && a.warm != nullptr;
     bool hint_ok = false;
+    double hint_obj = 0.0;          // NZ == 2: scaled objective of the hint-certified point (tz_cert2.cuh)
     bool fresh = false;             // first step of a run (or no usable hint): its active set becomes the run-start hint
     if (use_hint) {
       unsigned long long hint = 0ull;
@@ -582,20 +549,36 @@ __device__ __forceinline__ void run_program(unsigned char* smem_raw, const QpPro
       const int invalid = gor<G>((hint & kCodeValid) ? 0 : 1);
       const bool valid = solve_it && invalid == 0;
       if (__any_sync(0xffffffffu, valid)) {
-        double lam[NCL], xk[NZ], x0[NZ];
-#pragma unroll
-        for (int k = 0; k < NCL; ++k) lam[k] = 0.0;
-#pragma unroll
-        for (int j = 0; j < NZ; ++j) x0[j] = 0.0;
         const unsigned long long code = hint & ~(kCodeValid | kCodeFresh);
-        const bool ok = admm_certify<BK>(qp, inv_alpha, sp.polish > 0 ? sp.polish : 3, code, x0, lam, xk);
-        if (ok && valid) {
+        if constexpr (NZ == 2) {
+          // two-variable programs: the closed-form certificate of tz_cert2.cuh, evaluated redundantly by the G lanes of
+          // the group -- the function fast_step_kernel runs with one thread per scenario, hence bit-identical results
+          unsigned long long hwv[G];
 #pragma unroll
-          for (int j = 0; j < NZ; ++j) st.x[j] = xk[j];
+          for (int j = 0; j < G; ++j) hwv[j] = __shfl_sync(0xffffffffu, code, (lane & ~(G - 1)) + j);
+          const Cert2Result cr = certify2<BK>(pg, w, qp.q, hwv);
+          if (cr.verdict == kCertOk && valid) {
+            st.x[0] = cr.x[0];
+            st.x[NZ - 1] = cr.x[1];
+            st.code = code;
+            hint_obj = cr.obj;
+            hint_ok = true;
+          }
+        } else {
+          double lam[NCL], xk[NZ], x0[NZ];
 #pragma unroll
-          for (int k = 0; k < NCL; ++k) st.w[k] = lam[k];
-          st.code = code;
-          hint_ok = true;
+          for (int k = 0; k < NCL; ++k) lam[k] = 0.0;
+#pragma unroll
+          for (int j = 0; j < NZ; ++j) x0[j] = 0.0;
+          const bool ok = admm_certify<BK>(qp, inv_alpha, sp.polish > 0 ? sp.polish : 3, code, x0, lam, xk);
+          if (ok && valid) {
+#pragma unroll
+            for (int j = 0; j < NZ; ++j) st.x[j] = xk[j];
+#pragma unroll
+            for (int k = 0; k < NCL; ++k) st.w[k] = lam[k];
+            st.code = code;
+            hint_ok = true;
+          }
         }
       }
     }
@@ -622,8 +605,10 @@ __device__ __forceinline__ void run_program(unsigned char* smem_raw, const QpPro
       if (live) {
         unsigned long long wnext = 0ull;
         if (good) {
-          wnext = st.code | kCodeValid;
-          if (fresh) a.warm[(int64_t)(G + g) * LD + s] = __longlong_as_double((long long)wnext);
+          if (status == TZ_STATUS_OK) {        // (a MAXITER iterate is applied but its active set is not trusted as a hint)
+            wnext = st.code | kCodeValid;
+            if (fresh) a.warm[(int64_t)(G + g) * LD + s] = __longlong_as_double((long long)wnext);
+          }
         } else if (a.x_restart != nullptr) {
           const unsigned long long h0 = (unsigned long long)__double_as_longlong(a.warm[(int64_t)(G + g) * LD + s]);
           wnext = (h0 & kCodeValid) ? (h0 | kCodeFresh) : 0ull;
@@ -687,6 +672,7 @@ __device__ __forceinline__ void run_program(unsigned char* smem_raw, const QpPro
         acc = fma(0.5 * px + qp.q[j], st.x[j], acc);
       }
       cost = fma(acc, pg.cinv, c0);
+      if (NZ == 2 && hint_ok) cost = fma(hint_obj, pg.cinv, c0);      // the arithmetic of fast_step_kernel
     } else if (live && status == TZ_STATUS_INFEASIBLE) {
       cost = INFINITY;                      // cvxpy returns +inf for an infeasible Minimize (:374)
     }
@@ -730,8 +716,23 @@ template <class BK>
 __global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel(const QpProg<BK>* __restrict__ gpg, const Aux ax,
                                                                 const SolverParams sp, const StepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  run_program<BK>(smem_raw, gpg, ax, sp, a, (int64_t)blockIdx.x * BK::WPB, (int64_t)gridDim.x * BK::WPB,
-                  (a.S + BK::SPO - 1) / BK::SPO, blockIdx.x * BK::WPB);
+  int64_t ntiles = (a.S + BK::SPO - 1) / BK::SPO;
+  if (a.list_mode) {
+    // the tiles fast_step_kernel could not decide; every CTA takes an exit ticket and the last one clears the list
+    const int64_t cnt = *reinterpret_cast<volatile const int32_t*>(a.defer);
+    ntiles = cnt < 0 ? 0 : (cnt < ntiles ? cnt : ntiles);          // (a foreign scratch buffer cannot send the kernel out of bounds)
+    if ((int64_t)blockIdx.x * BK::WPB < ntiles)
+      run_program<BK>(smem_raw, gpg, ax, sp, a, (int64_t)blockIdx.x * BK::WPB, (int64_t)gridDim.x * BK::WPB, ntiles,
+                      blockIdx.x * BK::WPB);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int t = atomicAdd(a.defer + 1, 1);
+      if (t == (int)gridDim.x - 1) { a.defer[0] = 0; a.defer[1] = 0; }
+    }
+    return;
+  }
+  run_program<BK>(smem_raw, gpg, ax, sp, a, (int64_t)blockIdx.x * BK::WPB, (int64_t)gridDim.x * BK::WPB, ntiles,
+                  blockIdx.x * BK::WPB);
 }
 
 // Data-set axis (BASELINE.json north_star: scenarios = noise realisations x initial states x DATA SETS): `nprog` programs
@@ -817,7 +818,20 @@ struct TzProgram {
   std::vector<int32_t> tube_ent;         // entries of Ze[1].Z (row-major index) that are not structurally zero, in table order
   size_t smem_tab = 0;                   // bytes of the run-time tables staged behind Smem<bucket>
   int num_sms = 148;
+  int device = -1;                       // the CUDA device the program image lives on: launches on another device are refused
 };
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute of a kernel.  The only process-wide state of the
+// library is this cache of "already set on device d" bits, one word per kernel; setting the attribute is idempotent, so a
+// race between two threads only repeats the call.
+template <class K>
+int ensure_dynamic_smem(K kernel, int bytes, int device, std::atomic<unsigned long long>& done) {
+  const unsigned long long bit = 1ull << (device & 63);
+  if (device >= 0 && device < 64 && (done.load(std::memory_order_relaxed) & bit)) return TZ_OK;
+  TZ_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  if (device >= 0 && device < 64) done.fetch_or(bit, std::memory_order_relaxed);
+  return TZ_OK;
+}
 
 constexpr int kMaxTabBytes = 24 * 1024;
 
@@ -827,12 +841,8 @@ namespace tz {
 template <class BK>
 int launch_bucket(const TzProgram* p, const SolverParams& sp, const StepArgs& a, cudaStream_t st) {
   const size_t smem = sizeof(Smem<BK>) + p->smem_tab;
-  static bool configured = false;     // benign race: the attribute is idempotent
-  if (!configured) {
-    TZ_CUDA(cudaFuncSetAttribute(step_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(sizeof(Smem<BK>) + kMaxTabBytes)));
-    configured = true;
-  }
+  static std::atomic<unsigned long long> configured{0ull};
+  if (const int rc = ensure_dynamic_smem(step_kernel<BK>, (int)(sizeof(Smem<BK>) + kMaxTabBytes), p->device, configured)) return rc;
   // persistent grid: one wave of CTAs (MINB per SM); every warp loops over tiles of SPW scenarios
   const int64_t ntiles = (a.S + BK::SPO - 1) / BK::SPO;
   const int64_t need = (ntiles + BK::WPB - 1) / BK::WPB;
@@ -848,12 +858,8 @@ template <class BK>
 int launch_bucket_set(const TzProgram* p0, const SetEntry* entries_dev, int nprog, int64_t total_tiles, const SolverParams& sp,
                       const StepArgs& a, cudaStream_t st) {
   const size_t smem = sizeof(Smem<BK>) + p0->smem_tab;
-  static bool configured = false;     // benign race: the attribute is idempotent
-  if (!configured) {
-    TZ_CUDA(cudaFuncSetAttribute(step_kernel_set<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(sizeof(Smem<BK>) + kMaxTabBytes)));
-    configured = true;
-  }
+  static std::atomic<unsigned long long> configured{0ull};
+  if (const int rc = ensure_dynamic_smem(step_kernel_set<BK>, (int)(sizeof(Smem<BK>) + kMaxTabBytes), p0->device, configured)) return rc;
   static_assert(BK::SPO == TZ_SPO_MIN, "tz_program_set_create counts output tiles of TZ_SPO_MIN scenarios");
   // one wave of CTAs, each with an equal contiguous share of the tiles of all programs (at least one tile per warp)
   const int64_t wave = (int64_t)p0->num_sms * BK::MINB;

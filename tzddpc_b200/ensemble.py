@@ -49,7 +49,8 @@ class TZDDPCEnsemble(object):
         assert all(v % 16 == 0 for v in counts[:-1]), "scenarios per data set must be a multiple of 16 (all but the last)"
         self.controllers = list(controllers)
         self.begin = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
-        self._program = _SetProgram(_abi.ProgramSet([c._program for c in controllers], self.begin))
+        with torch.cuda.device(c0.device):                # the set's entry table lives on the controllers' device
+            self._program = _SetProgram(_abi.ProgramSet([c._program for c in controllers], self.begin))
         self.device, self.solver_options, self.verbose = c0.device, SolverOptions(), False
         self.dim_x, self.dim_u, self.horizon, self._dims = c0.dim_x, c0.dim_u, c0.horizon, list(c0._dims)
         self.zonotopes = c0.zonotopes

@@ -31,11 +31,12 @@ class SolverOptions:
     warm_start: int = 0      # 0 cold, 1 reuse (x, y) of the previous call, 2 active-set hint of the previous call
     cert_first: int = 3      # first ADMM iteration at which the active-set KKT certificate is tried, 0 = off
     tube_packed: int = 0     # 1: Ze[1].Z is written as n_nz rows (Program.tube_pattern) instead of the dense n(1+g1) rows
+    hot_path: int = 1        # 1: warm_start == 2 on a two-variable program runs fast_step_kernel first (bit-identical results)
 
     def pack(self) -> List[float]:
         return [self.rho, self.rho_active, self.rho_inactive, self.sigma, self.alpha, self.eps_abs, self.eps_rel,
                 float(self.max_iter), float(self.check_every), float(int(self.polish)), float(self.warm_start),
-                float(int(self.cert_first)), float(int(self.tube_packed))]
+                float(int(self.cert_first)), float(int(self.tube_packed)), float(int(self.hot_path))]
 
 
 def _opts(o: List[float]) -> _abi.TzSolverOpts:
@@ -44,6 +45,7 @@ def _opts(o: List[float]) -> _abi.TzSolverOpts:
     s.max_iter, s.check_every, s.polish, s.warm_start = int(o[7]), int(o[8]), int(o[9]), int(o[10])
     s.cert_first = int(o[11]) if len(o) > 11 else 3
     s.tube_packed = int(o[12]) if len(o) > 12 else 0
+    s.hot_path = int(o[13]) if len(o) > 13 else 1
     return s
 
 
@@ -57,6 +59,41 @@ def _stream(t: Tensor):
 
 def _chk(t: Tensor, dtype=torch.float64):
     assert t.is_cuda and t.dtype == dtype and t.is_contiguous(), "expected a contiguous CUDA tensor of " + str(dtype)
+
+
+def _chk_opt(t: Optional[Tensor], what: str, S: int, rows: Optional[int] = None, min_rows: Optional[int] = None,
+             dtype=torch.float64):
+    """Optional output / scratch tensors are handed to the kernels as raw pointers: the C ABI cannot know their sizes, so a
+    wrong dtype, a non-contiguous slice or too few rows would corrupt device memory silently."""
+    if t is None:
+        return
+    _chk(t, dtype)
+    shape = tuple(t.shape)
+    if rows is None and min_rows is None:
+        assert shape == (S,), f"{what}: expected shape ({S},), got {shape}"
+        return
+    assert len(shape) == 2 and shape[1] == S, f"{what}: expected (rows, {S}), got {shape}"
+    if rows is not None:
+        assert shape[0] == rows, f"{what}: expected {rows} rows, got {shape[0]}"
+    if min_rows is not None:
+        assert shape[0] >= min_rows, f"{what}: needs at least {min_rows} rows, got {shape[0]}"
+
+
+def _chk_step(prog_dims, S, x, cost, v, traj, ze1, u, iters, warm, stats, x_restart, status, packed):
+    n, m, nv, nt, nent, n_nz, warm_rows = prog_dims
+    for t, nm in ((x_restart, "x_restart"),):
+        _chk_opt(t, nm, S, rows=n)
+    _chk_opt(cost, "cost", S)
+    _chk_opt(status, "status", S, dtype=torch.int32)
+    _chk_opt(iters, "iters", S, dtype=torch.int32)
+    _chk_opt(v, "v", S, rows=nv)
+    _chk_opt(traj, "traj", S, rows=nt)
+    _chk_opt(ze1, "ze1", S, rows=(n_nz if packed else nent))
+    _chk_opt(u, "u", S, rows=m)
+    _chk_opt(warm, "warm", S, min_rows=warm_rows)
+    if stats is not None:
+        _chk(stats)
+        assert stats.numel() >= _abi.TZ_NSTATS, "stats: needs TZ_NSTATS doubles"
 
 
 @torch.library.custom_op("tzddpc::solve", mutates_args=("warm",), device_types="cuda")
@@ -75,6 +112,10 @@ def solve(prog: int, dims: List[int], xbar0: Tensor, e0: Tensor, warm: Optional[
     status = torch.empty(S, dtype=torch.int32, device=dev)
     iters = torch.empty(S, dtype=torch.int32, device=dev)
     o = _opts(opts)
+    d = _abi.program_dims(prog)
+    assert xbar0.shape == (d[0], S) and e0.shape == xbar0.shape, "xbar0, e0: (n, S)"
+    assert (nv, nt) == (d[2], d[3]) and (not want_tube or nent == (d[5] if o.tube_packed else d[4])), "dims do not match the program"
+    _chk_opt(warm if o.warm_start else None, "warm", S, min_rows=d[6])
     with torch.cuda.device(dev):
         rc = _abi.lib().tz_solve(C.c_void_p(prog), C.byref(o), S, _ptr(xbar0), _ptr(e0), _ptr(cost), _ptr(v), _ptr(traj),
                                  _ptr(ze1) if want_tube else None, _ptr(status), _ptr(iters), _ptr(warm), _stream(xbar0))
@@ -94,6 +135,11 @@ def closed_loop_step(prog: int, x: Tensor, xbar: Tensor, e: Tensor, noise: Tenso
     _chk(x), _chk(xbar), _chk(e), _chk(noise), _chk(A_true), _chk(B_true), _chk(status, torch.int32)
     S = x.shape[1]
     o = _opts(opts)
+    d = _abi.program_dims(prog)
+    assert x.shape == (d[0], S) and xbar.shape == x.shape and e.shape == x.shape and noise.shape == x.shape, "x, xbar, e, noise: (n, S)"
+    _chk_step(d, S, x, cost, v, traj, ze1, u, iters, warm if o.warm_start else None, stats, x_restart, status, o.tube_packed)
+    if warm is not None:
+        _chk(warm)
     with torch.cuda.device(x.device):
         rc = _abi.lib().tz_closed_loop_step(C.c_void_p(prog), C.byref(o), S, _ptr(x), _ptr(xbar), _ptr(e), _ptr(noise),
                                             _ptr(x_restart), _ptr(A_true), _ptr(B_true), _ptr(cost), _ptr(v), _ptr(traj), _ptr(ze1),
@@ -117,6 +163,10 @@ def solve_set(pset: int, dims: List[int], xbar0: Tensor, e0: Tensor, warm: Optio
     status = torch.empty(S, dtype=torch.int32, device=dev)
     iters = torch.empty(S, dtype=torch.int32, device=dev)
     o = _opts(opts)
+    d = _abi.program_dims(pset, True)
+    assert xbar0.shape == (d[0], S) and e0.shape == xbar0.shape, "xbar0, e0: (n, S)"
+    assert (nv, nt) == (d[2], d[3]) and (not want_tube or nent == (d[5] if o.tube_packed else d[4])), "dims do not match the program"
+    _chk_opt(warm if o.warm_start else None, "warm", S, min_rows=d[6])
     with torch.cuda.device(dev):
         rc = _abi.lib().tz_solve_set(C.c_void_p(pset), C.byref(o), S, _ptr(xbar0), _ptr(e0), _ptr(cost), _ptr(v), _ptr(traj),
                                      _ptr(ze1) if want_tube else None, _ptr(status), _ptr(iters), _ptr(warm), _stream(xbar0))
@@ -135,6 +185,11 @@ def closed_loop_step_set(pset: int, x: Tensor, xbar: Tensor, e: Tensor, noise: T
     _chk(x), _chk(xbar), _chk(e), _chk(noise), _chk(A_true), _chk(B_true), _chk(status, torch.int32)
     S = x.shape[1]
     o = _opts(opts)
+    d = _abi.program_dims(pset, True)
+    assert x.shape == (d[0], S) and xbar.shape == x.shape and e.shape == x.shape and noise.shape == x.shape, "x, xbar, e, noise: (n, S)"
+    _chk_step(d, S, x, cost, v, traj, ze1, u, iters, warm if o.warm_start else None, stats, x_restart, status, o.tube_packed)
+    if warm is not None:
+        _chk(warm)
     with torch.cuda.device(x.device):
         rc = _abi.lib().tz_closed_loop_step_set(C.c_void_p(pset), C.byref(o), S, _ptr(x), _ptr(xbar), _ptr(e), _ptr(noise),
                                                 _ptr(x_restart), _ptr(A_true), _ptr(B_true), _ptr(cost), _ptr(v), _ptr(traj),
@@ -287,6 +342,26 @@ def gain_synthesis(AB: Tensor, Pinv: Tensor, WZ: Tensor, tol: float, max_iter: i
                                           _ptr(K), _ptr(dA), _ptr(dB), _ptr(rho), _ptr(robust), _ptr(iters), _ptr(status), _stream(AB))
     _abi.check(rc, "tz_gain_synthesis")
     return K, dA, dB, rho, robust, iters, status
+
+
+@torch.library.custom_op("tzddpc::gain_adversary", mutates_args=(), device_types="cuda")
+def gain_adversary(AB: Tensor, Pinv: Tensor, WZ: Tensor, K: Tensor, num_init: int, accuracy: float, confidence: float,
+                   seed: int, dataset_offset: int) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """compute_A_B + is_gain_robust (tzddpc/utils.py:13-41,105-129) for given gains K (D, m, n), batched over D data sets.
+    Returns dA (D, n, n), dB (D, n, m), rho (D, 3), robust, status (D, int32)."""
+    _chk(AB), _chk(Pinv), _chk(WZ), _chk(K)
+    D, n, d = AB.shape
+    m, Tm = d - n, Pinv.shape[1]
+    dev = AB.device
+    f64 = dict(dtype=torch.float64, device=dev)
+    dA, dB, rho = torch.empty((D, n, n), **f64), torch.empty((D, n, m), **f64), torch.empty((D, 3), **f64)
+    robust, status = (torch.empty(D, dtype=torch.int32, device=dev) for _ in range(2))
+    with torch.cuda.device(dev):
+        rc = _abi.lib().tz_gain_adversary(D, Tm + 1, n, m, WZ.shape[1] - 1, _ptr(AB), _ptr(Pinv), _ptr(WZ), _ptr(K), int(num_init),
+                                          float(accuracy), float(confidence), int(seed), int(dataset_offset),
+                                          _ptr(dA), _ptr(dB), _ptr(rho), _ptr(robust), _ptr(status), _stream(AB))
+    _abi.check(rc, "tz_gain_adversary")
+    return dA, dB, rho, robust, status
 
 
 @torch.library.custom_op("tzddpc::qp_solve", mutates_args=(), device_types="cuda")

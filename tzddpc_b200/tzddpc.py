@@ -162,6 +162,7 @@ class TZDDPC(object):
         GW = self._t(W.generators)                              # n x gW
         gens = -(GW.t()[:, None, :, None] * self._Pinv[None, :, None, :])       # gW x (T-1) x n x (n+m)
         self.Mdata = MatrixZonotope(self._AB, gens.reshape(-1, self.dim_x, self.dim_x + self.dim_u).cpu().numpy())
+        self.Mdata.rank_one = (self._Pinv, self._t(W.Z))       # structure the utils.* gain helpers work on (utils.py)
         if self.verbose:
             print('--------------------------------------------')
         return self.Mdata
@@ -266,7 +267,8 @@ class TZDDPC(object):
             for k, g in enumerate(prog.gens_per_step):           # tzddpc/tzddpc.py:190,206
                 print(f'Step {k}')
                 print(g)
-        self._program = _abi.Program(prog, self.theta.K)
+        with torch.cuda.device(self.device):             # the program image lives on the controller's device
+            self._program = _abi.Program(prog, self.theta.K)
         self.problem_full = self._program
         self.horizon = horizon
         self.parameters = ("e0", "xbar0")
@@ -313,6 +315,11 @@ class TZDDPC(object):
             with open('zpc_logs.txt', 'w') as f:                             # tzddpc/tzddpc.py:368-371
                 print('Error while solving the TZDDPC problem. Details: non-finite data', file=f)
             raise Exception('Error while solving the TZDDPC problem. Details: non-finite data')
+        if status[0] == _abi.TZ_STATUS_MAXITER:
+            # the reference surfaces a solver failure as an exception (cp.SolverError -> tzddpc/tzddpc.py:366-371)
+            with open('zpc_logs.txt', 'w') as f:
+                print('Error while solving the TZDDPC problem. Details: the solver did not converge', file=f)
+            raise Exception('Error while solving the TZDDPC problem. Details: the solver did not converge')
         if np.isinf(cost[0]):
             raise Exception('Problem is unbounded')                          # tzddpc/tzddpc.py:374-375
         tube = TubeHandle(r.tube._ze1, n, self._program.compiled.g1, False, r.tube._pattern)
