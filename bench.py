@@ -444,17 +444,24 @@ def datasets_leg(args, tz, ops, torch, dev, cfg, nring):
     n, N = cfg.n, cfg.horizon
     Z = tz.Zonotope
     zon = tz.SystemZonotopes(Z(*cfg.X0), Z(*cfg.U), Z(*cfg.X), Z(*cfg.W))
+    f64 = dict(dtype=torch.float64, device=dev)
+    torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
-    data = [tz.Data(*configs.generate_dataset(cfg, np.random.default_rng(cfg.seed + 101 * d))) for d in range(D)]
-    # one tz_identify + one tz_gain_synthesis launch for all data sets, then the host canonicalisation per data set
-    ens = tz.TZDDPCEnsemble.from_datasets(data, zon, N, tz.StageCost(**cfg.cost),
+    # the D data sets are generated on the device (tz_generate_trajectories: examples/utils.py:6-45, one trajectory each) and
+    # never leave it; one tz_identify + one tz_gain_synthesis launch for all of them, the host canonicalisation batched over the
+    # data sets, one tz_program_create_batch
+    zt = lambda c, G: torch.tensor(np.hstack([np.asarray(c, dtype=np.float64)[:, None], np.asarray(G, dtype=np.float64)]), **f64)   # noqa: E731
+    Ud, Xd = ops.generate_trajectories(torch.tensor(cfg.A, **f64), torch.tensor(cfg.B, **f64), zt(*cfg.X0), zt(*cfg.U), zt(*cfg.W), D, cfg.T,
+                                       cfg.seed, 0)
+    torch.cuda.synchronize(dev)
+    gen_s = time.perf_counter() - t0
+    ens = tz.TZDDPCEnsemble.from_datasets((Ud, Xd), zon, N, tz.StageCost(**cfg.cost),
                                           tz.BoxConstraint(**cfg.box) if cfg.box else tz.BoxConstraint(), scenarios_per_dataset=per,
                                           device=dev)
     torch.cuda.synchronize(dev)
     setup_s = time.perf_counter() - t0
     prog = ens._program
     g1, nv = prog.compiled.g1, prog.compiled.nv
-    f64 = dict(dtype=torch.float64, device=dev)
     WZ = torch.tensor(np.hstack([cfg.W[0][:, None], cfg.W[1]]), **f64)
     noise = torch.stack([ops.sample_noise(WZ, S, cfg.noise == "vertex", cfg.seed, 0, t) for t in range(nring)])
     x0 = torch.tensor(cfg.X0[0], **f64)
@@ -493,7 +500,7 @@ def datasets_leg(args, tz, ops, torch, dev, cfg, nring):
     ms = a.elapsed_time(b) / Kd
     tot = stats[5:].sum(0).cpu().numpy()
     return {"datasets": D, "scenarios_per_dataset": per, "ms_per_step": ms, "value": S / (ms * 1e-3), "unit": UNIT, "steps": Kd,
-            "setup_s": setup_s, "gain": "tz_gain_synthesis (one launch, a robust LQR gain per data set)",
+            "setup_s": setup_s, "setup_generate_data_s": gen_s, "gain": "tz_gain_synthesis (one launch, a robust LQR gain per data set)",
             "gain_iterations_max": int(ens.theta_info["iterations"].max()), "rho_max": float(ens.theta_info["rho"].max()),
             "api": "TZDDPCEnsemble -> tz_closed_loop_step_set (one launch per step, one program per data set)",
             "status_ok_frac": float(1.0 - (tot[3] + tot[4] + tot[6]) / max(tot[7], 1.0)), "iters_mean": float(tot[5] / max(tot[7], 1.0))}
@@ -789,7 +796,7 @@ def main():
     ap.add_argument("--e2e-chunks", type=int, default=2)
     ap.add_argument("--e2e-chunks-resident", type=int, default=4)
     ap.add_argument("--regime-steps", type=int, default=200, help="length of the long window of the `regimes` leg (0 = skip)")
-    ap.add_argument("--datasets", type=int, default=64, help="data sets of the data-set-axis leg (0 = skip)")
+    ap.add_argument("--datasets", type=int, default=4096, help="data sets of the data-set-axis leg (0 = skip)")
     ap.add_argument("--cpu-scen", type=int, default=48, help="scenarios per core of the CPU baseline")
     ap.add_argument("--cpu-cores", type=int, default=0, help="processes of the CPU baseline (0 = all host cores)")
     ap.add_argument("--dump-steps", default="", help="write per-step kernel ms and solver statistics to this .npz (diagnostics)")

@@ -92,6 +92,14 @@ typedef struct TzProgram TzProgram;   /* opaque */
 
 int tz_program_create(const TzProgramDesc* desc, TzProgram** out);
 void tz_program_destroy(TzProgram* prog);
+/* D programs of one structure (the same problem built from D data sets: the data-set axis) created at once -- packed on the
+ * host, one device allocation and one copy for all of them.  tz_program_batch_get(batch, d) is a program handle as
+ * tz_program_create returns it, borrowed from the batch: pass it to tz_solve, tz_program_set_create, ...; do not destroy
+ * it, destroy the batch (after every set built from it). */
+typedef struct TzProgramBatch TzProgramBatch;   /* opaque */
+int tz_program_create_batch(const TzProgramDesc* descs, int32_t D, TzProgramBatch** out);
+const TzProgram* tz_program_batch_get(const TzProgramBatch* batch, int32_t d);
+void tz_program_batch_destroy(TzProgramBatch* batch);
 /* which compiled kernel bucket serves this program: writes e.g. "B2(NZ=2,NC=28,G=4)" into buf */
 int tz_program_bucket(const TzProgram* prog, char* buf, size_t cap);
 /* rows of the `warm` scratch array (rows x S doubles) that tz_solve / tz_closed_loop_step accept */

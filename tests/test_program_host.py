@@ -117,3 +117,48 @@ def test_callbacks_reduce_to_the_structured_cost():
     assert b3.x_hi[1] == 10 and b3.x_lo[1] == 2 and np.isinf(b3.x_hi[0]) and np.isinf(b3.x_lo[0])
     b0 = cp.extract_box_constraints(lambda u, y: [], 2, 5, 1, False)
     assert b0.x_lo is None or not np.any(np.isfinite(b0.x_lo))
+
+
+def test_batched_canonicalisation_equals_the_single_one_bit_for_bit():
+    """compile_program_batch (the data-set axis: D models of one structure canonicalised at once) against compile_program on
+    each model: every field of every slice identical, whatever the batch the model sits in."""
+    from tzddpc_b200 import program as P
+    for name, D in (("fivedim", 5), ("double_integrator", 3)):
+        cfg = configs.CONFIGS[name]()
+        models = []
+        for d in range(D):
+            u, x = common.dataset(cfg, seed=cfg.seed + 101 * d)
+            o, _ = common.make_oracle(cfg, u, x)
+            Xi, Ui = o.zonotopes.X.interval, o.zonotopes.U.interval
+            models.append(P.TubeModel(AB=o.Mdata.center, Acl=o.MdataK.center, GK=o.MdataK.generators, GD=o.Mdelta.generators,
+                                      K=o.theta.K, WZ=o.zonotopes.W.Z, X_lo=Xi.left_limit, X_hi=Xi.right_limit,
+                                      U_lo=Ui.left_limit, U_hi=Ui.right_limit))
+        cost, box = P.StageCost(**cfg.cost), (P.BoxConstraint(**cfg.box) if cfg.box else P.BoxConstraint())
+        B = P.compile_program_batch(P.TubeModelBatch.of(models), cfg.horizon, cost, box)
+        B2 = P.compile_program_batch(P.TubeModelBatch.of(models[::-1] + models), cfg.horizon, cost, box)     # another batch composition
+        assert B.num == D
+        for d in range(D):
+            s, b, b2 = P.compile_program(models[d], cfg.horizon, cost, box), B.program(d), B2.program(D + d)
+            for f in ("P", "q0", "Qp", "A", "l0", "u0", "kink0", "wabs", "R", "Bt", "gam", "Rchk", "cc", "CC2", "XB", "ze1_ptr", "ze1_idx",
+                      "ze1_val", "D", "E"):
+                assert np.array_equal(getattr(s, f), getattr(b, f)), (name, d, f)
+                assert np.array_equal(getattr(s, f), getattr(b2, f)), (name, d, f, "batch composition")
+            assert s.c == b.c and (s.nc, s.nz, s.na, s.g1) == (b.nc, b.nz, b.na, b.g1)
+
+
+def test_boxed_model_batch_equals_the_generator_form():
+    """TubeModelBatch.boxed (straight from tz_identify's centre and boxes) builds the model the MatrixZonotope route builds."""
+    from tzddpc_b200 import program as P
+    cfg = configs.fivedim()
+    u, x = common.dataset(cfg)
+    o, _ = common.make_oracle(cfg, u, x)
+    n, m = cfg.n, cfg.m
+    dAB = np.abs(o.Mdelta.generators).sum(axis=0)
+    dK = np.abs(o.MdataK.generators).sum(axis=0)
+    Xi, Ui = o.zonotopes.X.interval, o.zonotopes.U.interval
+    mb = P.TubeModelBatch.boxed(o.Mdata.center[None], dAB[None], dK[None], o.theta.K[None], o.zonotopes.W.Z, Xi.left_limit,
+                                Xi.right_limit, Ui.left_limit, Ui.right_limit)
+    np.testing.assert_allclose(mb.Acl[0], o.MdataK.center, rtol=1e-13, atol=1e-15)
+    # the generators in Girard's diag order: single-entry matrices d[r, c] E_rc
+    np.testing.assert_array_equal(mb.GD[0], o.Mdelta.generators)
+    np.testing.assert_array_equal(mb.GK[0], o.MdataK.generators)

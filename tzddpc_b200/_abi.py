@@ -44,7 +44,8 @@ EXPORTS = ["tz_version", "tz_last_error", "tz_device_cc", "tz_program_create", "
            "tz_identify", "tz_qp_solve", "tz_philox4x32_10_host", "tz_sample_noise", "tz_generate_trajectories",
            "tz_program_tube_pattern", "tz_program_set_create", "tz_program_set_destroy", "tz_program_set_scenarios",
            "tz_solve_set", "tz_closed_loop_step_set", "tz_gain_synthesis", "tz_gain_robust_samples", "tz_gain_adversary", "tz_program_dims",
-           "tz_program_set_dims", "tz_closed_loop_run_host"]
+           "tz_program_set_dims", "tz_closed_loop_run_host", "tz_program_create_batch",
+           "tz_program_batch_get", "tz_program_batch_destroy"]
 
 
 def lib() -> C.CDLL:
@@ -63,6 +64,12 @@ def lib() -> C.CDLL:
     L.tz_device_cc.restype = C.c_int
     L.tz_program_create.restype = C.c_int
     L.tz_program_create.argtypes = [C.POINTER(TzProgramDesc), C.POINTER(vp)]
+    L.tz_program_create_batch.restype = C.c_int
+    L.tz_program_create_batch.argtypes = [C.POINTER(TzProgramDesc), i32, C.POINTER(vp)]
+    L.tz_program_batch_get.restype = vp
+    L.tz_program_batch_get.argtypes = [vp, i32]
+    L.tz_program_batch_destroy.restype = None
+    L.tz_program_batch_destroy.argtypes = [vp]
     L.tz_program_destroy.restype = None
     L.tz_program_destroy.argtypes = [vp]
     L.tz_program_bucket.restype = C.c_int
@@ -149,13 +156,27 @@ def _host(a, dtype) -> np.ndarray:
     return np.ascontiguousarray(np.asarray(a, dtype=dtype))
 
 
+_DESC_ARRAYS = ("P", "q0", "Qp", "A", "l0", "u0", "kink0", "wabs", "R", "Bt", "gam", "Rchk", "cc", "CC2", "XB", "ze1_val", "D", "E", "K")
+
+
+def _describe(L, handle, obj):
+    """bucket name, warm rows and tube pattern of a program handle -> attributes of obj"""
+    buf = C.create_string_buffer(64)
+    L.tz_program_bucket(handle, buf, 64)
+    obj.bucket = buf.value.decode()
+    obj.warm_rows = int(L.tz_program_warm_rows(handle))
+    nnz = int(L.tz_program_tube_pattern(handle, None, 0))
+    pat = np.zeros(max(nnz, 1), dtype=np.int32)
+    L.tz_program_tube_pattern(handle, pat.ctypes.data, nnz)
+    obj.tube_pattern = pat[:nnz]           # row-major indices of the entries of Ze[1].Z that are not structurally zero
+
+
 class Program:
     """Owner of a TzProgram handle built from a tzddpc_b200.program.CompiledProgram."""
 
     def __init__(self, prog, K: np.ndarray):
         L = lib()
         order = np.argsort(-(prog.wabs > 0).astype(np.int64), kind="stable")       # |.|-cost rows first
-        keep = {}
         f64 = lambda a: _host(a, np.float64)                                        # noqa: E731
         A, l0, u0 = f64(prog.A[order]), f64(prog.l0[order]), f64(prog.u0[order])
         kink0, wabs, R, E = f64(prog.kink0[order]), f64(prog.wabs[order]), f64(prog.R[order]), f64(prog.E[order])
@@ -169,25 +190,75 @@ class Program:
         d.g1, d.nterms, d.c = prog.g1, len(prog.ze1_idx), float(prog.c)
         for k, a in arrs.items():
             setattr(d, k, a.ctypes.data if a.size else None)
-        keep["arrs"] = arrs
         h = C.c_void_p()
         check(L.tz_program_create(C.byref(d), C.byref(h)), "tz_program_create")
         self.handle = h
         self.row_order = order
         self.compiled = prog
-        buf = C.create_string_buffer(64)
-        L.tz_program_bucket(h, buf, 64)
-        self.bucket = buf.value.decode()
-        self.warm_rows = int(L.tz_program_warm_rows(h))
-        nnz = int(L.tz_program_tube_pattern(h, None, 0))
-        pat = np.zeros(max(nnz, 1), dtype=np.int32)
-        L.tz_program_tube_pattern(h, pat.ctypes.data, nnz)
-        self.tube_pattern = pat[:nnz]          # row-major indices of the entries of Ze[1].Z that are not structurally zero
+        _describe(L, h, self)
 
     def __del__(self):
         try:
             if getattr(self, "handle", None):
                 lib().tz_program_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class ProgramView:
+    """Program d of a ProgramBatch: the interface of Program (handle, compiled, bucket, ...), borrowed from the batch."""
+
+    def __init__(self, batch: "ProgramBatch", d: int, handle):
+        self._batch, self._d, self.handle = batch, d, handle
+        self.row_order, self.bucket, self.warm_rows, self.tube_pattern = batch.row_order, batch.bucket, batch.warm_rows, batch.tube_pattern
+        self._compiled = None
+
+    @property
+    def compiled(self):
+        if self._compiled is None:
+            self._compiled = self._batch.compiled.program(self._d)
+        return self._compiled
+
+
+class ProgramBatch:
+    """Owner of a TzProgramBatch: the D programs of a tzddpc_b200.program.CompiledProgramBatch (one per data set), packed on
+    the host and uploaded with one copy.  `programs[d]` behaves like a Program."""
+
+    def __init__(self, cbatch, K: np.ndarray):
+        L = lib()
+        D = cbatch.num
+        order = np.argsort(-(cbatch.wabs[0] > 0).astype(np.int64), kind="stable")   # |.|-cost rows first (the structure is shared)
+        f64 = lambda a: _host(a, np.float64)                                        # noqa: E731
+        K = np.broadcast_to(np.asarray(K, dtype=np.float64).reshape((-1, cbatch.m, cbatch.n)), (D, cbatch.m, cbatch.n))
+        arrs = dict(P=f64(cbatch.P), q0=f64(cbatch.q0), Qp=f64(cbatch.Qp), A=f64(cbatch.A[:, order]), l0=f64(cbatch.l0[:, order]),
+                    u0=f64(cbatch.u0[:, order]), kink0=f64(cbatch.kink0[:, order]), wabs=f64(cbatch.wabs[:, order]),
+                    R=f64(cbatch.R[:, order]), Bt=f64(cbatch.Bt), gam=f64(cbatch.gam), Rchk=f64(cbatch.Rchk), cc=f64(cbatch.cc),
+                    CC2=f64(cbatch.CC2), XB=f64(cbatch.XB), ze1_val=f64(cbatch.ze1_val), D=f64(cbatch.D_), E=f64(cbatch.E[:, order]), K=f64(K))
+        ptr, idx = _host(cbatch.ze1_ptr, np.int32), _host(cbatch.ze1_idx, np.int32)
+        descs = (TzProgramDesc * D)()
+        nkink = int((cbatch.wabs[0] > 0).sum())
+        base = {k: (a.ctypes.data, a[0].nbytes if a.size else 0, a.size) for k, a in arrs.items()}
+        for d in range(D):
+            t = descs[d]
+            t.n, t.m, t.horizon, t.nv, t.nz, t.nc = cbatch.n, cbatch.m, cbatch.N, cbatch.nv, cbatch.nz, cbatch.nc
+            t.npar, t.na, t.nchk, t.nkink = cbatch.npar, cbatch.na, cbatch.Rchk.shape[1], nkink
+            t.g1, t.nterms, t.c = cbatch.g1, len(idx), float(cbatch.c[d])
+            for k in _DESC_ARRAYS:
+                p0, stride, size = base[k]
+                setattr(t, k, p0 + d * stride if size else None)
+            t.ze1_ptr, t.ze1_idx = ptr.ctypes.data, (idx.ctypes.data if idx.size else None)
+        h = C.c_void_p()
+        check(L.tz_program_create_batch(descs, D, C.byref(h)), "tz_program_create_batch")
+        self.handle, self.compiled, self.row_order, self.num = h, cbatch, order, D
+        h0 = C.c_void_p(L.tz_program_batch_get(h, 0))
+        _describe(L, h0, self)
+        self.programs = [ProgramView(self, d, C.c_void_p(L.tz_program_batch_get(h, d))) for d in range(D)]
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                lib().tz_program_batch_destroy(self.handle)
                 self.handle = None
         except Exception:
             pass

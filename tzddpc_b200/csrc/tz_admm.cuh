@@ -93,6 +93,8 @@ struct QpProg {
   int grp_order[BK::NC];               // t -> row slot
   int grp_new[BK::NC];                 // t -> 1: first row of a group
   double grp_sgn[BK::NC];              // t -> sign of A relative to the group's first row
+  int grp_first[BK::NC + 4];           // group g owns t in [grp_first[g], grp_first[g + 1]); entries beyond ngrp repeat nc
+  int ngrp;
   int nz, nc, npar, nag, nchk, has_cc2, has_qp;
 };
 

@@ -45,6 +45,31 @@ __device__ __forceinline__ void row_LA(const QpProg<BK>& pg, int i, const double
   }
 }
 
+// (L, A) of NR rows at once: 2 NR independent fma chains in flight (a thread of fast_step_kernel runs through the program
+// once, at ~14 warps per SM: the dependent-issue latency of a single chain is what bounds it).  Same arithmetic per row.
+template <class BK, int NR>
+__device__ __forceinline__ void row_LAn(const QpProg<BK>& pg, const int (&rows)[NR], const double (&w)[2 * BK::NCOL2],
+                                        double (&L)[NR], double (&A)[NR]) {
+  const double2* Rr[NR];
+#pragma unroll
+  for (int q = 0; q < NR; ++q) {
+    Rr[q] = reinterpret_cast<const double2*>(&pg.R[rows[q]][0]);
+    L[q] = 0.0;
+    A[q] = 0.0;
+  }
+#pragma unroll
+  for (int j = 0; j < BK::NCOL2; ++j) {
+#pragma unroll
+    for (int q = 0; q < NR; ++q) {
+      const double2 c2 = Rr[q][j];
+      if (2 * j >= 1 && 2 * j <= BK::NPAR) L[q] = fma(c2.x, w[2 * j], L[q]);
+      else A[q] = fma(c2.x, w[2 * j], A[q]);
+      if (2 * j + 1 >= 1 && 2 * j + 1 <= BK::NPAR) L[q] = fma(c2.y, w[2 * j + 1], L[q]);
+      else A[q] = fma(c2.y, w[2 * j + 1], A[q]);
+    }
+  }
+}
+
 // r_i(p) = E_i (R_i . w): the arithmetic every kernel of this library uses for the parametric shift of a row
 template <class BK>
 __device__ __forceinline__ double row_shift(const QpProg<BK>& pg, int i, const double (&w)[2 * BK::NCOL2]) {
@@ -194,15 +219,29 @@ __device__ __forceinline__ Cert2Result certify2(const QpProg<BK>& pg, const doub
   // (upper) bound carry -inf (+inf), so one expression serves the three row classes.
   double viol = -INFINITY, scale = 1.0;
   {
-    double L = 0.0, A = 0.0;
+    constexpr int GB = 4;                                          // groups per trip: 8 fma chains in flight
 #pragma unroll 1
-    for (int t = 0; t < pg.nc; ++t) {
-      const int i = pg.grp_order[t];
-      if (pg.grp_new[t]) row_LA<BK>(pg, i, w, L, A);            // (uniform branch: the same program for the whole warp)
-      const double r = pg.Rs[i] * fma(pg.grp_sgn[t], A, L);      // == row_shift(pg, i, w): sgn = -1 negates A exactly
-      const double ax = fma(pg.A[i][1], x1, pg.A[i][0] * x0);
-      viol = dmax(viol, dmax((pg.l0[i] + r) - ax, ax - (pg.u0[i] + r)));
-      scale = dmax(scale, fabs(ax));
+    for (int g0 = 0; g0 < pg.ngrp; g0 += GB) {
+      int reps[GB];
+      double L[GB], A[GB];
+#pragma unroll
+      for (int q = 0; q < GB; ++q) {
+        const int t = pg.grp_first[g0 + q];                        // (groups beyond ngrp are empty: t == nc, clamped below)
+        reps[q] = pg.grp_order[t < pg.nc ? t : pg.nc - 1];
+      }
+      row_LAn<BK, GB>(pg, reps, w, L, A);
+#pragma unroll
+      for (int q = 0; q < GB; ++q) {
+        const int t1 = pg.grp_first[g0 + q + 1];
+#pragma unroll 2
+        for (int t = pg.grp_first[g0 + q]; t < t1; ++t) {          // (uniform bounds: the same program for the whole warp)
+          const int i = pg.grp_order[t];
+          const double r = pg.Rs[i] * fma(pg.grp_sgn[t], A[q], L[q]);   // == row_shift(pg, i, w): sgn = -1 negates A exactly
+          const double ax = fma(pg.A[i][1], x1, pg.A[i][0] * x0);
+          viol = dmax(viol, dmax((pg.l0[i] + r) - ax, ax - (pg.u0[i] + r)));
+          scale = dmax(scale, fabs(ax));
+        }
+      }
     }
   }
   // ---- |.| rows: cost and the side of the kink the guess assumed

@@ -3,4 +3,5 @@
 
 namespace tz {
 template int launch_fast<B0>(const TzProgram*, const SolverParams&, const StepArgs&, cudaStream_t);
+template int launch_fast_set<B0>(const TzProgram*, const SolverParams&, const StepArgs&, const SetEntry*, const int32_t*, int, cudaStream_t);
 }

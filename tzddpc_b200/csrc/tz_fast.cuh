@@ -35,43 +35,65 @@
 
 namespace tz {
 
-template <class BK, int TPB>
-struct alignas(16) FastSmem {
-  QpProg<BK> pg;
-  double om[BK::KOM][TPB];                 // per-scenario vector [1 | v | xbar0 | e0 | centre of Ze[1]] for the term table's dynamic index
-};
-
 constexpr int kDeferTile = TZ_SPO_MIN;     // scenarios per deferred tile = output tile of step_kernel
 
-template <class BK, int TPB>
+// NSLOT = 0: one program for the whole batch, staged once per CTA of a persistent grid.
+// NSLOT = 1 / 2: a program SET (the data-set axis, tz_closed_loop_step_set): one block of TPB scenarios per CTA; its
+// 16-scenario tiles look their program up in tile_prog.  NSLOT = 1: the set guarantees that a block lies within one
+// program; NSLOT = 2 (TPB = 32): the two half-warps of the warp may belong to two programs, each staged in its own slot --
+// a coefficient load then has two distinct addresses per warp instead of one.
+template <class BK, int TPB, int NSLOT>
 __global__ void __launch_bounds__(TPB, 512 / TPB) fast_step_kernel(const QpProg<BK>* __restrict__ gpg, const Aux ax,
-                                                                  const SolverParams sp, const StepArgs a) {
+                                                                  const SolverParams sp, const StepArgs a,
+                                                                  const SetEntry* __restrict__ entries,
+                                                                  const int32_t* __restrict__ tile_prog, const int slot_bytes) {
   constexpr int NZ = BK::NZ, NPAR = BK::NPAR, HP = BK::NPAR / 2, NCOL = BK::NCOL, NW = BK::NW, G = BK::G;
   static_assert(kDeferTile == 16 && BK::SPO == 16, "deferred tiles are the 16-scenario output tiles of step_kernel");
+  static_assert(NSLOT <= 1 || TPB == 32, "two program slots: one warp per CTA");
+  constexpr int QPB = (int)((sizeof(QpProg<BK>) + 15) & ~(size_t)15);
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  FastSmem<BK, TPB>& sm = *reinterpret_cast<FastSmem<BK, TPB>*>(smem_raw);
-  double* tabd = reinterpret_cast<double*>(smem_raw + sizeof(FastSmem<BK, TPB>));
   const int tid = threadIdx.x, lane = tid & 31;
   const int n = ax.n, m = ax.m, nv = ax.nv;
   const bool closed = a.x != nullptr;
   const int64_t LD = a.ld;
   const bool dense = a.ze1 != nullptr && !sp.tube_packed;
-  // ---- stage the program and its tables (cp.async, all in flight at once)
-  {
-    const char* src = reinterpret_cast<const char*>(gpg);
-    char* dst = reinterpret_cast<char*>(&sm.pg);
+  // shared memory: NSLOT (or one) x [QpProg | tables | A_true | B_true], then om[KOM][TPB]
+  double (*om)[TPB] = reinterpret_cast<double (*)[TPB]>(smem_raw + (NSLOT > 1 ? NSLOT : 1) * (size_t)slot_bytes);
+  // ---- stage a program and its tables into a slot (cp.async, all in flight at once)
+  auto stage = [&](unsigned char* slot, const void* pg_src, const double* tab_src) {
+    const char* src = reinterpret_cast<const char*>(pg_src);
+    char* dst = reinterpret_cast<char*>(slot);
+    double* td = reinterpret_cast<double*>(slot + QPB);
     constexpr int NCH = (int)(sizeof(QpProg<BK>) / 16);
     for (int i = tid; i < NCH; i += TPB) cp_async16(dst + 16 * i, src + 16 * i);
     if (tid == 0 && (sizeof(QpProg<BK>) % 16) != 0) cp_async8(dst + 16 * NCH, src + 16 * NCH);
-    for (int i = tid; i < ax.n_dbl; i += TPB) cp_async8(tabd + i, ax.tab + i);
+    for (int i = tid; i < ax.n_dbl; i += TPB) cp_async8(td + i, tab_src + i);
     if (closed) {
-      for (int i = tid; i < n * n; i += TPB) cp_async8(tabd + ax.n_dbl + i, a.A_true + i);
-      for (int i = tid; i < n * m; i += TPB) cp_async8(tabd + ax.n_dbl + n * n + i, a.B_true + i);
+      for (int i = tid; i < n * n; i += TPB) cp_async8(td + ax.n_dbl + i, a.A_true + i);
+      for (int i = tid; i < n * m; i += TPB) cp_async8(td + ax.n_dbl + n * n + i, a.B_true + i);
     }
-    cp_async_commit();
+  };
+  unsigned char* my_slot = smem_raw;
+  if constexpr (NSLOT == 0) {
+    stage(smem_raw, gpg, ax.tab);
+  } else {
+    constexpr int TILES = TPB / kDeferTile;
+    const int64_t last_tile = (a.S + kDeferTile - 1) / kDeferTile - 1;
+    const int64_t t0 = (int64_t)blockIdx.x * TILES;
+    const int j0 = tile_prog[t0 < last_tile ? t0 : last_tile];
+    stage(smem_raw, entries[j0].pg, entries[j0].tab);
+    if constexpr (NSLOT == 2) {
+      const int j1 = tile_prog[t0 + 1 < last_tile ? t0 + 1 : last_tile];
+      if (j1 != j0) {                      // (uniform: one warp)
+        stage(smem_raw + slot_bytes, entries[j1].pg, entries[j1].tab);
+        if (lane >= 16) my_slot = smem_raw + slot_bytes;
+      }
+    }
   }
+  cp_async_commit();
+  double* tabd = reinterpret_cast<double*>(my_slot + QPB);
   bool staged = false;
-  const QpProg<BK>& pg = sm.pg;
+  const QpProg<BK>& pg = *reinterpret_cast<const QpProg<BK>*>(my_slot);
   const double* sXB = tabd + ax.o_XB;
   const double* sCZ = tabd + ax.o_CZ;
   const double* sK = tabd + ax.o_K;
@@ -79,13 +101,15 @@ __global__ void __launch_bounds__(TPB, 512 / TPB) fast_step_kernel(const QpProg<
   const double* sB = sA + n * n;
   const double2* tt = reinterpret_cast<const double2*>(tabd + ax.o_tt);      // term table: (coef, idx | ent << 32)
   const int* zs = reinterpret_cast<const int*>(tabd + ax.o_zrun);           // zero runs: (first row, length) pairs
+  // 16-byte zero stores need 16-byte aligned rows and an even batch (a pair of scenarios is in or out together)
+  const bool zvec = dense && (reinterpret_cast<uintptr_t>(a.ze1) & 15u) == 0 && (a.ld & 1) == 0 && (a.S & 1) == 0;
   const unsigned long long* hint = reinterpret_cast<const unsigned long long*>(a.warm);
   unsigned long long* hint_w = reinterpret_cast<unsigned long long*>(a.warm);
   const unsigned half_mask = lane < 16 ? 0x0000ffffu : 0xffff0000u;
-  const double* omc = &sm.om[0][tid];                                       // this thread's column of om
+  const double* omc = &om[0][tid];                                          // this thread's column of om
 
   const int64_t nblk = (a.S + TPB - 1) / TPB;
-  for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+  for (int64_t blk = blockIdx.x; blk < nblk; blk += (NSLOT == 0 ? (int64_t)gridDim.x : nblk)) {
     const int64_t s = blk * TPB + tid;
     const bool live = s < a.S;
     const int64_t sc = live ? s : a.S - 1;                 // dead lanes shadow the last scenario and write nothing
@@ -122,15 +146,42 @@ __global__ void __launch_bounds__(TPB, 512 / TPB) fast_step_kernel(const QpProg<
         for (int c = zs[2 * r + 1]; c > 0; --c, ptr += LD) __stcs(ptr, 0.0);
       }
     };
+    // Vector form (16-byte aligned rows): a thread keeps a 16-byte chunk (two scenarios) of the block's [entries x TPB
+    // scenarios] slab and walks down the zero runs -- the first half of the CTA the runs [0, zrun_split), the second half the
+    // rest -- so a warp instruction stores 512 contiguous bytes and the loop body is a store and a pointer increment.  The
+    // zero entries are disjoint from the table's entries: no ordering is needed, and every warp still does its share when
+    // it likes (before or behind its solve).
+    auto zero_rows_vec = [&]() {
+      constexpr int CPR = TPB / 2;                                   // 16-byte chunks per entry row of the slab
+      const int chunk = tid % CPR, half = tid / CPR;
+      const int64_t sv = blk * TPB + 2 * chunk;
+      if (sv < a.S) {
+        double* base = a.ze1 + sv;
+        const int r1 = half == 0 ? ax.zrun_split : ax.n_zrun;
+#pragma unroll 1
+        for (int r = half == 0 ? 0 : ax.zrun_split; r < r1; ++r) {
+          double* ptr = base + (int64_t)zs[2 * r] * LD;
+#pragma unroll 4
+          for (int c = zs[2 * r + 1]; c > 0; --c, ptr += LD) __stcs(reinterpret_cast<double2*>(ptr), make_double2(0.0, 0.0));
+        }
+      }
+    };
     const bool zero_first = dense && (((tid >> 5) + (int)blk) & 1);
-    if (zero_first && live) zero_runs();
+    if (zero_first) {
+      if (zvec) zero_rows_vec();
+      else if (live) zero_runs();
+    }
 
     eval_atoms<BK>(pg, w);
     double q[NZ];
     eval_q<BK>(pg, w, q);
     bool param_ok = true;
+    {
+      int bad_rows = 0;                                     // (four rows per trip: eight independent fma chains)
 #pragma unroll 1
-    for (int i = 0; i < pg.nchk; ++i) param_ok = param_ok && !param_row_violated<BK>(pg, i, w);
+      for (int i = 0; i < pg.nchk; i += 4) bad_rows |= param_rows_violated<BK, 4>(pg, i, w) ? 1 : 0;
+      param_ok = bad_rows == 0;
+    }
     const double c0 = cost_const<BK>(pg, w);
 
     bool valid = true;
@@ -166,6 +217,7 @@ __global__ void __launch_bounds__(TPB, 512 / TPB) fast_step_kernel(const QpProg<
     }
     const bool emit = live && !deferred;
     const bool good = status == TZ_STATUS_OK;
+    if (dense && zvec && !zero_first) zero_rows_vec();      // (the whole warp: its share covers other lanes' scenarios)
     double nrm2 = 0.0, cost = NAN;
     if (emit) {
       // ---- hints: rows [0, G) the active set for the next step, rows [G, 2G) the active set of the run's first step
@@ -191,14 +243,19 @@ __global__ void __launch_bounds__(TPB, 512 / TPB) fast_step_kernel(const QpProg<
       if (good) cost = fma(res.obj, pg.cinv, c0);
       else if (status == TZ_STATUS_INFEASIBLE) cost = INFINITY;      // cvxpy returns +inf for an infeasible Minimize (:374)
 #pragma unroll
-      for (int j = 0; j < NW; ++j) sm.om[j][tid] = omr[j];
-#pragma unroll 1
-      for (int r = 0; r < n; ++r) {
-        const double* row = sCZ + r * NW;
-        double acc = 0.0;
+      for (int j = 0; j < NW; ++j) om[j][tid] = omr[j];
+      {
+        double acc[HP];                                     // the n rows at once: n independent fma chains
 #pragma unroll
-        for (int j = 0; j < NW; ++j) acc = fma(row[j], omr[j], acc);
-        sm.om[BK::OM_C + r][tid] = acc;
+        for (int r = 0; r < HP; ++r) acc[r] = 0.0;
+#pragma unroll
+        for (int j = 0; j < NW; ++j)
+#pragma unroll
+          for (int r = 0; r < HP; ++r)
+            if (r < n) acc[r] = fma(sCZ[r * NW + j], omr[j], acc[r]);
+#pragma unroll
+        for (int r = 0; r < HP; ++r)
+          if (r < n) om[BK::OM_C + r][tid] = acc[r];
       }
       // (sm.om columns are thread-private: no barrier)
       // ---- Ze[1].Z at the optimum (examples/2.pulley_sim.py:96): the entries of the term table
@@ -212,7 +269,7 @@ __global__ void __launch_bounds__(TPB, 512 / TPB) fast_step_kernel(const QpProg<
             __stcs(ptr, e.x * omc[(int)(__double_as_longlong(e.y) & 0xffffffffll) * TPB]);
           }
         } else {
-          if (!zero_first) zero_runs();
+          if (!zero_first && !zvec) zero_runs();
 #pragma unroll 4
           for (int i = 0; i < ax.n_nz; ++i) {
             const double2 e = tt[i];
@@ -225,26 +282,28 @@ __global__ void __launch_bounds__(TPB, 512 / TPB) fast_step_kernel(const QpProg<
       double xb1[HP];
 #pragma unroll
       for (int i = 0; i < HP; ++i) xb1[i] = 0.0;
-      auto xb_row = [&](int i) {
-        const double* row = sXB + i * NW;
-        double acc = 0.0;
+      // block k of the trajectory (rows k n .. k n + n - 1 = xbar_k): its n rows at once, n independent fma chains
+      auto xb_block = [&](int k, double (&acc)[HP]) {
+        const double* blk_rows = sXB + k * n * NW;
 #pragma unroll
-        for (int j = 0; j < NW; ++j) acc = fma(row[j], omr[j], acc);
-        if (a.xbar_traj != nullptr) a.xbar_traj[(int64_t)i * LD + s] = acc;
-        return acc;
+        for (int r = 0; r < HP; ++r) acc[r] = 0.0;
+#pragma unroll
+        for (int j = 0; j < NW; ++j)
+#pragma unroll
+          for (int r = 0; r < HP; ++r)
+            if (r < n) acc[r] = fma(blk_rows[r * NW + j], omr[j], acc[r]);
+        if (a.xbar_traj != nullptr) {
+#pragma unroll
+          for (int r = 0; r < HP; ++r)
+            if (r < n) a.xbar_traj[(int64_t)(k * n + r) * LD + s] = acc[r];
+        }
       };
+      if (a.xbar_traj != nullptr || closed) xb_block(1, xb1);
       if (a.xbar_traj != nullptr) {
+        double tmp[HP];
+        xb_block(0, tmp);
 #pragma unroll 1
-        for (int i = 0; i < n; ++i) (void)xb_row(i);
-      }
-      if (a.xbar_traj != nullptr || closed) {
-#pragma unroll
-        for (int k = 0; k < HP; ++k)
-          if (k < n) xb1[k] = xb_row(n + k);
-      }
-      if (a.xbar_traj != nullptr) {
-#pragma unroll 1
-        for (int i = 2 * n; i < (ax.N + 1) * n; ++i) (void)xb_row(i);
+        for (int k = 2; k <= ax.N; ++k) xb_block(k, tmp);
       }
       if (a.v != nullptr)
         for (int j = 0; j < nv; ++j) a.v[(int64_t)j * LD + s] = omc[(BK::OM_V + j) * TPB];
@@ -323,17 +382,24 @@ __global__ void __launch_bounds__(TPB, 512 / TPB) fast_step_kernel(const QpProg<
   if (!staged) cp_async_wait<0>();
 }
 
-template <class BK, int TPB>
-int launch_fast_tpb(const TzProgram* p, const SolverParams& sp, const StepArgs& a, cudaStream_t st) {
-  const size_t smem = sizeof(FastSmem<BK, TPB>) + p->smem_tab;
+template <class BK>
+size_t fast_slot_bytes(const TzProgram* p) {
+  return ((sizeof(QpProg<BK>) + 15) & ~(size_t)15) + p->smem_tab;
+}
+
+template <class BK, int TPB, int NSLOT>
+int launch_fast_tpb(const TzProgram* p, const SolverParams& sp, const StepArgs& a, const SetEntry* entries, const int32_t* tile_prog,
+                    cudaStream_t st) {
+  const size_t slot = fast_slot_bytes<BK>(p);
+  const size_t smem = (NSLOT > 1 ? NSLOT : 1) * slot + sizeof(double) * BK::KOM * TPB;
   static std::atomic<unsigned long long> configured{0ull};
-  if (const int rc = ensure_dynamic_smem(fast_step_kernel<BK, TPB>, (int)(sizeof(FastSmem<BK, TPB>) + kMaxTabBytes), p->device,
-                                         configured))
-    return rc;
+  const size_t smem_max = (NSLOT > 1 ? NSLOT : 1) * (((sizeof(QpProg<BK>) + 15) & ~(size_t)15) + kMaxTabBytes) + sizeof(double) * BK::KOM * TPB;
+  if (const int rc = ensure_dynamic_smem(fast_step_kernel<BK, TPB, NSLOT>, (int)smem_max, p->device, configured)) return rc;
   const int64_t nblk = (a.S + TPB - 1) / TPB;
   const int64_t wave = (int64_t)p->num_sms * (512 / TPB);
-  const unsigned grid = (unsigned)(nblk < wave ? nblk : wave);
-  fast_step_kernel<BK, TPB><<<grid, TPB, smem, st>>>(reinterpret_cast<const QpProg<BK>*>(p->packed_dev), p->aux, sp, a);
+  const unsigned grid = (unsigned)(NSLOT == 0 ? (nblk < wave ? nblk : wave) : nblk);
+  fast_step_kernel<BK, TPB, NSLOT><<<grid, TPB, smem, st>>>(reinterpret_cast<const QpProg<BK>*>(p->packed_dev), p->aux, sp, a, entries,
+                                                            tile_prog, (int)slot);
   TZ_CUDA(cudaGetLastError());
   return TZ_OK;
 }
@@ -345,13 +411,24 @@ template <class BK>
 int launch_fast(const TzProgram* p, const SolverParams& sp, const StepArgs& a, cudaStream_t st) {
   if (const char* e = getenv("TZDDPC_FAST_TPB")) {      // tuning knob (read per launch, no state): force the CTA size
     const int t = atoi(e);
-    if (t == 128) return launch_fast_tpb<BK, 128>(p, sp, a, st);
-    if (t == 64) return launch_fast_tpb<BK, 64>(p, sp, a, st);
-    if (t == 32) return launch_fast_tpb<BK, 32>(p, sp, a, st);
+    if (t == 128) return launch_fast_tpb<BK, 128, 0>(p, sp, a, nullptr, nullptr, st);
+    if (t == 64) return launch_fast_tpb<BK, 64, 0>(p, sp, a, nullptr, nullptr, st);
+    if (t == 32) return launch_fast_tpb<BK, 32, 0>(p, sp, a, nullptr, nullptr, st);
   }
-  if (a.S >= (int64_t)p->num_sms * 128 * 2) return launch_fast_tpb<BK, 128>(p, sp, a, st);
-  if (a.S >= (int64_t)p->num_sms * 64 * 2) return launch_fast_tpb<BK, 64>(p, sp, a, st);
-  return launch_fast_tpb<BK, 32>(p, sp, a, st);
+  if (a.S >= (int64_t)p->num_sms * 128 * 2) return launch_fast_tpb<BK, 128, 0>(p, sp, a, nullptr, nullptr, st);
+  if (a.S >= (int64_t)p->num_sms * 64 * 2) return launch_fast_tpb<BK, 64, 0>(p, sp, a, nullptr, nullptr, st);
+  return launch_fast_tpb<BK, 32, 0>(p, sp, a, nullptr, nullptr, st);
+}
+
+// Program set: `block` = the largest of 128 / 64 / 32 that divides every program's first scenario (so that a CTA's block of
+// scenarios lies within one program), or 16: two program slots per one-warp CTA.
+template <class BK>
+int launch_fast_set(const TzProgram* p0, const SolverParams& sp, const StepArgs& a, const SetEntry* entries, const int32_t* tile_prog,
+                    int block, cudaStream_t st) {
+  if (block >= 128) return launch_fast_tpb<BK, 128, 1>(p0, sp, a, entries, tile_prog, st);
+  if (block >= 64) return launch_fast_tpb<BK, 64, 1>(p0, sp, a, entries, tile_prog, st);
+  if (block >= 32) return launch_fast_tpb<BK, 32, 1>(p0, sp, a, entries, tile_prog, st);
+  return launch_fast_tpb<BK, 32, 2>(p0, sp, a, entries, tile_prog, st);
 }
 
 }  // namespace tz

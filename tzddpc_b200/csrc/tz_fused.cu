@@ -22,12 +22,19 @@ namespace tz {
 template <class BK>
 int launch_fast(const TzProgram* p, const SolverParams& sp, const StepArgs& a, cudaStream_t st);
 extern template int launch_fast<B0>(const TzProgram*, const SolverParams&, const StepArgs&, cudaStream_t);
+template <class BK>
+int launch_fast_set(const TzProgram* p0, const SolverParams& sp, const StepArgs& a, const SetEntry* entries, const int32_t* tile_prog,
+                    int block, cudaStream_t st);
+extern template int launch_fast_set<B0>(const TzProgram*, const SolverParams&, const StepArgs&, const SetEntry*, const int32_t*, int,
+                                        cudaStream_t);
 extern template int launch_bucket<B1>(const TzProgram*, const SolverParams&, const StepArgs&, cudaStream_t);
 extern template int launch_bucket<B2>(const TzProgram*, const SolverParams&, const StepArgs&, cudaStream_t);
 extern template int launch_bucket<B3>(const TzProgram*, const SolverParams&, const StepArgs&, cudaStream_t);
 extern template int launch_bucket_set<B1>(const TzProgram*, const SetEntry*, int, int64_t, const SolverParams&, const StepArgs&, cudaStream_t);
 extern template int launch_bucket_set<B2>(const TzProgram*, const SetEntry*, int, int64_t, const SolverParams&, const StepArgs&, cudaStream_t);
 extern template int launch_bucket_set<B3>(const TzProgram*, const SetEntry*, int, int64_t, const SolverParams&, const StepArgs&, cudaStream_t);
+
+constexpr int64_t kHotMinBatch = 256;
 
 struct RowClasses { int n2 = 0, nu = 0, nl = 0; };
 
@@ -152,13 +159,17 @@ void pack(const TzProgramDesc& d, QpProg<BK>& g) {
       if (found < 0) { rep_of.push_back(s); members.emplace_back(); found = (int)rep_of.size() - 1; }
       members[found].push_back({s, sgn});
     }
-    int t = 0;
-    for (auto& mem : members)
+    int t = 0, gi = 0;
+    for (auto& mem : members) {
+      g.grp_first[gi++] = t;
       for (size_t k = 0; k < mem.size(); ++k, ++t) {
         g.grp_order[t] = mem[k].first;
         g.grp_new[t] = k == 0 ? 1 : 0;
         g.grp_sgn[t] = mem[k].second;
       }
+    }
+    g.ngrp = gi;
+    for (; gi < BK::NC + 4; ++gi) g.grp_first[gi] = t;
     for (; t < BK::NC; ++t) { g.grp_order[t] = 0; g.grp_new[t] = 0; g.grp_sgn[t] = 1.0; }
   }
   g.cinv = 1.0 / d.c;
@@ -171,26 +182,26 @@ void pack(const TzProgramDesc& d, QpProg<BK>& g) {
 
 using namespace tz;
 
+// host images of one program: the packed QpProg<bucket> and the run-time sized tables
+struct HostImage {
+  std::vector<unsigned char> packed, aux;
+};
+
 template <class BK>
-static int create_bucket(const TzProgramDesc& d, TzProgram* p, int id) {
+static int create_bucket(const TzProgramDesc& d, TzProgram* p, int id, HostImage& img) {
   p->bucket = id;
-  std::vector<unsigned char> packed(sizeof(QpProg<BK>));
-  pack<BK>(d, *reinterpret_cast<QpProg<BK>*>(packed.data()));
+  img.packed.assign(sizeof(QpProg<BK>), 0);
+  pack<BK>(d, *reinterpret_cast<QpProg<BK>*>(img.packed.data()));
   p->NZ = BK::NZ;
   p->NC = BK::NC;
   p->G = BK::G;
   p->NW = BK::NW; p->OM_V = BK::OM_V; p->OM_P = BK::OM_P; p->OM_C = BK::OM_C; p->HP = BK::NPAR / 2;
-  int dev = 0;
-  TZ_CUDA(cudaGetDevice(&dev));
-  p->device = dev;
-  TZ_CUDA(cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, dev));
-  TZ_CUDA(cudaMalloc(&p->packed_dev, sizeof(QpProg<BK>)));
-  TZ_CUDA(cudaMemcpy(p->packed_dev, packed.data(), sizeof(QpProg<BK>), cudaMemcpyHostToDevice));
   return TZ_OK;
 }
 
-extern "C" int tz_program_create(const TzProgramDesc* d, TzProgram** out) {
-  TZ_REQUIRE(d && out, "null argument");
+// Everything of tz_program_create that runs on the host: validation, bucket choice, packing, tables.  No CUDA call.
+static int build_program_host(const TzProgramDesc* d, TzProgram* p, HostImage& img) {
+  TZ_REQUIRE(d != nullptr, "null argument");
   TZ_REQUIRE(d->n >= 1 && d->n <= kMaxN && d->m >= 1 && d->m <= kMaxM, "dim_x must be 1..%d and dim_u 1..%d", kMaxN, kMaxM);
   TZ_REQUIRE(d->npar == 2 * d->n, "npar must be 2*dim_x");
   TZ_REQUIRE(d->nv == d->horizon * d->m && d->nv <= 16 && d->nz >= d->nv, "bad nv/nz");
@@ -200,15 +211,12 @@ extern "C" int tz_program_create(const TzProgramDesc* d, TzProgram** out) {
   for (int e = 0; e < d->n * (1 + d->g1); ++e)
     TZ_REQUIRE(d->ze1_ptr[e + 1] >= d->ze1_ptr[e], "ze1_ptr must be non-decreasing (entry %d)", e);
   TZ_REQUIRE(d->ze1_ptr[d->n * (1 + d->g1)] == d->nterms, "ze1_ptr[n(1+g1)] must equal nterms");
-  TzProgram* p = new (std::nothrow) TzProgram();
-  if (!p) return fail(TZ_ENOMEM, "out of host memory");
   int rc = TZ_ERANGE;
 #define TZ_TRY(BK, ID) \
-  if (rc == TZ_ERANGE && fits<BK>(*d)) rc = create_bucket<BK>(*d, p, ID);
+  if (rc == TZ_ERANGE && fits<BK>(*d)) rc = create_bucket<BK>(*d, p, ID, img);
   TZ_TRY(B0, 0) TZ_TRY(B1, 1) TZ_TRY(B2, 2) TZ_TRY(B3, 3)
 #undef TZ_TRY
   if (rc != TZ_OK) {
-    tz_program_destroy(p);              // (frees the device image when the upload failed half-way)
     if (rc == TZ_ERANGE) {
       const RowClasses c = classify(*d, nullptr);
       return fail(TZ_ERANGE, "program (nz=%d rows: %d two-sided, %d upper, %d lower; npar=%d general atoms=%d nchk=%d) "
@@ -234,7 +242,7 @@ extern "C" int tz_program_create(const TzProgramDesc* d, TzProgram** out) {
   for (int e = 0; e < nent; ++e) {
     const int t0 = d->ze1_ptr[e], t1 = d->ze1_ptr[e + 1];
     for (int t = t0; t < t1; ++t)
-      if (d->ze1_idx[t] < 0 || d->ze1_idx[t] >= nwc) { tz_program_destroy(p); return fail(TZ_EINVAL, "ze1_idx[%d] out of range", t); }
+      if (d->ze1_idx[t] < 0 || d->ze1_idx[t] >= nwc) return fail(TZ_EINVAL, "ze1_idx[%d] out of range", t);
     const int r = e / ld1, j = e % ld1;
     if (j == 0) {                        // centre column: its (possibly many) terms become om[OM_C + r]
       for (int t = t0; t < t1; ++t) CZ[(size_t)r * NW + omidx(d->ze1_idx[t])] += d->ze1_val[t];
@@ -242,7 +250,6 @@ extern "C" int tz_program_create(const TzProgramDesc* d, TzProgram** out) {
     } else if (t1 - t0 == 1) {
       ent.push_back(e); idx.push_back(omidx(d->ze1_idx[t0])); coef.push_back(d->ze1_val[t0]);
     } else if (t1 - t0 > 1) {
-      tz_program_destroy(p);
       return fail(TZ_EINVAL, "generator entry %d of Ze[1] has %d terms: only single-term generator entries are supported "
                   "(boxed M_K / M_Delta)", e, t1 - t0);
     }
@@ -262,13 +269,19 @@ extern "C" int tz_program_create(const TzProgramDesc* d, TzProgram** out) {
   // then the zero runs as int32 pairs
   const size_t o_tt = (nXB + nCZ + nK + nco + 1) & ~(size_t)1;
   const size_t o_zrun = o_tt + 2 * nco;
+  int zrun_split = 0;
+  {
+    int total = 0, acc = 0;
+    for (int v : zlen) total += v;
+    while (zrun_split < (int)zlen.size() && 2 * acc < total) acc += zlen[zrun_split++];
+  }
   const size_t ndbl = o_zrun + zstart.size(), nint = ent.size() + idx.size();
   const size_t smem_tab = (ndbl + (size_t)n * n + (size_t)n * d->m) * sizeof(double) + nint * sizeof(int32_t);
   if (smem_tab > kMaxTabBytes) {
-    tz_program_destroy(p);
     return fail(TZ_ERANGE, "program tables need %zu bytes of shared memory (limit %d)", smem_tab, kMaxTabBytes);
   }
-  std::vector<unsigned char> host(ndbl * sizeof(double) + nint * sizeof(int32_t) + 16);
+  std::vector<unsigned char>& host = img.aux;
+  host.assign(ndbl * sizeof(double) + nint * sizeof(int32_t) + 16, 0);
   double* hd = reinterpret_cast<double*>(host.data());
   std::memcpy(hd, XB.data(), nXB * sizeof(double));
   std::memcpy(hd + nXB, CZ.data(), nCZ * sizeof(double));
@@ -286,31 +299,131 @@ extern "C" int tz_program_create(const TzProgramDesc* d, TzProgram** out) {
     const int32_t pr[2] = {zstart[i], zlen[i]};
     std::memcpy(&hd[o_zrun + i], pr, sizeof(pr));
   }
-  cudaError_t err = cudaMalloc(&p->aux_dev, host.size());
-  if (err == cudaSuccess) err = cudaMemcpy(p->aux_dev, host.data(), host.size(), cudaMemcpyHostToDevice);
-  if (err != cudaSuccess) {
-    tz_program_destroy(p);
-    return fail(TZ_ECUDA, "aux upload: %s", cudaGetErrorString(err));
-  }
   Aux& ax = p->aux;
-  ax.tab = reinterpret_cast<const double*>(p->aux_dev);
+  ax.tab = nullptr;                      // (set when the tables are uploaded)
   ax.n_dbl = (int)ndbl; ax.n_int = (int)nint;
   ax.o_XB = 0; ax.o_CZ = (int)nXB; ax.o_K = (int)(nXB + nCZ); ax.o_coef = (int)(nXB + nCZ + nK);
   ax.o_ent = 0; ax.o_idx = (int)ent.size();
   ax.o_tt = (int)o_tt; ax.o_zrun = (int)o_zrun; ax.n_zrun = (int)zstart.size();
+  ax.zrun_split = zrun_split;
   ax.n_nz = (int)ent.size();
   p->tube_ent = ent;
   ax.n = n; ax.m = d->m; ax.N = d->horizon; ax.nv = d->nv; ax.g1 = d->g1;
   p->smem_tab = (smem_tab + 15) & ~(size_t)15;
+  return TZ_OK;
+}
+
+static int device_info(TzProgram* p) {
+  int dev = 0;
+  TZ_CUDA(cudaGetDevice(&dev));
+  p->device = dev;
+  TZ_CUDA(cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, dev));
+  return TZ_OK;
+}
+
+extern "C" int tz_program_create(const TzProgramDesc* d, TzProgram** out) {
+  TZ_REQUIRE(d && out, "null argument");
+  TzProgram* p = new (std::nothrow) TzProgram();
+  if (!p) return fail(TZ_ENOMEM, "out of host memory");
+  HostImage img;
+  int rc = build_program_host(d, p, img);
+  if (rc == TZ_OK) rc = device_info(p);
+  if (rc != TZ_OK) {
+    delete p;
+    return rc;
+  }
+  cudaError_t err = cudaMalloc(&p->packed_dev, img.packed.size());
+  if (err == cudaSuccess) err = cudaMemcpy(p->packed_dev, img.packed.data(), img.packed.size(), cudaMemcpyHostToDevice);
+  if (err == cudaSuccess) err = cudaMalloc(&p->aux_dev, img.aux.size());
+  if (err == cudaSuccess) err = cudaMemcpy(p->aux_dev, img.aux.data(), img.aux.size(), cudaMemcpyHostToDevice);
+  if (err != cudaSuccess) {
+    tz_program_destroy(p);              // (frees whatever was allocated before the failure)
+    return fail(TZ_ECUDA, "program upload: %s", cudaGetErrorString(err));
+  }
+  p->aux.tab = reinterpret_cast<const double*>(p->aux_dev);
   *out = p;
   return TZ_OK;
 }
 
 extern "C" void tz_program_destroy(TzProgram* p) {
   if (!p) return;
-  if (p->packed_dev) cudaFree(p->packed_dev);
-  if (p->aux_dev) cudaFree(p->aux_dev);
+  if (p->owns_device) {
+    if (p->packed_dev) cudaFree(p->packed_dev);
+    if (p->aux_dev) cudaFree(p->aux_dev);
+  }
   delete p;
+}
+
+// ---- D programs of one structure created at once (the data-set axis: one program per data set): packed on the host,
+// ONE device allocation and ONE copy for all images, one for all tables
+struct TzProgramBatch {
+  std::vector<TzProgram*> progs;          // views into the two allocations below (owns_device = false)
+  void* packed_all = nullptr;
+  void* aux_all = nullptr;
+};
+
+extern "C" void tz_program_batch_destroy(TzProgramBatch* b) {
+  if (!b) return;
+  for (TzProgram* p : b->progs) delete p;
+  if (b->packed_all) cudaFree(b->packed_all);
+  if (b->aux_all) cudaFree(b->aux_all);
+  delete b;
+}
+
+extern "C" int tz_program_create_batch(const TzProgramDesc* descs, int32_t D, TzProgramBatch** out) {
+  TZ_REQUIRE(descs && out && D >= 1, "null argument / empty batch");
+  TzProgramBatch* b = new (std::nothrow) TzProgramBatch();
+  if (!b) return fail(TZ_ENOMEM, "out of host memory");
+  std::vector<unsigned char> packed_h, aux_h;
+  size_t pstride = 0, astride = 0;
+  int rc = TZ_OK;
+  for (int d = 0; d < D && rc == TZ_OK; ++d) {
+    TzProgram* p = new (std::nothrow) TzProgram();
+    if (!p) { rc = fail(TZ_ENOMEM, "out of host memory"); break; }
+    p->owns_device = false;
+    b->progs.push_back(p);
+    HostImage img;
+    rc = build_program_host(&descs[d], p, img);
+    if (rc != TZ_OK) break;
+    if (d == 0) {
+      pstride = (img.packed.size() + 255) & ~(size_t)255;
+      astride = (img.aux.size() + 255) & ~(size_t)255;
+      packed_h.assign(pstride * (size_t)D, 0);
+      aux_h.assign(astride * (size_t)D, 0);
+    }
+    const TzProgram* p0 = b->progs[0];
+    if (p->bucket != p0->bucket || img.packed.size() > pstride || img.aux.size() > astride || p->smem_tab != p0->smem_tab) {
+      rc = fail(TZ_EINVAL, "program %d of the batch does not have the structure of program 0", d);
+      break;
+    }
+    std::memcpy(packed_h.data() + pstride * (size_t)d, img.packed.data(), img.packed.size());
+    std::memcpy(aux_h.data() + astride * (size_t)d, img.aux.data(), img.aux.size());
+  }
+  if (rc == TZ_OK) {
+    cudaError_t err = cudaMalloc(&b->packed_all, packed_h.size());
+    if (err == cudaSuccess) err = cudaMemcpy(b->packed_all, packed_h.data(), packed_h.size(), cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) err = cudaMalloc(&b->aux_all, aux_h.size());
+    if (err == cudaSuccess) err = cudaMemcpy(b->aux_all, aux_h.data(), aux_h.size(), cudaMemcpyHostToDevice);
+    if (err != cudaSuccess) rc = fail(TZ_ECUDA, "program batch upload: %s", cudaGetErrorString(err));
+  }
+  for (int d = 0; d < D && rc == TZ_OK; ++d) {
+    TzProgram* p = b->progs[d];
+    rc = device_info(p);
+    p->packed_dev = static_cast<unsigned char*>(b->packed_all) + pstride * (size_t)d;
+    p->aux_dev = static_cast<unsigned char*>(b->aux_all) + astride * (size_t)d;
+    p->aux.tab = reinterpret_cast<const double*>(p->aux_dev);
+  }
+  if (rc != TZ_OK) {
+    tz_program_batch_destroy(b);
+    return rc;
+  }
+  *out = b;
+  return TZ_OK;
+}
+
+extern "C" const TzProgram* tz_program_batch_get(const TzProgramBatch* b, int32_t d) {
+  if (!b || d < 0 || d >= (int32_t)b->progs.size()) return nullptr;
+  return b->progs[d];
 }
 
 extern "C" int tz_program_bucket(const TzProgram* p, char* buf, size_t cap) {
@@ -377,7 +490,8 @@ static int launch(const TzProgram* p, const TzSolverOpts* o, const StepArgs& a_i
   TZ_REQUIRE(sp.max_iter >= 1 && sp.rho > 0 && sp.rho_act > 0 && sp.rho_inact > 0 && sp.alpha > 0 && sp.alpha < 2,
              "bad solver options");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (p->bucket == 0 && sp.hot && sp.warm == 2 && a.warm != nullptr && a.q_in == nullptr) {
+  // (batches below kHotMinBatch scenarios stay on the ADMM kernel: one launch instead of two -- batch-1 latency)
+  if (p->bucket == 0 && sp.hot && sp.warm == 2 && a.warm != nullptr && a.q_in == nullptr && a.S >= kHotMinBatch) {
     // hint mode of the two-variable programs: fast_step_kernel (one thread per scenario, closed-form certificate) decides
     // every scenario whose hint still holds; the 16-scenario tiles it defers are listed in the warm-start scratch (rows
     // 2G: counters, 2G + 1: list) and solved by step_kernel right behind it
@@ -437,6 +551,8 @@ struct TzProgramSet {
   std::vector<const TzProgram*> progs;
   std::vector<int64_t> begin;          // nprog + 1
   tz::SetEntry* entries_dev = nullptr;
+  int32_t* tile_prog_dev = nullptr;    // program of every global 16-scenario tile (the hot path: fast_step_kernel over a set)
+  int block = 16;                      // largest of 128 / 64 / 32 / 16 that divides every program's first scenario
   int64_t max_scen = 0, total_tiles = 0;
 };
 
@@ -455,7 +571,7 @@ extern "C" int tz_program_set_create(const TzProgram* const* progs, int32_t npro
     // horizon, cost and constraint structure) built from different data
     TZ_REQUIRE(p->bucket == p0->bucket && p->smem_tab == p0->smem_tab && a.n_dbl == b.n_dbl && a.n_int == b.n_int &&
                a.o_XB == b.o_XB && a.o_CZ == b.o_CZ && a.o_K == b.o_K && a.o_coef == b.o_coef && a.o_ent == b.o_ent &&
-               a.o_idx == b.o_idx && a.o_tt == b.o_tt && a.o_zrun == b.o_zrun && a.n_zrun == b.n_zrun && a.n_nz == b.n_nz && a.n == b.n && a.m == b.m && a.N == b.N && a.nv == b.nv && a.g1 == b.g1,
+               a.o_idx == b.o_idx && a.o_tt == b.o_tt && a.o_zrun == b.o_zrun && a.n_zrun == b.n_zrun && a.zrun_split == b.zrun_split && a.n_nz == b.n_nz && a.n == b.n && a.m == b.m && a.N == b.N && a.nv == b.nv && a.g1 == b.g1,
                "program %d does not have the structure of program 0 (bucket / table sizes differ)", j);
     TZ_REQUIRE(p->tube_ent == p0->tube_ent, "program %d: Ze[1] has a different sparsity pattern than program 0", j);
     const int64_t cnt = begin[j + 1] - begin[j];
@@ -472,10 +588,22 @@ extern "C" int tz_program_set_create(const TzProgram* const* progs, int32_t npro
   s->begin.assign(begin, begin + nprog + 1);
   s->max_scen = mx;
   s->total_tiles = tiles;
+  // tile -> program (programs start on whole tiles; an empty program owns no tile)
+  std::vector<int32_t> tile_prog((size_t)((begin[nprog] + TZ_SPO_MIN - 1) / TZ_SPO_MIN) + 1, nprog - 1);
+  s->block = 128;
+  for (int j = 0; j < nprog; ++j) {
+    for (int64_t t = begin[j] / TZ_SPO_MIN; t < (begin[j + 1] + TZ_SPO_MIN - 1) / TZ_SPO_MIN; ++t) tile_prog[(size_t)t] = j;
+    if (begin[j + 1] > begin[j])
+      while (s->block > 16 && begin[j] % s->block != 0) s->block /= 2;
+  }
   cudaError_t err = cudaMalloc(&s->entries_dev, ent.size() * sizeof(tz::SetEntry));
   if (err == cudaSuccess) err = cudaMemcpy(s->entries_dev, ent.data(), ent.size() * sizeof(tz::SetEntry), cudaMemcpyHostToDevice);
+  if (err == cudaSuccess) err = cudaMalloc(&s->tile_prog_dev, tile_prog.size() * sizeof(int32_t));
+  if (err == cudaSuccess)
+    err = cudaMemcpy(s->tile_prog_dev, tile_prog.data(), tile_prog.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
   if (err != cudaSuccess) {
     if (s->entries_dev) cudaFree(s->entries_dev);
+    if (s->tile_prog_dev) cudaFree(s->tile_prog_dev);
     delete s;
     return fail(TZ_ECUDA, "program set upload: %s", cudaGetErrorString(err));
   }
@@ -486,6 +614,7 @@ extern "C" int tz_program_set_create(const TzProgram* const* progs, int32_t npro
 extern "C" void tz_program_set_destroy(TzProgramSet* s) {
   if (!s) return;
   if (s->entries_dev) cudaFree(s->entries_dev);
+  if (s->tile_prog_dev) cudaFree(s->tile_prog_dev);
   delete s;
 }
 
@@ -513,6 +642,22 @@ static int launch_set(const TzProgramSet* s, const TzSolverOpts* o, const StepAr
   const int np = (int)s->progs.size();
   if (np == 1) return launch(p0, o, a_in, stream);       // one program: exactly step_kernel (tiles strided over the grid)
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  {
+    int cur = -1;
+    TZ_CUDA(cudaGetDevice(&cur));
+    TZ_REQUIRE(cur == p0->device, "the program set was created on CUDA device %d, the current device is %d", p0->device, cur);
+  }
+  if (p0->bucket == 0 && sp.hot && sp.warm == 2 && a.warm != nullptr && a.q_in == nullptr && a.S >= kHotMinBatch) {
+    // the hot path over a set: fast_step_kernel looks the program of every 16-scenario tile up, the tiles it defers are
+    // solved by step_kernel_set_list (same scratch layout as the single-program path)
+    a.defer = reinterpret_cast<int32_t*>(a.warm + (int64_t)(2 * B0::G) * a.ld);
+    a.defer_list = reinterpret_cast<int32_t*>(a.warm + (int64_t)(2 * B0::G + 1) * a.ld);
+    a.list_mode = 0;
+    const int rc = launch_fast_set<B0>(p0, sp, a, s->entries_dev, s->tile_prog_dev, s->block, st);
+    if (rc != TZ_OK) return rc;
+    a.list_mode = 1;
+    return launch_bucket_set_list<B0>(p0, s->entries_dev, s->tile_prog_dev, sp, a, st);
+  }
   switch (p0->bucket) {
     case 0: return launch_bucket_set<B0>(p0, s->entries_dev, np, s->total_tiles, sp, a, st);
     case 1: return launch_bucket_set<B1>(p0, s->entries_dev, np, s->total_tiles, sp, a, st);

@@ -70,4 +70,32 @@ __device__ __forceinline__ bool param_row_violated(const QpProg<BK>& pg, int i, 
   return r + r1 > pg.chk_tol[i];
 }
 
+// NR parameter-only rows at once (rows beyond nchk are clamped to the last one): 2 NR fma chains in flight
+template <class BK, int NR>
+__device__ __forceinline__ bool param_rows_violated(const QpProg<BK>& pg, int i0, const double (&w)[2 * BK::NCOL2]) {
+  const double2* Rc[NR];
+  double r[NR], r1[NR];
+  int rows[NR];
+#pragma unroll
+  for (int q = 0; q < NR; ++q) {
+    rows[q] = i0 + q < pg.nchk ? i0 + q : pg.nchk - 1;
+    Rc[q] = reinterpret_cast<const double2*>(&pg.Rchk[rows[q]][0]);
+    r[q] = 0.0;
+    r1[q] = 0.0;
+  }
+#pragma unroll
+  for (int j = 0; j < BK::NCOL2; ++j) {
+#pragma unroll
+    for (int q = 0; q < NR; ++q) {
+      const double2 c2 = Rc[q][j];
+      r[q] = fma(c2.x, w[2 * j], r[q]);
+      r1[q] = fma(c2.y, w[2 * j + 1], r1[q]);
+    }
+  }
+  bool bad = false;
+#pragma unroll
+  for (int q = 0; q < NR; ++q) bad = bad || (r[q] + r1[q] > pg.chk_tol[rows[q]]);
+  return bad;
+}
+
 }  // namespace tz

@@ -32,6 +32,7 @@ struct Aux {
   int o_ent, o_idx;                // offsets (int32, from the start of the int part)
   int o_tt;                        // (doubles, even) term table of fast_step_kernel: n_nz pairs (coef, bits of idx | ent << 32)
   int o_zrun, n_zrun;              // (doubles) zero runs of the dense Ze[1].Z between its non-zero entries: int32 pairs (first row, length)
+  int zrun_split;                  // runs [0, zrun_split) hold about half of the zero entries (the two halves of a CTA share the zero-fill)
   int n_nz;                        // entries of Ze[1].Z that are not structurally zero (centre column included)
   int n, m, N, nv, g1;
 };
@@ -796,6 +797,40 @@ __global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel_set(const SetEn
   }
 }
 
+// The tiles fast_step_kernel deferred, for a program set: listed tile t (a global 16-scenario tile) belongs to program
+// tile_prog[t]; a CTA takes one listed tile at a time (its first warp solves it), re-staging the program image when the
+// program changes.  Every CTA takes an exit ticket and the last one clears the list, as step_kernel does.
+template <class BK>
+__global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel_set_list(const SetEntry* __restrict__ entries,
+                                                                         const int32_t* __restrict__ tile_prog, const Aux ax0,
+                                                                         const SolverParams sp, const StepArgs a0) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int64_t max_tiles = (a0.S + BK::SPO - 1) / BK::SPO;
+  const int64_t cnt = *reinterpret_cast<volatile const int32_t*>(a0.defer);
+  const int64_t ntl = cnt < 0 ? 0 : (cnt < max_tiles ? cnt : max_tiles);
+  int staged = -1;
+  for (int64_t i = blockIdx.x; i < ntl; i += gridDim.x) {
+    int64_t t = a0.defer_list[i];
+    t = t < 0 ? 0 : (t >= max_tiles ? max_tiles - 1 : t);
+    const int j = tile_prog[t];
+    const SetEntry en = entries[j];
+    Aux ax = ax0;
+    ax.tab = en.tab;
+    StepArgs a = shift_args(a0, en.begin, en.end - en.begin);
+    a.list_mode = 0;
+    const bool stage = staged != j;
+    if (stage && staged >= 0) __syncthreads();     // every warp is done with the previous program's image
+    staged = j;
+    const int64_t tl = t - en.begin / BK::SPO;     // the tile within its program (programs start on whole tiles)
+    run_program<BK>(smem_raw, reinterpret_cast<const QpProg<BK>*>(en.pg), ax, sp, a, tl, BK::WPB, tl + 1, (unsigned)(t % 1024), stage);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int tk = atomicAdd(a0.defer + 1, 1);
+    if (tk == (int)gridDim.x - 1) { a0.defer[0] = 0; a0.defer[1] = 0; }
+  }
+}
+
 // ---- compiled buckets: <NZ, N2, NU, NL, G, NPAR, NAG, NCHK, MINB> -------------------------------
 #ifndef TZ_B0_MINB
 #define TZ_B0_MINB 3
@@ -819,6 +854,7 @@ struct TzProgram {
   size_t smem_tab = 0;                   // bytes of the run-time tables staged behind Smem<bucket>
   int num_sms = 148;
   int device = -1;                       // the CUDA device the program image lives on: launches on another device are refused
+  bool owns_device = true;               // false: packed_dev / aux_dev are slices of a TzProgramBatch's allocations
 };
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute of a kernel.  The only process-wide state of the
@@ -846,7 +882,8 @@ int launch_bucket(const TzProgram* p, const SolverParams& sp, const StepArgs& a,
   // persistent grid: one wave of CTAs (MINB per SM); every warp loops over tiles of SPW scenarios
   const int64_t ntiles = (a.S + BK::SPO - 1) / BK::SPO;
   const int64_t need = (ntiles + BK::WPB - 1) / BK::WPB;
-  const int64_t wave = (int64_t)p->num_sms * BK::MINB;
+  // (list mode -- the tiles fast_step_kernel deferred, normally none or a handful: one CTA per SM keeps the empty pass short)
+  const int64_t wave = (int64_t)p->num_sms * (a.list_mode ? 1 : BK::MINB);
   const unsigned grid = (unsigned)(need < wave ? need : wave);
   step_kernel<BK><<<grid, BK::TPB, smem, st>>>(reinterpret_cast<const QpProg<BK>*>(p->packed_dev), p->aux, sp, a);
   TZ_CUDA(cudaGetLastError());
@@ -866,6 +903,19 @@ int launch_bucket_set(const TzProgram* p0, const SetEntry* entries_dev, int npro
   const int64_t need = (total_tiles + BK::WPB - 1) / BK::WPB;
   const unsigned grid = (unsigned)(need < wave ? need : wave);
   step_kernel_set<BK><<<grid, BK::TPB, smem, st>>>(entries_dev, nprog, total_tiles, p0->aux, sp, a);
+  TZ_CUDA(cudaGetLastError());
+  return TZ_OK;
+}
+
+template <class BK>
+int launch_bucket_set_list(const TzProgram* p0, const SetEntry* entries_dev, const int32_t* tile_prog, const SolverParams& sp,
+                           const StepArgs& a, cudaStream_t st) {
+  const size_t smem = sizeof(Smem<BK>) + p0->smem_tab;
+  static std::atomic<unsigned long long> configured{0ull};
+  if (const int rc = ensure_dynamic_smem(step_kernel_set_list<BK>, (int)(sizeof(Smem<BK>) + kMaxTabBytes), p0->device, configured)) return rc;
+  const int64_t ntiles = (a.S + BK::SPO - 1) / BK::SPO;
+  const unsigned grid = (unsigned)(ntiles < p0->num_sms ? ntiles : p0->num_sms);
+  step_kernel_set_list<BK><<<grid, BK::TPB, smem, st>>>(entries_dev, tile_prog, p0->aux, sp, a);
   TZ_CUDA(cudaGetLastError());
   return TZ_OK;
 }

@@ -774,169 +774,6 @@ __global__ void __launch_bounds__(kGirardThreads) tube_rollout_kernel(
   if (tid == 0) gfinal[s] = overflow ? -g_cur : g_cur;       // negative: gcap was too small at some step (truncated)
 }
 
-// ---------------------------------------------------------------------------------------
-// identify: one CTA per dataset.  D = [X0; U0] ((n+m) x (T-1)), P = pinv(D) = D'(DD')^{-1}
-// (Jacobi-scaled Gram matrix + Cholesky), AB = (X1 - c_W 1') P, and the order-1 boxes
-//   dAB = (sum_k |g_k|) (sum_j |P[j,:]|)',  dK = (sum_k |g_k|) (sum_j |P[j,:] [I;K]|)'
-// (closed form of tzddpc/tzddpc.py:81-83,119-128 for rank-one generators).
-// ---------------------------------------------------------------------------------------
-constexpr int kIdThreads = 128;
-constexpr int kMaxD = kMaxN + kMaxM;
-
-__global__ void __launch_bounds__(kIdThreads) identify_kernel(int T, int n, int m, int gW, const double* __restrict__ X,
-                                                              const double* __restrict__ U, const double* __restrict__ WZ,
-                                                              const double* __restrict__ K, double* __restrict__ AB,
-                                                              double* __restrict__ dAB, double* __restrict__ dK,
-                                                              double* __restrict__ Pinv, int32_t* __restrict__ status) {
-  extern __shared__ double smd[];                   // D: (T-1) x d  (row j = sample j), X1c: (T-1) x n
-  __shared__ double gram[kMaxD * kMaxD];            // then its scaled Cholesky factor
-  __shared__ double hmat[kMaxN * kMaxD];
-  __shared__ double scale[kMaxD];
-  __shared__ double part[kIdThreads / 32][kMaxD * kMaxD];
-  __shared__ double sP[kMaxD], sPK[kMaxN];
-  __shared__ int bad;
-  const int64_t s = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int d = n + m, Tm = T - 1;
-  double* Dm = smd;
-  double* X1 = smd + (size_t)Tm * d;
-  const double* Xs = X + s * (int64_t)T * n;
-  const double* Us = U + s * (int64_t)T * m;
-  for (int i = tid; i < Tm * n; i += kIdThreads) {
-    const int j = i / n, r = i - j * n;
-    Dm[(size_t)j * d + r] = Xs[i];                                   // Xm = x[:-1]   (tzddpc/tzddpc.py:60)
-    X1[i] = Xs[i + n] - WZ[(int64_t)r * (1 + gW)];                   // Xp = x[1:] minus c_W (:61, App. A.7)
-  }
-  for (int i = tid; i < Tm * m; i += kIdThreads) {
-    const int j = i / m, r = i - j * m;
-    Dm[(size_t)j * d + n + r] = Us[i];                               // Um = u[:-1]   (:62)
-  }
-  if (tid == 0) bad = 0;
-  __syncthreads();
-  // Gram matrix G = D D' and H = X1c D' : every thread accumulates a slice of samples
-  {
-    double acc[kMaxD * kMaxD];
-    for (int pass = 0; pass < 2; ++pass) {
-      const int rows = pass == 0 ? d : n;
-#pragma unroll
-      for (int i = 0; i < kMaxD * kMaxD; ++i) acc[i] = 0.0;
-      for (int j = tid; j < Tm; j += kIdThreads) {
-        const double* dj = Dm + (size_t)j * d;
-        const double* lj = pass == 0 ? dj : X1 + (size_t)j * n;
-        for (int a = 0; a < rows; ++a) {
-          const double la = lj[a];
-          for (int b = 0; b < d; ++b) acc[a * kMaxD + b] = fma(la, dj[b], acc[a * kMaxD + b]);
-        }
-      }
-      for (int a = 0; a < rows; ++a)
-        for (int b = 0; b < d; ++b) {
-          const double v = warp_sum(acc[a * kMaxD + b]);
-          if (lane == 0) part[wid][a * kMaxD + b] = v;
-        }
-      __syncthreads();
-      for (int i = tid; i < rows * d; i += kIdThreads) {
-        const int a = i / d, b = i - a * d;
-        double t = 0.0;
-        for (int w = 0; w < kIdThreads / 32; ++w) t += part[w][a * kMaxD + b];
-        if (pass == 0) gram[a * kMaxD + b] = t;
-        else hmat[a * kMaxD + b] = t;
-      }
-      __syncthreads();
-    }
-  }
-  // Jacobi scaling + Cholesky of the scaled Gram matrix (thread 0; d <= 12)
-  if (tid == 0) {
-    for (int a = 0; a < d; ++a) {
-      const double g = gram[a * kMaxD + a];
-      if (!(g > 0.0)) bad = 1;
-      scale[a] = g > 0.0 ? rsqrt(g) : 1.0;
-    }
-    for (int a = 0; a < d; ++a)
-      for (int b = 0; b < d; ++b) gram[a * kMaxD + b] *= scale[a] * scale[b];
-    for (int j = 0; j < d; ++j) {
-      double dj = gram[j * kMaxD + j];
-      for (int k = 0; k < j; ++k) dj -= gram[j * kMaxD + k] * gram[j * kMaxD + k];
-      if (!(dj > 1e-14)) { bad = 1; dj = 1.0; }
-      const double l = sqrt(dj);
-      gram[j * kMaxD + j] = l;
-      for (int i = j + 1; i < d; ++i) {
-        double v = gram[i * kMaxD + j];
-        for (int k = 0; k < j; ++k) v -= gram[i * kMaxD + k] * gram[j * kMaxD + k];
-        gram[i * kMaxD + j] = v / l;
-      }
-    }
-  }
-  for (int i = tid; i < kMaxD; i += kIdThreads) sP[i] = 0.0;
-  for (int i = tid; i < kMaxN; i += kIdThreads) sPK[i] = 0.0;
-  __syncthreads();
-  auto solve = [&](double* v) {     // v <- G^{-1} v  with G = S^{-1} L L' S^{-1}, S = diag(scale)
-    for (int a = 0; a < d; ++a) v[a] *= scale[a];
-    for (int i = 0; i < d; ++i) {
-      double t = v[i];
-      for (int k = 0; k < i; ++k) t -= gram[i * kMaxD + k] * v[k];
-      v[i] = t / gram[i * kMaxD + i];
-    }
-    for (int i = d - 1; i >= 0; --i) {
-      double t = v[i];
-      for (int k = i + 1; k < d; ++k) t -= gram[k * kMaxD + i] * v[k];
-      v[i] = t / gram[i * kMaxD + i];
-    }
-    for (int a = 0; a < d; ++a) v[a] *= scale[a];
-  };
-  // AB = H G^{-1}: row r of AB solves G ab_r = h_r
-  if (tid < n) {
-    double v[kMaxD];
-    for (int b = 0; b < d; ++b) v[b] = hmat[tid * kMaxD + b];
-    solve(v);
-    for (int b = 0; b < d; ++b) AB[s * (int64_t)n * d + tid * d + b] = v[b];
-  }
-  // rows of the pseudo-inverse and their absolute column sums
-  {
-    double aP[kMaxD], aPK[kMaxN];
-    for (int b = 0; b < kMaxD; ++b) aP[b] = 0.0;
-    for (int b = 0; b < kMaxN; ++b) aPK[b] = 0.0;
-    const double* Ks = K ? K + s * (int64_t)m * n : nullptr;
-    for (int j = tid; j < Tm; j += kIdThreads) {
-      double v[kMaxD];
-      for (int b = 0; b < d; ++b) v[b] = Dm[(size_t)j * d + b];
-      solve(v);
-      for (int b = 0; b < d; ++b) {
-        aP[b] += fabs(v[b]);
-        if (Pinv) Pinv[s * (int64_t)Tm * d + (int64_t)j * d + b] = v[b];
-      }
-      if (Ks)
-        for (int c = 0; c < n; ++c) {
-          double t = v[c];                                        // P[j,:] [I; K] column c
-          for (int k = 0; k < m; ++k) t = fma(v[n + k], Ks[k * n + c], t);
-          aPK[c] += fabs(t);
-        }
-    }
-    for (int b = 0; b < d; ++b) {
-      const double v = warp_sum(aP[b]);
-      if (lane == 0) atomicAdd(&sP[b], v);
-    }
-    for (int c = 0; c < n; ++c) {
-      const double v = warp_sum(aPK[c]);
-      if (lane == 0) atomicAdd(&sPK[c], v);
-    }
-  }
-  __syncthreads();
-  for (int i = tid; i < n * d; i += kIdThreads) {
-    const int r = i / d, c = i - r * d;
-    double gw = 0.0;
-    for (int k = 0; k < gW; ++k) gw += fabs(WZ[(int64_t)r * (1 + gW) + 1 + k]);
-    dAB[s * (int64_t)n * d + i] = gw * sP[c];
-  }
-  if (K && dK)
-    for (int i = tid; i < n * n; i += kIdThreads) {
-      const int r = i / n, c = i - r * n;
-      double gw = 0.0;
-      for (int k = 0; k < gW; ++k) gw += fabs(WZ[(int64_t)r * (1 + gW) + 1 + k]);
-      dK[s * (int64_t)n * n + i] = gw * sPK[c];
-    }
-  if (tid == 0 && status) status[s] = bad ? TZ_STATUS_NONFINITE : TZ_STATUS_OK;
-}
-
 }  // namespace tz
 
 using namespace tz;
@@ -1029,21 +866,6 @@ extern "C" int tz_tube_rollout(int64_t S, int32_t n, int32_t m, int32_t NK, int3
   tube_rollout_kernel<<<(unsigned)S, kGirardThreads, smem, (cudaStream_t)stream>>>(
       n, m, NK, ND, gW, g0, steps, order, metric, gcap, (int)gpre_cap, CK, GK, GD, per_scenario_model, Z0, XU, gW ? W : nullptr,
       Zfinal, gfinal, hull_lo, hull_hi);
-  TZ_CUDA(cudaGetLastError());
-  return TZ_OK;
-}
-
-extern "C" int tz_identify(int64_t S, int32_t T, int32_t n, int32_t m, int32_t gW, const double* X, const double* U,
-                           const double* WZ, const double* K, double* AB, double* dAB, double* dK, double* Pinv,
-                           int32_t* status, void* stream) {
-  TZ_REQUIRE(S >= 0 && T >= 2 && n >= 1 && n <= kMaxN && m >= 1 && m <= kMaxM && gW >= 0, "bad shape");
-  if (S == 0) return TZ_OK;
-  TZ_REQUIRE(X && U && WZ && AB && dAB, "null pointer");
-  TZ_REQUIRE(!dK || K, "dK needs K");
-  const size_t smem = (size_t)(T - 1) * (2 * n + m) * sizeof(double);
-  TZ_REQUIRE(smem <= 200 * 1024, "dataset too long for shared memory (T=%d)", T);
-  if (smem + 8192 > 48 * 1024) TZ_CUDA(cudaFuncSetAttribute(identify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  identify_kernel<<<(unsigned)S, kIdThreads, smem, (cudaStream_t)stream>>>(T, n, m, gW, X, U, WZ, K, AB, dAB, dK, Pinv, status);
   TZ_CUDA(cudaGetLastError());
   return TZ_OK;
 }

@@ -111,6 +111,31 @@ class Zonotope:
         pts = [self.center + self.generators[:, nz] @ np.asarray(s) for s in itertools.product((-1.0, 1.0), repeat=len(nz))]
         return np.unique(np.round(np.asarray(pts).reshape(-1, self.dimension), 14), axis=0)
 
+    def polygon_vertices(self) -> np.ndarray:
+        """Boundary of a 2-D zonotope, counter-clockwise, as a (k, 2) array: the generators, flipped into the upper half
+        plane and sorted by angle, are walked once forth and once back (O(g log g); no vertex enumeration).  Plotting
+        helper of examples/1.double_integrator_sim.py:170 (`Z.reduce(min(3, Z.order)).polygon`); host side."""
+        assert self.dimension == 2, "polygon export is for 2-D zonotopes"
+        G = self.generators[:, np.any(self.generators != 0.0, axis=0)].T.copy()          # (g, 2)
+        if G.shape[0] == 0:
+            return self.center[None].copy()
+        flip = (G[:, 1] < 0) | ((G[:, 1] == 0) & (G[:, 0] < 0))
+        G[flip] *= -1.0
+        G = G[np.argsort(np.arctan2(G[:, 1], G[:, 0]), kind="stable")]
+        start = self.center - G.sum(axis=0)                                            # lowest vertex
+        up = start + np.cumsum(2.0 * G, axis=0)
+        down = up[-1] - np.cumsum(2.0 * G, axis=0)
+        return np.vstack([start[None], up, down[:-1]])
+
+    @property
+    def polygon(self):
+        """matplotlib patch of a 2-D zonotope, as pyzonotope's `Zonotope.polygon` (examples/1.double_integrator_sim.py:170)."""
+        try:
+            from matplotlib.patches import Polygon
+        except ImportError as exc:         # matplotlib is a plotting-only dependency of the examples
+            raise ImportError("Zonotope.polygon needs matplotlib; Zonotope.polygon_vertices() returns the boundary as an array") from exc
+        return Polygon(self.polygon_vertices(), closed=True)
+
     def __repr__(self) -> str:
         return f"Zonotope(dimension={self.dimension}, num_generators={self.num_generators})"
 
