@@ -586,6 +586,103 @@ def e2e_legs(args, tz, ops, torch, dev, cfg, prog, loop, K_steps, world, barrier
     return out
 
 
+def run_stress(args):
+    """BASELINE.json configs[4]: synthetic 5-dim system, long horizon, high zonotope order (stress test of the Girard
+    reduction), 262,144 scenarios sharded over the GPUs.  Not a reference workload (the reference never reduces Ze); the
+    generator spec is fixed here (seed 0).  Two measurements per order cap rho:
+      rollout_order*     tz_tube_rollout: product + Minkowski sum + Girard reduction + hull per step with the zonotope resident
+                         in shared memory (the fused path; rho <= 30 at n = 5);
+      standalone_order*  tz_reach_step / tz_girard_reduce / tz_interval_hull on blocks of the same size: algorithmic bytes (read
+                         + written once) over the CUDA-event time, as a fraction of the measured HBM peak.
+    `value` = scenario-steps/s of the fused rollout at rho = 20, all ranks."""
+    import torch
+    import torch.distributed as dist
+    from tzddpc_b200 import ops, shard    # noqa: F401  (registers torch.ops.tzddpc.*)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    total = args.scenarios if args.scenarios != 65536 else 262144
+    s0, s1 = shard.shard_bounds(total, rank, world)
+    S = min(s1 - s0, args.stress_cap) if args.stress_cap > 0 else s1 - s0
+    n, m, steps = 5, 1, 32
+    rng = np.random.default_rng(0)
+    dK = rng.uniform(0.001, 0.02, size=(n, n)); dD = rng.uniform(0.001, 0.02, size=(n, n + m))
+    GK = np.zeros((n * n, n, n)); GD = np.zeros((n * (n + m), n, n + m))
+    for r in range(n):
+        for c in range(n):
+            GK[r * n + c, r, c] = dK[r, c]
+        for c in range(n + m):
+            GD[r * (n + m) + c, r, c] = dD[r, c]
+    A = rng.normal(size=(n, n)); A *= 0.85 / np.abs(np.linalg.eigvals(A)).max()
+    W = np.hstack([np.zeros((n, 1)), 0.1 * np.ones((n, 1))])
+    f = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(dev)      # noqa: E731
+    peak, peak_src = measured_hbm_peak()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def ev(fn, reps):
+        fn()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        barrier()
+        return shard.max_over_ranks(a.elapsed_time(b) / reps, dev)
+
+    out = {}
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    for order in (10, 20, 30):
+        gcap = n * (order - 1) + n
+        Z0 = torch.zeros((S, n, 2), dtype=torch.float64, device=dev)
+        Z0[:, :, 0] = torch.rand((S, n), dtype=torch.float64, device=dev, generator=gen) - 0.5
+        XU = torch.rand((S, steps, n + m), dtype=torch.float64, device=dev, generator=gen) * 4 - 2
+        targs = (f(A), f(GK), f(GD), Z0, XU, f(W), float(order), 0, gcap)
+        ms = ev(lambda: torch.ops.tzddpc.tube_rollout(*targs), max(1, args.steps // 10))
+        gpre = 26 * gcap + 25 + 30 + 1
+        out[f"rollout_order{order}"] = {"ms": ms, "scenario_steps_per_s": world * S * steps / ms * 1e3, "pre_reduce_generators": gpre,
+                                        "equiv_unfused_GBps_per_gpu": S * steps * 8 * n * (2 * gpre + 2 * gcap) / ms / 1e6}
+        Sz = min(S, 8192)
+        Zin = torch.rand((Sz, n, 1 + gcap), dtype=torch.float64, device=dev, generator=gen) - 0.5
+        dA_, dGK_ = f(A), f(GK)
+        t_reach = ev(lambda: torch.ops.tzddpc.reach_step(dA_, dGK_, Zin, None), 5)
+        pre = torch.ops.tzddpc.reach_step(dA_, dGK_, Zin, None)
+        b_reach = 8 * n * Sz * ((1 + gcap) + pre.shape[2])
+        t_gir = ev(lambda: torch.ops.tzddpc.girard_reduce(pre, float(order), 0, gcap), 5)
+        b_gir = 8 * n * Sz * (pre.shape[2] + 1 + gcap)
+        t_hull = ev(lambda: torch.ops.tzddpc.interval_hull(pre), 5)
+        b_hull = 8 * n * Sz * pre.shape[2]
+        out[f"standalone_order{order}"] = {"frac_reach": b_reach / t_reach / 1e6 / peak, "frac_girard": b_gir / t_gir / 1e6 / peak,
+                                           "frac_hull": b_hull / t_hull / 1e6 / peak, "girard_GBps": b_gir / t_gir / 1e6,
+                                           "generators_in": int(pre.shape[2] - 1), "zonotopes_per_gpu": Sz}
+        del Z0, XU, Zin, pre
+    r20 = out["rollout_order20"]
+    line = {"metric": "tube-rollout scenario-steps/s (synthetic stress: Girard order cap 20, horizon 32)", "value": r20["scenario_steps_per_s"],
+            "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r20["ms"] / steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"stress: synthetic 5-dim system, horizon {steps}, Girard order cap 10 / 20 / 30, {world * S} scenarios over "
+                                   f"{world} GPU(s) (BASELINE.json configs[4]: 262,144 over 8)", "scenarios_this_rank": S,
+                       "parallelism": f"scenario-dp{world}"},
+            "gpu_launches": 3 * (1 + max(1, args.steps // 10)), "roofline": {"bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peak_src,
+                                                                            "achieved": out["standalone_order20"]["girard_GBps"],
+                                                                            "frac": out["standalone_order20"]["frac_girard"],
+                                                                            "kernel": "tz::girard_kernel", "traffic": None},
+            "stress": out}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -784,7 +881,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="fivedim", choices=["fivedim", "pulley", "double_integrator"])
+    ap.add_argument("--workload", default="fivedim", choices=["fivedim", "pulley", "double_integrator", "stress"])
+    ap.add_argument("--stress-cap", type=int, default=0, help="stress workload: cap on the scenarios per GPU (0 = the whole shard)")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="strong: --scenarios in total, sharded over the GPUs (BASELINE.json configs[3]); weak: --scenarios per GPU")
     ap.add_argument("--scenarios", type=int, default=65536)
@@ -813,7 +911,12 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    if args.impl == "reference":
+    if args.workload == "stress":
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "the stress configuration is not a reference workload (the reference never reduces Ze)"}))
+        else:
+            run_stress(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_gpu(args)

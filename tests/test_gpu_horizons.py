@@ -1,6 +1,7 @@
 """BASELINE.json configs[1]: the double-integrator complexity sweep at batch 1 -- `build_problem(N, ...)` for horizons other
 than 2 and `build_problem_simplified(k0, N, ...)` (examples/1.double_integrator_computation_complexity.py:48-122), solved on
-the GPU (kernel buckets B1 / B2 and, for the largest, B3) and compared with the oracle.  Only uniquely determined outputs
+the GPU (kernel buckets B1 / B2 / B3 and, beyond 12 variables -- `-m stzddpc -ho 10 -k0 1` has 31 -- the generic
+warp-per-scenario path of csrc/tz_big.cu) and compared with the oracle.  Only uniquely determined outputs
 are compared (quirk Q12): cost, xbar[1], v[0], status, and Ze[1].Z at equal v."""
 import numpy as np
 import pytest
@@ -11,7 +12,8 @@ from tzddpc_b200 import configs
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("horizon,k0", [(1, None), (3, None), (4, None), (5, None), (3, 1), (5, 1), (4, 2)])
+@pytest.mark.parametrize("horizon,k0", [(1, None), (3, None), (4, None), (5, None), (3, 1), (5, 1), (4, 2),
+                                        (6, 1), (8, 1), (10, 1), (8, 2), (10, 3)])
 def test_sweep_horizons_batch1(cuda_lib, horizon, k0):
     cfg = configs.sweep()
     u, x = common.dataset(cfg)
@@ -36,8 +38,11 @@ def test_sweep_horizons_batch1(cuda_lib, horizon, k0):
         assert v.shape == (horizon, cfg.m) and xbar.shape == (horizon + 1, cfg.n)
         assert common.cost_close(cost, r.cost, wmax), (cost, r.cost)
         if horizon >= 2 or k0 is not None:        # N = 1 of build_problem: the cost is xbar_0's alone (quirk Q7), v is not unique
-            np.testing.assert_allclose(xbar[1], r.xbar[1], rtol=1e-6, atol=1e-6)
-            np.testing.assert_allclose(v[0], r.v[0], rtol=1e-6, atol=1e-6)
+            # generic path (more than 12 variables): degenerate LP vertices whose active set the certificate cannot close
+            # leave by ADMM's residual test at eps = 1e-6, i.e. a few 1e-6 in the minimiser
+            tol = 1e-6 if t._program.compiled.nz <= 12 else 2e-5
+            np.testing.assert_allclose(xbar[1], r.xbar[1], rtol=tol, atol=tol)
+            np.testing.assert_allclose(v[0], r.v[0], rtol=tol, atol=tol)
         if horizon >= 2:
             Zo = o.evaluate_tube(xb, e, v.ravel(), 1)
             np.testing.assert_allclose(tube.Z.value, Zo, rtol=common.GEN_RTOL, atol=1e-12)
@@ -51,4 +56,4 @@ def test_program_too_large_is_reported(cuda_lib):
     u, x = common.dataset(cfg)
     o, K = common.make_oracle(cfg, u, x, horizon=2)
     with pytest.raises(RuntimeError, match="exceeds every compiled bucket"):
-        common.make_product(cfg, u, x, K, horizon=10, k0=1)
+        common.make_product(cfg, u, x, K, horizon=14, k0=3)          # 46 variables: beyond the 32 of the generic path

@@ -134,10 +134,39 @@ def test_identify_batched_datasets(T, name):
         z = common.oracle_zonotopes(cfg)
         o.build_zonotopes_theta(z, Ks[s])
         np.testing.assert_allclose(AB[s].cpu().numpy(), o.Mdata.center, rtol=1e-9, atol=1e-11)
-        np.testing.assert_allclose(dAB[s].cpu().numpy(), np.abs(o.Mdelta.generators).sum(0), rtol=1e-8, atol=1e-13)
-        np.testing.assert_allclose(dK[s].cpu().numpy(), np.abs(o.MdataK.generators).sum(0), rtol=1e-8, atol=1e-13)
+        np.testing.assert_allclose(dAB[s].cpu().numpy(), np.abs(o.Mdelta.generators).sum(0), rtol=common.GEN_RTOL, atol=1e-13)
+        np.testing.assert_allclose(dK[s].cpu().numpy(), np.abs(o.MdataK.generators).sum(0), rtol=common.GEN_RTOL, atol=1e-13)
         D = np.vstack([X[s, :-1].T, U[s, :-1].T])
-        np.testing.assert_allclose(Pinv[s].cpu().numpy(), np.linalg.pinv(D), rtol=1e-7, atol=1e-11)
+        Pref = np.linalg.pinv(D)
+        np.testing.assert_allclose(Pinv[s].cpu().numpy(), Pref, rtol=common.GEN_RTOL, atol=common.GEN_RTOL * np.abs(Pref).max())
+
+
+@pytest.mark.parametrize("scale", [1e-3, 1e-5])
+def test_identify_ill_conditioned_data(T, scale):
+    """cond([X0; U0]) up to ~1e6 (one state channel recorded in other units): the Householder route keeps the error at
+    cond * eps where normal equations lose cond^2 * eps (round 1: 1e-8 .. 1e-7 already on the well-conditioned examples)."""
+    cfg = configs.fivedim()
+    rng = np.random.default_rng(5)
+    U, X = configs.generate_dataset(cfg, rng)
+    X = X.copy()
+    X[:, 0] *= scale
+    D = np.vstack([X[:-1].T, U[:-1].T])
+    cond = np.linalg.cond(D)
+    assert cond > 0.05 / scale
+    WZ = np.hstack([cfg.W[0][:, None], cfg.W[1]])
+    Ks = rng.normal(size=(1, cfg.m, cfg.n)) * 0.3
+    AB, dAB, dK, Pinv, status = T.ops.tzddpc.identify(_gpu(T, X[None]), _gpu(T, U[None]), _gpu(T, WZ), _gpu(T, Ks), True)
+    assert int(status[0].item()) == 0
+    Pref = np.linalg.pinv(D)
+    tol = max(common.GEN_RTOL, 50 * cond * np.finfo(np.float64).eps)
+    # column-wise: the column of the rescaled channel is 1/scale times larger than the others
+    err = np.abs(Pinv[0].cpu().numpy() - Pref).max(axis=0) / np.abs(Pref).max(axis=0)
+    assert err.max() <= tol, (err, tol, cond)
+    ABref = (X[1:].T - cfg.W[0][:, None]) @ Pref
+    errAB = np.abs(AB[0].cpu().numpy() - ABref).max(axis=0) / np.abs(ABref).max(axis=0)
+    assert errAB.max() <= tol, (errAB, tol, cond)
+    gw = np.abs(cfg.W[1]).sum(axis=1)
+    np.testing.assert_allclose(dAB[0].cpu().numpy(), np.outer(gw, np.abs(Pref).sum(axis=0)), rtol=tol)
 
 
 def test_identify_flags_rank_deficient_data(T):
@@ -157,8 +186,8 @@ def test_solve_matches_committed_golden(T, name):
     fx = np.load(os.path.join(GOLD, f"oracle_{name}.npz"))
     t = common.make_product(cfg, fx["u_data"], fx["x_data"], fx["K"])
     np.testing.assert_allclose(t.Mdata.center, fx["AB"], rtol=1e-9, atol=1e-12)
-    np.testing.assert_allclose(t.Mdelta.generators, fx["GD"], rtol=1e-8, atol=1e-13)
-    np.testing.assert_allclose(t.MdataK.generators, fx["GK"], rtol=1e-8, atol=1e-13)
+    np.testing.assert_allclose(t.Mdelta.generators, fx["GD"], rtol=common.GEN_RTOL, atol=1e-13)
+    np.testing.assert_allclose(t.MdataK.generators, fx["GK"], rtol=common.GEN_RTOL, atol=1e-13)
     cost, v, xbar, tube, status = t.solve(fx["xbar0"], fx["e0"])
     Z = tube.Z.value
     wmax = t._program.compiled.wmax

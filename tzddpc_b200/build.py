@@ -21,7 +21,7 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 OUT_DIR = HERE / "lib"
 LIB = OUT_DIR / "libtzddpc.so"
-SOURCES = ["tz_abi.cu", "tz_fused.cu", "tz_fast.cu", "tz_bucket1.cu", "tz_bucket2.cu", "tz_bucket3.cu", "tz_zono.cu", "tz_identify.cu", "tz_rng.cu", "tz_gain.cu"]
+SOURCES = ["tz_abi.cu", "tz_fused.cu", "tz_fast.cu", "tz_bucket1.cu", "tz_bucket2.cu", "tz_bucket3.cu", "tz_big.cu", "tz_zono.cu", "tz_identify.cu", "tz_rng.cu", "tz_gain.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + os.environ.get("TZ_EXTRA_NVCC", "").split()
 

@@ -87,10 +87,15 @@ struct Cert2Result {
   int nact;         // active rows of the guess (diagnostics)
 };
 
+struct NoHook {
+  __device__ __forceinline__ void operator()() const {}
+};
+
 // hw[g] (g < G): the scenario's hint words without the flag bits; word g carries rows k*G + g at bits [3k, 3k+3).
-template <class BK>
+// hook(): called once per row group of the feasibility pass (fast_step_kernel slips a few of its zero stores in there).
+template <class BK, class Hook = NoHook>
 __device__ __forceinline__ Cert2Result certify2(const QpProg<BK>& pg, const double (&w)[2 * BK::NCOL2], const double (&q)[BK::NZ],
-                                                const unsigned long long (&hw)[BK::G]) {
+                                                const unsigned long long (&hw)[BK::G], Hook hook = Hook()) {
   static_assert(BK::NZ == 2, "the closed-form certificate is for two decision variables");
   constexpr int G = BK::G, NCL = BK::NCL, NC = BK::NC, NK = BK::NK;
   constexpr unsigned long long M0 = 0x1249249249249249ull & ((NCL >= 21) ? ~0ull : ((1ull << (3 * NCL)) - 1ull));
@@ -219,29 +224,18 @@ __device__ __forceinline__ Cert2Result certify2(const QpProg<BK>& pg, const doub
   // (upper) bound carry -inf (+inf), so one expression serves the three row classes.
   double viol = -INFINITY, scale = 1.0;
   {
-    constexpr int GB = 4;                                          // groups per trip: 8 fma chains in flight
-#pragma unroll 1
-    for (int g0 = 0; g0 < pg.ngrp; g0 += GB) {
-      int reps[GB];
-      double L[GB], A[GB];
-#pragma unroll
-      for (int q = 0; q < GB; ++q) {
-        const int t = pg.grp_first[g0 + q];                        // (groups beyond ngrp are empty: t == nc, clamped below)
-        reps[q] = pg.grp_order[t < pg.nc ? t : pg.nc - 1];
-      }
-      row_LAn<BK, GB>(pg, reps, w, L, A);
-#pragma unroll
-      for (int q = 0; q < GB; ++q) {
-        const int t1 = pg.grp_first[g0 + q + 1];
+    double L = 0.0, A = 0.0;
 #pragma unroll 2
-        for (int t = pg.grp_first[g0 + q]; t < t1; ++t) {          // (uniform bounds: the same program for the whole warp)
-          const int i = pg.grp_order[t];
-          const double r = pg.Rs[i] * fma(pg.grp_sgn[t], A[q], L[q]);   // == row_shift(pg, i, w): sgn = -1 negates A exactly
-          const double ax = fma(pg.A[i][1], x1, pg.A[i][0] * x0);
-          viol = dmax(viol, dmax((pg.l0[i] + r) - ax, ax - (pg.u0[i] + r)));
-          scale = dmax(scale, fabs(ax));
-        }
+    for (int t = 0; t < pg.nc; ++t) {
+      const int i = pg.grp_order[t];
+      if (pg.grp_new[t]) {                                          // (uniform branch: the same program for the whole warp)
+        row_LA<BK>(pg, i, w, L, A);
+        hook();
       }
+      const double r = pg.Rs[i] * fma(pg.grp_sgn[t], A, L);          // == row_shift(pg, i, w): sgn = -1 negates A exactly
+      const double ax = fma(pg.A[i][1], x1, pg.A[i][0] * x0);
+      viol = dmax(viol, dmax((pg.l0[i] + r) - ax, ax - (pg.u0[i] + r)));
+      scale = dmax(scale, fabs(ax));
     }
   }
   // ---- |.| rows: cost and the side of the kink the guess assumed

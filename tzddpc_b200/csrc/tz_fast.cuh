@@ -42,14 +42,21 @@ constexpr int kDeferTile = TZ_SPO_MIN;     // scenarios per deferred tile = outp
 // 16-scenario tiles look their program up in tile_prog.  NSLOT = 1: the set guarantees that a block lies within one
 // program; NSLOT = 2 (TPB = 32): the two half-warps of the warp may belong to two programs, each staged in its own slot --
 // a coefficient load then has two distinct addresses per warp instead of one.
-template <class BK, int TPB, int NSLOT>
-__global__ void __launch_bounds__(TPB, 512 / TPB) fast_step_kernel(const QpProg<BK>* __restrict__ gpg, const Aux ax,
-                                                                  const SolverParams sp, const StepArgs a,
-                                                                  const SetEntry* __restrict__ entries,
-                                                                  const int32_t* __restrict__ tile_prog, const int slot_bytes) {
+// ZW = 1: the CTA carries one extra warp (threads [TPB, TPB + 32)) that does nothing but store the structural zeros of the
+// block's dense Ze[1].Z slab, paced with nanosleep so that its stores trickle out while the TPB solve threads compute.
+// The solve warps are latency-bound (13.8 warps per SM at one thread per scenario, ~12 cycles per issued instruction:
+// profiles/r2_fast_v4_*), so every instruction taken off them shortens the step, and the zero warp rides on issue slots
+// that were idle.  Needs the 16-byte store form (the launcher checks alignment and an even batch).
+template <class BK, int TPB, int NSLOT, int ZW>
+__global__ void __launch_bounds__(TPB + 32 * ZW, ZW ? 4 : 512 / TPB)
+    fast_step_kernel(const QpProg<BK>* __restrict__ gpg, const Aux ax, const SolverParams sp, const StepArgs a,
+                     const SetEntry* __restrict__ entries, const int32_t* __restrict__ tile_prog, const int slot_bytes,
+                     const int zero_pace) {
   constexpr int NZ = BK::NZ, NPAR = BK::NPAR, HP = BK::NPAR / 2, NCOL = BK::NCOL, NW = BK::NW, G = BK::G;
   static_assert(kDeferTile == 16 && BK::SPO == 16, "deferred tiles are the 16-scenario output tiles of step_kernel");
   static_assert(NSLOT <= 1 || TPB == 32, "two program slots: one warp per CTA");
+  static_assert(ZW == 0 || (NSLOT <= 1 && TPB % 64 == 0), "zero warp: one program per CTA, whole 64-scenario chunks");
+  constexpr int NT = TPB + 32 * ZW;                         // threads of the CTA
   constexpr int QPB = (int)((sizeof(QpProg<BK>) + 15) & ~(size_t)15);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31;
@@ -65,12 +72,12 @@ __global__ void __launch_bounds__(TPB, 512 / TPB) fast_step_kernel(const QpProg<
     char* dst = reinterpret_cast<char*>(slot);
     double* td = reinterpret_cast<double*>(slot + QPB);
     constexpr int NCH = (int)(sizeof(QpProg<BK>) / 16);
-    for (int i = tid; i < NCH; i += TPB) cp_async16(dst + 16 * i, src + 16 * i);
+    for (int i = tid; i < NCH; i += NT) cp_async16(dst + 16 * i, src + 16 * i);
     if (tid == 0 && (sizeof(QpProg<BK>) % 16) != 0) cp_async8(dst + 16 * NCH, src + 16 * NCH);
-    for (int i = tid; i < ax.n_dbl; i += TPB) cp_async8(td + i, tab_src + i);
+    for (int i = tid; i < ax.n_dbl; i += NT) cp_async8(td + i, tab_src + i);
     if (closed) {
-      for (int i = tid; i < n * n; i += TPB) cp_async8(td + ax.n_dbl + i, a.A_true + i);
-      for (int i = tid; i < n * m; i += TPB) cp_async8(td + ax.n_dbl + n * n + i, a.B_true + i);
+      for (int i = tid; i < n * n; i += NT) cp_async8(td + ax.n_dbl + i, a.A_true + i);
+      for (int i = tid; i < n * m; i += NT) cp_async8(td + ax.n_dbl + n * n + i, a.B_true + i);
     }
   };
   unsigned char* my_slot = smem_raw;
@@ -103,12 +110,36 @@ __global__ void __launch_bounds__(TPB, 512 / TPB) fast_step_kernel(const QpProg<
   const int* zs = reinterpret_cast<const int*>(tabd + ax.o_zrun);           // zero runs: (first row, length) pairs
   // 16-byte zero stores need 16-byte aligned rows and an even batch (a pair of scenarios is in or out together)
   const bool zvec = dense && (reinterpret_cast<uintptr_t>(a.ze1) & 15u) == 0 && (a.ld & 1) == 0 && (a.S & 1) == 0;
+  const int64_t nblk = (a.S + TPB - 1) / TPB;
+  if constexpr (ZW > 0) {
+    if (tid >= TPB) {
+      // ---- the zero warp: lane l owns the 16-byte chunks (scenarios 2l, 2l + 1) + 64 h of every structurally zero row
+      cp_async_wait<0>();
+      __syncthreads();
+      const int zl = tid - TPB;
+      int cnt = 0;
+      for (int64_t blk = blockIdx.x; blk < nblk; blk += (NSLOT == 0 ? (int64_t)gridDim.x : nblk)) {
+        const int64_t sv0 = blk * TPB + 2 * zl;
+#pragma unroll 1
+        for (int r = 0; r < ax.n_zrun; ++r) {
+          double* ptr = a.ze1 + sv0 + (int64_t)zs[2 * r] * LD;
+#pragma unroll 2
+          for (int c = zs[2 * r + 1]; c > 0; --c, ptr += LD) {
+#pragma unroll
+            for (int h = 0; h < TPB / 64; ++h)
+              if (sv0 + 64 * h < a.S) __stcs(reinterpret_cast<double2*>(ptr + 64 * h), make_double2(0.0, 0.0));
+            if (zero_pace > 0 && (++cnt & 3) == 0) __nanosleep(zero_pace);
+          }
+        }
+      }
+      return;
+    }
+  }
   const unsigned long long* hint = reinterpret_cast<const unsigned long long*>(a.warm);
   unsigned long long* hint_w = reinterpret_cast<unsigned long long*>(a.warm);
   const unsigned half_mask = lane < 16 ? 0x0000ffffu : 0xffff0000u;
   const double* omc = &om[0][tid];                                          // this thread's column of om
 
-  const int64_t nblk = (a.S + TPB - 1) / TPB;
   for (int64_t blk = blockIdx.x; blk < nblk; blk += (NSLOT == 0 ? (int64_t)gridDim.x : nblk)) {
     const int64_t s = blk * TPB + tid;
     const bool live = s < a.S;
@@ -148,38 +179,51 @@ __global__ void __launch_bounds__(TPB, 512 / TPB) fast_step_kernel(const QpProg<
     };
     // Vector form (16-byte aligned rows): a thread keeps a 16-byte chunk (two scenarios) of the block's [entries x TPB
     // scenarios] slab and walks down the zero runs -- the first half of the CTA the runs [0, zrun_split), the second half the
-    // rest -- so a warp instruction stores 512 contiguous bytes and the loop body is a store and a pointer increment.  The
-    // zero entries are disjoint from the table's entries: no ordering is needed, and every warp still does its share when
-    // it likes (before or behind its solve).
-    auto zero_rows_vec = [&]() {
-      constexpr int CPR = TPB / 2;                                   // 16-byte chunks per entry row of the slab
-      const int chunk = tid % CPR, half = tid / CPR;
-      const int64_t sv = blk * TPB + 2 * chunk;
-      if (sv < a.S) {
-        double* base = a.ze1 + sv;
-        const int r1 = half == 0 ? ax.zrun_split : ax.n_zrun;
-#pragma unroll 1
-        for (int r = half == 0 ? 0 : ax.zrun_split; r < r1; ++r) {
-          double* ptr = base + (int64_t)zs[2 * r] * LD;
-#pragma unroll 4
-          for (int c = zs[2 * r + 1]; c > 0; --c, ptr += LD) __stcs(reinterpret_cast<double2*>(ptr), make_double2(0.0, 0.0));
+    // rest -- so a warp instruction stores 512 contiguous bytes.  The zero entries are disjoint from the table's entries, so
+    // no ordering is needed, and the stores are DRIPPED: a few at a time between the stages of the solve (`drip(k)` resumes
+    // where the previous call stopped).  Issued in one burst -- before or behind the solve -- a warp sits on the back-pressure
+    // of a saturated DRAM for ~20 us while its own arithmetic waits (profiles/r2_fast_v3_*): the step took solve + stores,
+    // 0.071 ms; spread over the solve the stores ride along.
+    constexpr int CPR = TPB / 2;                                     // 16-byte chunks per entry row of the slab
+    const int z_half = tid / CPR;
+    const int64_t z_sv = blk * TPB + 2 * (tid % CPR);
+    int z_run = z_half == 0 ? 0 : ax.zrun_split;                     // current run, rows left in it, next row's address
+    const int z_end = z_half == 0 ? ax.zrun_split : ax.n_zrun;
+    int z_left = 0;
+    double* z_ptr = a.ze1;
+    if (!(zvec && z_sv < a.S) || ZW > 0) z_run = z_end;
+    auto drip = [&](int budget) {
+      if constexpr (ZW > 0) return;                                  // (the zero warp stores them)
+      while (budget > 0) {
+        if (z_left == 0) {
+          if (z_run >= z_end) return;
+          z_ptr = a.ze1 + z_sv + (int64_t)zs[2 * z_run] * LD;
+          z_left = zs[2 * z_run + 1];
+          ++z_run;
         }
+        const int k = z_left < budget ? z_left : budget;
+#pragma unroll 4
+        for (int c = k; c > 0; --c, z_ptr += LD) __stcs(reinterpret_cast<double2*>(z_ptr), make_double2(0.0, 0.0));
+        z_left -= k;
+        budget -= k;
       }
     };
-    const bool zero_first = dense && (((tid >> 5) + (int)blk) & 1);
-    if (zero_first) {
-      if (zvec) zero_rows_vec();
-      else if (live) zero_runs();
-    }
+    const bool zero_first = ZW == 0 && dense && !zvec && (((tid >> 5) + (int)blk) & 1);
+    if (zero_first && live) zero_runs();
+    drip(24);
 
     eval_atoms<BK>(pg, w);
     double q[NZ];
     eval_q<BK>(pg, w, q);
+    drip(8);
     bool param_ok = true;
     {
-      int bad_rows = 0;                                     // (four rows per trip: eight independent fma chains)
+      int bad_rows = 0;                                     // (two rows per trip: four independent fma chains)
 #pragma unroll 1
-      for (int i = 0; i < pg.nchk; i += 4) bad_rows |= param_rows_violated<BK, 4>(pg, i, w) ? 1 : 0;
+      for (int i = 0; i < pg.nchk; i += 2) {
+        bad_rows |= param_rows_violated<BK, 2>(pg, i, w) ? 1 : 0;
+        drip(4);
+      }
       param_ok = bad_rows == 0;
     }
     const double c0 = cost_const<BK>(pg, w);
@@ -200,7 +244,7 @@ __global__ void __launch_bounds__(TPB, 512 / TPB) fast_step_kernel(const QpProg<
     res.obj = 0.0;
     res.verdict = kCertUndecided;
     if (__any_sync(0xffffffffu, status == kDefer && valid)) {
-      res = certify2<BK>(pg, w, q, code);
+      res = certify2<BK>(pg, w, q, code, [&]() { drip(12); });
       if (status == kDefer && valid && res.verdict == kCertOk) status = TZ_STATUS_OK;
     }
     // a hint that does not certify: is the program infeasible outright (singleton presolve, exact)?  Otherwise defer.
@@ -217,7 +261,7 @@ __global__ void __launch_bounds__(TPB, 512 / TPB) fast_step_kernel(const QpProg<
     }
     const bool emit = live && !deferred;
     const bool good = status == TZ_STATUS_OK;
-    if (dense && zvec && !zero_first) zero_rows_vec();      // (the whole warp: its share covers other lanes' scenarios)
+    drip(16);
     double nrm2 = 0.0, cost = NAN;
     if (emit) {
       // ---- hints: rows [0, G) the active set for the next step, rows [G, 2G) the active set of the run's first step
@@ -244,19 +288,15 @@ __global__ void __launch_bounds__(TPB, 512 / TPB) fast_step_kernel(const QpProg<
       else if (status == TZ_STATUS_INFEASIBLE) cost = INFINITY;      // cvxpy returns +inf for an infeasible Minimize (:374)
 #pragma unroll
       for (int j = 0; j < NW; ++j) om[j][tid] = omr[j];
-      {
-        double acc[HP];                                     // the n rows at once: n independent fma chains
+#pragma unroll 2
+      for (int r = 0; r < n; ++r) {
+        const double* row = sCZ + r * NW;
+        double acc = 0.0;
 #pragma unroll
-        for (int r = 0; r < HP; ++r) acc[r] = 0.0;
-#pragma unroll
-        for (int j = 0; j < NW; ++j)
-#pragma unroll
-          for (int r = 0; r < HP; ++r)
-            if (r < n) acc[r] = fma(sCZ[r * NW + j], omr[j], acc[r]);
-#pragma unroll
-        for (int r = 0; r < HP; ++r)
-          if (r < n) om[BK::OM_C + r][tid] = acc[r];
+        for (int j = 0; j < NW; ++j) acc = fma(row[j], omr[j], acc);
+        om[BK::OM_C + r][tid] = acc;
       }
+      drip(16);
       // (sm.om columns are thread-private: no barrier)
       // ---- Ze[1].Z at the optimum (examples/2.pulley_sim.py:96): the entries of the term table
       if (a.ze1 != nullptr) {
@@ -269,7 +309,7 @@ __global__ void __launch_bounds__(TPB, 512 / TPB) fast_step_kernel(const QpProg<
             __stcs(ptr, e.x * omc[(int)(__double_as_longlong(e.y) & 0xffffffffll) * TPB]);
           }
         } else {
-          if (!zero_first && !zvec) zero_runs();
+          if (ZW == 0 && !zero_first && !zvec) zero_runs();
 #pragma unroll 4
           for (int i = 0; i < ax.n_nz; ++i) {
             const double2 e = tt[i];
@@ -282,28 +322,28 @@ __global__ void __launch_bounds__(TPB, 512 / TPB) fast_step_kernel(const QpProg<
       double xb1[HP];
 #pragma unroll
       for (int i = 0; i < HP; ++i) xb1[i] = 0.0;
-      // block k of the trajectory (rows k n .. k n + n - 1 = xbar_k): its n rows at once, n independent fma chains
-      auto xb_block = [&](int k, double (&acc)[HP]) {
-        const double* blk_rows = sXB + k * n * NW;
+      auto xb_row = [&](int i) {
+        const double* row = sXB + i * NW;
+        double acc = 0.0;
 #pragma unroll
-        for (int r = 0; r < HP; ++r) acc[r] = 0.0;
-#pragma unroll
-        for (int j = 0; j < NW; ++j)
-#pragma unroll
-          for (int r = 0; r < HP; ++r)
-            if (r < n) acc[r] = fma(blk_rows[r * NW + j], omr[j], acc[r]);
-        if (a.xbar_traj != nullptr) {
-#pragma unroll
-          for (int r = 0; r < HP; ++r)
-            if (r < n) a.xbar_traj[(int64_t)(k * n + r) * LD + s] = acc[r];
-        }
+        for (int j = 0; j < NW; ++j) acc = fma(row[j], omr[j], acc);
+        if (a.xbar_traj != nullptr) a.xbar_traj[(int64_t)i * LD + s] = acc;
+        return acc;
       };
-      if (a.xbar_traj != nullptr || closed) xb_block(1, xb1);
       if (a.xbar_traj != nullptr) {
-        double tmp[HP];
-        xb_block(0, tmp);
-#pragma unroll 1
-        for (int k = 2; k <= ax.N; ++k) xb_block(k, tmp);
+#pragma unroll 2
+        for (int i = 0; i < n; ++i) (void)xb_row(i);
+      }
+      drip(16);
+      if (a.xbar_traj != nullptr || closed) {
+#pragma unroll
+        for (int k = 0; k < HP; ++k)
+          if (k < n) xb1[k] = xb_row(n + k);
+      }
+      drip(16);
+      if (a.xbar_traj != nullptr) {
+#pragma unroll 2
+        for (int i = 2 * n; i < (ax.N + 1) * n; ++i) (void)xb_row(i);
       }
       if (a.v != nullptr)
         for (int j = 0; j < nv; ++j) a.v[(int64_t)j * LD + s] = omc[(BK::OM_V + j) * TPB];
@@ -356,6 +396,7 @@ __global__ void __launch_bounds__(TPB, 512 / TPB) fast_step_kernel(const QpProg<
         }
       }
     }
+    drip(1 << 20);      // whatever is left of this thread's share of the zero entries (every thread: the shares cover other lanes' scenarios)
     // ---- closed-loop statistics: warp reduction, one atomic per statistic and warp
     if (a.stats != nullptr && closed) {
       const bool eg = emit && good;
@@ -387,21 +428,40 @@ size_t fast_slot_bytes(const TzProgram* p) {
   return ((sizeof(QpProg<BK>) + 15) & ~(size_t)15) + p->smem_tab;
 }
 
-template <class BK, int TPB, int NSLOT>
-int launch_fast_tpb(const TzProgram* p, const SolverParams& sp, const StepArgs& a, const SetEntry* entries, const int32_t* tile_prog,
-                    cudaStream_t st) {
+template <class BK, int TPB, int NSLOT, int ZW>
+int launch_fast_zw(const TzProgram* p, const SolverParams& sp, const StepArgs& a, const SetEntry* entries, const int32_t* tile_prog,
+                   int zero_pace, cudaStream_t st) {
   const size_t slot = fast_slot_bytes<BK>(p);
   const size_t smem = (NSLOT > 1 ? NSLOT : 1) * slot + sizeof(double) * BK::KOM * TPB;
   static std::atomic<unsigned long long> configured{0ull};
   const size_t smem_max = (NSLOT > 1 ? NSLOT : 1) * (((sizeof(QpProg<BK>) + 15) & ~(size_t)15) + kMaxTabBytes) + sizeof(double) * BK::KOM * TPB;
-  if (const int rc = ensure_dynamic_smem(fast_step_kernel<BK, TPB, NSLOT>, (int)smem_max, p->device, configured)) return rc;
+  if (const int rc = ensure_dynamic_smem(fast_step_kernel<BK, TPB, NSLOT, ZW>, (int)smem_max, p->device, configured)) return rc;
   const int64_t nblk = (a.S + TPB - 1) / TPB;
   const int64_t wave = (int64_t)p->num_sms * (512 / TPB);
   const unsigned grid = (unsigned)(NSLOT == 0 ? (nblk < wave ? nblk : wave) : nblk);
-  fast_step_kernel<BK, TPB, NSLOT><<<grid, TPB, smem, st>>>(reinterpret_cast<const QpProg<BK>*>(p->packed_dev), p->aux, sp, a, entries,
-                                                            tile_prog, (int)slot);
+  fast_step_kernel<BK, TPB, NSLOT, ZW><<<grid, TPB + 32 * ZW, smem, st>>>(reinterpret_cast<const QpProg<BK>*>(p->packed_dev), p->aux, sp, a,
+                                                                         entries, tile_prog, (int)slot, zero_pace);
   TZ_CUDA(cudaGetLastError());
   return TZ_OK;
+}
+
+// Tuning knobs, read per launch (no state): TZDDPC_FAST_ZW = 0 keeps the zero stores in the solve threads (dripped),
+// TZDDPC_ZERO_PACE = nanoseconds the zero warp sleeps after every 4 rows of zero stores.
+constexpr int kZeroPaceDefault = 100;
+
+template <class BK, int TPB, int NSLOT>
+int launch_fast_tpb(const TzProgram* p, const SolverParams& sp, const StepArgs& a, const SetEntry* entries, const int32_t* tile_prog,
+                    cudaStream_t st) {
+  if constexpr (TPB == 128 && NSLOT <= 1) {
+    const bool zvec = a.ze1 != nullptr && !sp.tube_packed && (reinterpret_cast<uintptr_t>(a.ze1) & 15u) == 0 && (a.ld & 1) == 0 &&
+                      (a.S & 1) == 0 && p->aux.n_zrun > 0;
+    const char* ez = getenv("TZDDPC_FAST_ZW");
+    if (zvec && !(ez && atoi(ez) == 0)) {
+      const char* ep = getenv("TZDDPC_ZERO_PACE");
+      return launch_fast_zw<BK, TPB, NSLOT, 1>(p, sp, a, entries, tile_prog, ep ? atoi(ep) : kZeroPaceDefault, st);
+    }
+  }
+  return launch_fast_zw<BK, TPB, NSLOT, 0>(p, sp, a, entries, tile_prog, 0, st);
 }
 
 // CTA size by batch size: big CTAs amortise the program staging (128 threads: 0.072 ms per 65,536-scenario step against

@@ -14,6 +14,7 @@
 // Algorithmic HBM bytes per scenario-step:
 //   8*[6n + N*m + (N+1)n + 1 + n(1+g1)] + 4.
 #include "tz_step.cuh"
+#include "tz_big.h"
 
 namespace tz {
 
@@ -216,6 +217,17 @@ static int build_program_host(const TzProgramDesc* d, TzProgram* p, HostImage& i
   if (rc == TZ_ERANGE && fits<BK>(*d)) rc = create_bucket<BK>(*d, p, ID, img);
   TZ_TRY(B0, 0) TZ_TRY(B1, 1) TZ_TRY(B2, 2) TZ_TRY(B3, 3)
 #undef TZ_TRY
+  if (rc == TZ_ERANGE && big_fits(*d)) {
+    // larger than every register-resident bucket: the generic warp-per-scenario path (tz_big.cu); no packed image, no tables
+    p->bucket = 4;
+    p->NZ = d->nz; p->NC = d->nc; p->G = 32;
+    p->nz = d->nz; p->nc = d->nc; p->n = d->n; p->m = d->m; p->N = d->horizon; p->nv = d->nv; p->g1 = d->g1; p->npar = d->npar;
+    for (int e = 0; e < d->n * (1 + d->g1); ++e)
+      if (d->ze1_ptr[e + 1] > d->ze1_ptr[e]) p->tube_ent.push_back(e);
+    p->aux.n_nz = (int)p->tube_ent.size();
+    p->aux.n = d->n; p->aux.m = d->m; p->aux.N = d->horizon; p->aux.nv = d->nv; p->aux.g1 = d->g1;
+    return TZ_OK;
+  }
   if (rc != TZ_OK) {
     if (rc == TZ_ERANGE) {
       const RowClasses c = classify(*d, nullptr);
@@ -328,9 +340,14 @@ extern "C" int tz_program_create(const TzProgramDesc* d, TzProgram** out) {
   HostImage img;
   int rc = build_program_host(d, p, img);
   if (rc == TZ_OK) rc = device_info(p);
+  if (rc == TZ_OK && p->bucket == 4) rc = big_create(*d, &p->big);
   if (rc != TZ_OK) {
     delete p;
     return rc;
+  }
+  if (p->bucket == 4) {
+    *out = p;
+    return TZ_OK;
   }
   cudaError_t err = cudaMalloc(&p->packed_dev, img.packed.size());
   if (err == cudaSuccess) err = cudaMemcpy(p->packed_dev, img.packed.data(), img.packed.size(), cudaMemcpyHostToDevice);
@@ -351,6 +368,7 @@ extern "C" void tz_program_destroy(TzProgram* p) {
     if (p->packed_dev) cudaFree(p->packed_dev);
     if (p->aux_dev) cudaFree(p->aux_dev);
   }
+  if (p->big) big_destroy(p->big);
   delete p;
 }
 
@@ -384,6 +402,7 @@ extern "C" int tz_program_create_batch(const TzProgramDesc* descs, int32_t D, Tz
     b->progs.push_back(p);
     HostImage img;
     rc = build_program_host(&descs[d], p, img);
+    if (rc == TZ_OK && p->bucket == 4) rc = fail(TZ_ERANGE, "programs of the generic large-program path cannot be batched");
     if (rc != TZ_OK) break;
     if (d == 0) {
       pstride = (img.packed.size() + 255) & ~(size_t)255;
@@ -434,6 +453,7 @@ extern "C" int tz_program_bucket(const TzProgram* p, char* buf, size_t cap) {
 
 extern "C" int tz_program_warm_rows(const TzProgram* p) {
   if (!p) return fail(TZ_EINVAL, "null program");
+  if (p->bucket == 4) return 1;           // (the generic large-program path starts cold: no warm-start rows)
   return p->NZ + p->NC + p->G + 1;        // x | y | activity words | valid flag
 }
 
@@ -504,6 +524,9 @@ static int launch(const TzProgram* p, const TzSolverOpts* o, const StepArgs& a_i
     return launch_bucket<B0>(p, sp, a, st);
   }
   switch (p->bucket) {
+    case 4:
+      TZ_REQUIRE(a.q_in == nullptr, "tz_qp_solve is not available for programs of the generic large-program path");
+      return big_launch(p->big, sp, a, st);
     case 0: return launch_bucket<B0>(p, sp, a, st);
     case 1: return launch_bucket<B1>(p, sp, a, st);
     case 2: return launch_bucket<B2>(p, sp, a, st);
@@ -569,6 +592,7 @@ extern "C" int tz_program_set_create(const TzProgram* const* progs, int32_t npro
     const Aux &a = p->aux, &b = p0->aux;
     // one kernel instance and one table layout serve the whole set: the programs must be the same problem (dimensions,
     // horizon, cost and constraint structure) built from different data
+    TZ_REQUIRE(p->bucket != 4, "programs of the generic large-program path cannot be combined into a set");
     TZ_REQUIRE(p->bucket == p0->bucket && p->smem_tab == p0->smem_tab && a.n_dbl == b.n_dbl && a.n_int == b.n_int &&
                a.o_XB == b.o_XB && a.o_CZ == b.o_CZ && a.o_K == b.o_K && a.o_coef == b.o_coef && a.o_ent == b.o_ent &&
                a.o_idx == b.o_idx && a.o_tt == b.o_tt && a.o_zrun == b.o_zrun && a.n_zrun == b.n_zrun && a.zrun_split == b.zrun_split && a.n_nz == b.n_nz && a.n == b.n && a.m == b.m && a.N == b.N && a.nv == b.nv && a.g1 == b.g1,

@@ -842,6 +842,8 @@ using B3 = Bucket<12, 1, 4, 4, 8, 16, 24, 32, 1>;    // large           (72 row 
 
 }  // namespace tz
 
+namespace tz { struct BigProgram; }
+
 struct TzProgram {
   int bucket = -1;
   void* packed_dev = nullptr;            // device image of QpProg<bucket>, staged into shared memory by every CTA
@@ -855,6 +857,7 @@ struct TzProgram {
   int num_sms = 148;
   int device = -1;                       // the CUDA device the program image lives on: launches on another device are refused
   bool owns_device = true;               // false: packed_dev / aux_dev are slices of a TzProgramBatch's allocations
+  tz::BigProgram* big = nullptr;         // bucket 4: the generic large-program path (tz_big.cu) instead of a packed image
 };
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute of a kernel.  The only process-wide state of the
