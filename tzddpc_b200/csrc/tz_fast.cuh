@@ -42,21 +42,18 @@ constexpr int kDeferTile = TZ_SPO_MIN;     // scenarios per deferred tile = outp
 // 16-scenario tiles look their program up in tile_prog.  NSLOT = 1: the set guarantees that a block lies within one
 // program; NSLOT = 2 (TPB = 32): the two half-warps of the warp may belong to two programs, each staged in its own slot --
 // a coefficient load then has two distinct addresses per warp instead of one.
-// ZW = 1: the CTA carries one extra warp (threads [TPB, TPB + 32)) that does nothing but store the structural zeros of the
-// block's dense Ze[1].Z slab, paced with nanosleep so that its stores trickle out while the TPB solve threads compute.
-// The solve warps are latency-bound (13.8 warps per SM at one thread per scenario, ~12 cycles per issued instruction:
-// profiles/r2_fast_v4_*), so every instruction taken off them shortens the step, and the zero warp rides on issue slots
-// that were idle.  Needs the 16-byte store form (the launcher checks alignment and an even batch).
-template <class BK, int TPB, int NSLOT, int ZW>
-__global__ void __launch_bounds__(TPB + 32 * ZW, ZW ? 4 : 512 / TPB)
+// resident CTAs per SM the register budget is set for (128 registers per thread)
+constexpr int fast_ctas_per_sm(int tpb) { return tpb >= 512 ? 1 : 512 / tpb; }
+
+// (Output stores are st.cs: default-policy and write-through stores measured 0.0689 / 0.0674 ms against 0.0598.)
+template <class BK, int TPB, int NSLOT>
+__global__ void __launch_bounds__(TPB, fast_ctas_per_sm(TPB))
     fast_step_kernel(const QpProg<BK>* __restrict__ gpg, const Aux ax, const SolverParams sp, const StepArgs a,
-                     const SetEntry* __restrict__ entries, const int32_t* __restrict__ tile_prog, const int slot_bytes,
-                     const int zero_pace) {
+                     const SetEntry* __restrict__ entries, const int32_t* __restrict__ tile_prog, const int slot_bytes) {
   constexpr int NZ = BK::NZ, NPAR = BK::NPAR, HP = BK::NPAR / 2, NCOL = BK::NCOL, NW = BK::NW, G = BK::G;
   static_assert(kDeferTile == 16 && BK::SPO == 16, "deferred tiles are the 16-scenario output tiles of step_kernel");
   static_assert(NSLOT <= 1 || TPB == 32, "two program slots: one warp per CTA");
-  static_assert(ZW == 0 || (NSLOT <= 1 && TPB % 64 == 0), "zero warp: one program per CTA, whole 64-scenario chunks");
-  constexpr int NT = TPB + 32 * ZW;                         // threads of the CTA
+  constexpr int OM_X = NW + HP, OM_NS = NW + 2 * HP;        // om rows of this kernel: [1 | v | p | centre | x | noise]
   constexpr int QPB = (int)((sizeof(QpProg<BK>) + 15) & ~(size_t)15);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31;
@@ -72,14 +69,18 @@ __global__ void __launch_bounds__(TPB + 32 * ZW, ZW ? 4 : 512 / TPB)
     char* dst = reinterpret_cast<char*>(slot);
     double* td = reinterpret_cast<double*>(slot + QPB);
     constexpr int NCH = (int)(sizeof(QpProg<BK>) / 16);
-    for (int i = tid; i < NCH; i += NT) cp_async16(dst + 16 * i, src + 16 * i);
+    for (int i = tid; i < NCH; i += TPB) cp_async16(dst + 16 * i, src + 16 * i);
     if (tid == 0 && (sizeof(QpProg<BK>) % 16) != 0) cp_async8(dst + 16 * NCH, src + 16 * NCH);
-    for (int i = tid; i < ax.n_dbl; i += NT) cp_async8(td + i, tab_src + i);
+    for (int i = tid; i < ax.n_dbl; i += TPB) cp_async8(td + i, tab_src + i);
+  };
+  auto stage_plant = [&](unsigned char* slot) {              // (caller-owned arrays: behind pdl_wait)
+    double* td = reinterpret_cast<double*>(slot + QPB);
     if (closed) {
-      for (int i = tid; i < n * n; i += NT) cp_async8(td + ax.n_dbl + i, a.A_true + i);
-      for (int i = tid; i < n * m; i += NT) cp_async8(td + ax.n_dbl + n * n + i, a.B_true + i);
+      for (int i = tid; i < n * n; i += TPB) cp_async8(td + ax.n_dbl + i, a.A_true + i);
+      for (int i = tid; i < n * m; i += TPB) cp_async8(td + ax.n_dbl + n * n + i, a.B_true + i);
     }
   };
+  pdl_trigger();
   unsigned char* my_slot = smem_raw;
   if constexpr (NSLOT == 0) {
     stage(smem_raw, gpg, ax.tab);
@@ -98,6 +99,10 @@ __global__ void __launch_bounds__(TPB + 32 * ZW, ZW ? 4 : 512 / TPB)
     }
   }
   cp_async_commit();
+  pdl_wait();                                    // from here on: data earlier kernels of the stream may have written
+  stage_plant(smem_raw);
+  if constexpr (NSLOT == 2) stage_plant(smem_raw + slot_bytes);
+  cp_async_commit();
   double* tabd = reinterpret_cast<double*>(my_slot + QPB);
   bool staged = false;
   const QpProg<BK>& pg = *reinterpret_cast<const QpProg<BK>*>(my_slot);
@@ -111,30 +116,6 @@ __global__ void __launch_bounds__(TPB + 32 * ZW, ZW ? 4 : 512 / TPB)
   // 16-byte zero stores need 16-byte aligned rows and an even batch (a pair of scenarios is in or out together)
   const bool zvec = dense && (reinterpret_cast<uintptr_t>(a.ze1) & 15u) == 0 && (a.ld & 1) == 0 && (a.S & 1) == 0;
   const int64_t nblk = (a.S + TPB - 1) / TPB;
-  if constexpr (ZW > 0) {
-    if (tid >= TPB) {
-      // ---- the zero warp: lane l owns the 16-byte chunks (scenarios 2l, 2l + 1) + 64 h of every structurally zero row
-      cp_async_wait<0>();
-      __syncthreads();
-      const int zl = tid - TPB;
-      int cnt = 0;
-      for (int64_t blk = blockIdx.x; blk < nblk; blk += (NSLOT == 0 ? (int64_t)gridDim.x : nblk)) {
-        const int64_t sv0 = blk * TPB + 2 * zl;
-#pragma unroll 1
-        for (int r = 0; r < ax.n_zrun; ++r) {
-          double* ptr = a.ze1 + sv0 + (int64_t)zs[2 * r] * LD;
-#pragma unroll 2
-          for (int c = zs[2 * r + 1]; c > 0; --c, ptr += LD) {
-#pragma unroll
-            for (int h = 0; h < TPB / 64; ++h)
-              if (sv0 + 64 * h < a.S) __stcs(reinterpret_cast<double2*>(ptr + 64 * h), make_double2(0.0, 0.0));
-            if (zero_pace > 0 && (++cnt & 3) == 0) __nanosleep(zero_pace);
-          }
-        }
-      }
-      return;
-    }
-  }
   const unsigned long long* hint = reinterpret_cast<const unsigned long long*>(a.warm);
   unsigned long long* hint_w = reinterpret_cast<unsigned long long*>(a.warm);
   const unsigned half_mask = lane < 16 ? 0x0000ffffu : 0xffff0000u;
@@ -161,6 +142,17 @@ __global__ void __launch_bounds__(TPB + 32 * ZW, ZW ? 4 : 512 / TPB)
       w[1 + NPAR + j] = fabs(xv);
       w[1 + NPAR + HP + j] = fabs(ev);
       finite = finite && (fabs(xv) < 1e300) && (fabs(ev) < 1e300);
+    }
+    // the closed-loop update's inputs (x, noise) are fetched now, into this thread's column of om: every load of the step is
+    // in flight before the first store is issued (a load queued behind the step's ~300 MB of stores waits microseconds)
+    if (closed) {
+#pragma unroll
+      for (int i = 0; i < HP; ++i)
+        if (i < n) {
+          cp_async8(&om[OM_X + i][tid], a.x + (int64_t)i * LD + sc);
+          if (a.noise) cp_async8(&om[OM_NS + i][tid], a.noise + (int64_t)i * LD + sc);
+        }
+      cp_async_commit();
     }
     if (!staged) {
       cp_async_wait<0>();
@@ -191,9 +183,8 @@ __global__ void __launch_bounds__(TPB + 32 * ZW, ZW ? 4 : 512 / TPB)
     const int z_end = z_half == 0 ? ax.zrun_split : ax.n_zrun;
     int z_left = 0;
     double* z_ptr = a.ze1;
-    if (!(zvec && z_sv < a.S) || ZW > 0) z_run = z_end;
+    if (!(zvec && z_sv < a.S)) z_run = z_end;
     auto drip = [&](int budget) {
-      if constexpr (ZW > 0) return;                                  // (the zero warp stores them)
       while (budget > 0) {
         if (z_left == 0) {
           if (z_run >= z_end) return;
@@ -208,7 +199,7 @@ __global__ void __launch_bounds__(TPB + 32 * ZW, ZW ? 4 : 512 / TPB)
         budget -= k;
       }
     };
-    const bool zero_first = ZW == 0 && dense && !zvec && (((tid >> 5) + (int)blk) & 1);
+    const bool zero_first = dense && !zvec && (((tid >> 5) + (int)blk) & 1);
     if (zero_first && live) zero_runs();
     drip(24);
 
@@ -309,7 +300,7 @@ __global__ void __launch_bounds__(TPB + 32 * ZW, ZW ? 4 : 512 / TPB)
             __stcs(ptr, e.x * omc[(int)(__double_as_longlong(e.y) & 0xffffffffll) * TPB]);
           }
         } else {
-          if (ZW == 0 && !zero_first && !zvec) zero_runs();
+          if (!zero_first && !zvec) zero_runs();
 #pragma unroll 4
           for (int i = 0; i < ax.n_nz; ++i) {
             const double2 e = tt[i];
@@ -366,12 +357,13 @@ __global__ void __launch_bounds__(TPB + 32 * ZW, ZW ? 4 : 512 / TPB)
           us[j] = acc;                                                              // u = K e + v[0]
         }
         double xo[HP];
+        cp_async_wait<0>();
 #pragma unroll
-        for (int i = 0; i < HP; ++i) xo[i] = (i < n) ? a.x[(int64_t)i * LD + s] : 0.0;
+        for (int i = 0; i < HP; ++i) xo[i] = (i < n) ? omc[(OM_X + i) * TPB] : 0.0;
 #pragma unroll
         for (int i = 0; i < HP; ++i) {
           if (i < n) {
-            double acc = a.noise ? a.noise[(int64_t)i * LD + s] : 0.0;
+            double acc = a.noise ? omc[(OM_NS + i) * TPB] : 0.0;
 #pragma unroll
             for (int k = 0; k < HP; ++k)
               if (k < n) acc = fma(sA[i * n + k], xo[k], acc);
@@ -428,56 +420,61 @@ size_t fast_slot_bytes(const TzProgram* p) {
   return ((sizeof(QpProg<BK>) + 15) & ~(size_t)15) + p->smem_tab;
 }
 
-template <class BK, int TPB, int NSLOT, int ZW>
-int launch_fast_zw(const TzProgram* p, const SolverParams& sp, const StepArgs& a, const SetEntry* entries, const int32_t* tile_prog,
-                   int zero_pace, cudaStream_t st) {
-  const size_t slot = fast_slot_bytes<BK>(p);
-  const size_t smem = (NSLOT > 1 ? NSLOT : 1) * slot + sizeof(double) * BK::KOM * TPB;
-  static std::atomic<unsigned long long> configured{0ull};
-  const size_t smem_max = (NSLOT > 1 ? NSLOT : 1) * (((sizeof(QpProg<BK>) + 15) & ~(size_t)15) + kMaxTabBytes) + sizeof(double) * BK::KOM * TPB;
-  if (const int rc = ensure_dynamic_smem(fast_step_kernel<BK, TPB, NSLOT, ZW>, (int)smem_max, p->device, configured)) return rc;
-  const int64_t nblk = (a.S + TPB - 1) / TPB;
-  const int64_t wave = (int64_t)p->num_sms * (512 / TPB);
-  const unsigned grid = (unsigned)(NSLOT == 0 ? (nblk < wave ? nblk : wave) : nblk);
-  fast_step_kernel<BK, TPB, NSLOT, ZW><<<grid, TPB + 32 * ZW, smem, st>>>(reinterpret_cast<const QpProg<BK>*>(p->packed_dev), p->aux, sp, a,
-                                                                         entries, tile_prog, (int)slot, zero_pace);
-  TZ_CUDA(cudaGetLastError());
-  return TZ_OK;
+// CTAs of `tpb` threads that are resident on one SM: registers (launch bounds) and shared memory (227 KB, 1 KB per CTA reserved)
+template <class BK>
+int fast_resident(const TzProgram* p, int tpb, int nslot) {
+  const size_t per_cta = (nslot > 1 ? nslot : 1) * fast_slot_bytes<BK>(p) + sizeof(double) * (BK::NW + 3 * (BK::NPAR / 2)) * tpb + 1024;
+  const int by_smem = (int)((size_t)227 * 1024 / per_cta);
+  const int by_regs = fast_ctas_per_sm(tpb);
+  return by_smem < by_regs ? (by_smem > 0 ? by_smem : 1) : by_regs;
 }
-
-// Tuning knobs, read per launch (no state): TZDDPC_FAST_ZW = 0 keeps the zero stores in the solve threads (dripped),
-// TZDDPC_ZERO_PACE = nanoseconds the zero warp sleeps after every 4 rows of zero stores.
-constexpr int kZeroPaceDefault = 100;
 
 template <class BK, int TPB, int NSLOT>
 int launch_fast_tpb(const TzProgram* p, const SolverParams& sp, const StepArgs& a, const SetEntry* entries, const int32_t* tile_prog,
                     cudaStream_t st) {
-  if constexpr (TPB == 128 && NSLOT <= 1) {
-    const bool zvec = a.ze1 != nullptr && !sp.tube_packed && (reinterpret_cast<uintptr_t>(a.ze1) & 15u) == 0 && (a.ld & 1) == 0 &&
-                      (a.S & 1) == 0 && p->aux.n_zrun > 0;
-    const char* ez = getenv("TZDDPC_FAST_ZW");
-    if (zvec && !(ez && atoi(ez) == 0)) {
-      const char* ep = getenv("TZDDPC_ZERO_PACE");
-      return launch_fast_zw<BK, TPB, NSLOT, 1>(p, sp, a, entries, tile_prog, ep ? atoi(ep) : kZeroPaceDefault, st);
-    }
-  }
-  return launch_fast_zw<BK, TPB, NSLOT, 0>(p, sp, a, entries, tile_prog, 0, st);
+  const size_t slot = fast_slot_bytes<BK>(p);
+  constexpr size_t om_bytes = sizeof(double) * (BK::NW + 3 * (BK::NPAR / 2)) * TPB;
+  const size_t smem = (NSLOT > 1 ? NSLOT : 1) * slot + om_bytes;
+  static std::atomic<unsigned long long> configured{0ull};
+  const size_t smem_max = (NSLOT > 1 ? NSLOT : 1) * (((sizeof(QpProg<BK>) + 15) & ~(size_t)15) + kMaxTabBytes) + om_bytes;
+  if (const int rc = ensure_dynamic_smem(fast_step_kernel<BK, TPB, NSLOT>, (int)smem_max, p->device, configured)) return rc;
+  const int64_t nblk = (a.S + TPB - 1) / TPB;
+  const int64_t wave = (int64_t)p->num_sms * fast_resident<BK>(p, TPB, NSLOT);
+  const unsigned grid = (unsigned)(NSLOT == 0 ? (nblk < wave ? nblk : wave) : nblk);
+  TZ_CUDA(launch_kernel(fast_step_kernel<BK, TPB, NSLOT>, grid, TPB, smem, st, pdl_enabled(a.S),
+                        reinterpret_cast<const QpProg<BK>*>(p->packed_dev), p->aux, sp, a, entries, tile_prog, (int)slot));
+  return TZ_OK;
 }
 
-// CTA size by batch size: big CTAs amortise the program staging (128 threads: 0.072 ms per 65,536-scenario step against
-// 0.079 / 0.097 with 64 / 32), small ones keep every SM busy when the batch is a fraction of a wave (strong scaling:
-// 8,192 scenarios per GPU are 256 warps on 148 SMs)
+// CTA size by batch size, measured on 148 SMs (profiles/r2_fast_cta_size_sweep.txt; ms per dense 5-dim step):
+//   65,536 scenarios:  32: 0.077   64: 0.0626   96: 0.0645   128: 0.0649   160: 0.0632   224: 0.0621   256: 0.0598   512: 0.0644
+//   32,768:  64: 0.0377  128: 0.0390  256: 0.0412        16,384:  64: 0.0319  128: 0.0318  256: 0.0380        8,192:  64: 0.0293  128: 0.0307
+// Two effects: a CTA's stores of one output row are TPB * 8 contiguous bytes (256 threads: 2 KB runs, kinder to DRAM than the
+// 1 KB of 128), and a batch below ~1.5 scenarios per thread slot of the wave wants many small CTAs so that every SM has work.
+// Beyond one wave of 256-thread CTAs the persistent loop takes over; the size that leaves the fullest SM least full is used.
 template <class BK>
 int launch_fast(const TzProgram* p, const SolverParams& sp, const StepArgs& a, cudaStream_t st) {
-  if (const char* e = getenv("TZDDPC_FAST_TPB")) {      // tuning knob (read per launch, no state): force the CTA size
-    const int t = atoi(e);
-    if (t == 128) return launch_fast_tpb<BK, 128, 0>(p, sp, a, nullptr, nullptr, st);
-    if (t == 64) return launch_fast_tpb<BK, 64, 0>(p, sp, a, nullptr, nullptr, st);
-    if (t == 32) return launch_fast_tpb<BK, 32, 0>(p, sp, a, nullptr, nullptr, st);
+  int tpb = 0;
+  if (const char* e = getenv("TZDDPC_FAST_TPB")) tpb = atoi(e);      // tuning knob (read per launch, no state): force the CTA size
+  if (tpb == 0) {
+    const int64_t sms = p->num_sms;
+    if (a.S <= sms * 512) tpb = a.S >= sms * 384 ? 256 : 64;
+    else {
+      int64_t best = INT64_MAX;
+      for (int t = 256; t >= 64; t >>= 1) {
+        const int64_t ctas = (a.S + t - 1) / t, per_sm = (ctas + sms - 1) / sms, cap = fast_resident<BK>(p, t, 0);
+        const int64_t rounds = (per_sm + cap - 1) / cap;
+        const int64_t load = (int64_t)t * ((per_sm + rounds - 1) / rounds) * rounds;
+        if (load < best) { best = load; tpb = t; }
+      }
+    }
   }
-  if (a.S >= (int64_t)p->num_sms * 128 * 2) return launch_fast_tpb<BK, 128, 0>(p, sp, a, nullptr, nullptr, st);
-  if (a.S >= (int64_t)p->num_sms * 64 * 2) return launch_fast_tpb<BK, 64, 0>(p, sp, a, nullptr, nullptr, st);
-  return launch_fast_tpb<BK, 32, 0>(p, sp, a, nullptr, nullptr, st);
+  switch (tpb) {
+    case 256: return launch_fast_tpb<BK, 256, 0>(p, sp, a, nullptr, nullptr, st);
+    case 128: return launch_fast_tpb<BK, 128, 0>(p, sp, a, nullptr, nullptr, st);
+    case 32: return launch_fast_tpb<BK, 32, 0>(p, sp, a, nullptr, nullptr, st);
+    default: return launch_fast_tpb<BK, 64, 0>(p, sp, a, nullptr, nullptr, st);
+  }
 }
 
 // Program set: `block` = the largest of 128 / 64 / 32 that divides every program's first scenario (so that a CTA's block of

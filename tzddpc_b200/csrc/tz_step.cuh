@@ -717,6 +717,8 @@ template <class BK>
 __global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel(const QpProg<BK>* __restrict__ gpg, const Aux ax,
                                                                 const SolverParams sp, const StepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  pdl_trigger();
+  pdl_wait();
   int64_t ntiles = (a.S + BK::SPO - 1) / BK::SPO;
   if (a.list_mode) {
     // the tiles fast_step_kernel could not decide; every CTA takes an exit ticket and the last one clears the list
@@ -766,6 +768,8 @@ __global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel_set(const SetEn
                                                                     const int64_t total_tiles, const Aux ax0,
                                                                     const SolverParams sp, const StepArgs a0) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  pdl_trigger();
+  pdl_wait();
   int staged = -1;                                 // program whose image is in shared memory
   int lo = 0;
   // round k: the CTA's WPB warps take the consecutive tiles [base, base + WPB) of the global numbering
@@ -805,6 +809,8 @@ __global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel_set_list(const 
                                                                          const int32_t* __restrict__ tile_prog, const Aux ax0,
                                                                          const SolverParams sp, const StepArgs a0) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  pdl_trigger();
+  pdl_wait();
   const int64_t max_tiles = (a0.S + BK::SPO - 1) / BK::SPO;
   const int64_t cnt = *reinterpret_cast<volatile const int32_t*>(a0.defer);
   const int64_t ntl = cnt < 0 ? 0 : (cnt < max_tiles ? cnt : max_tiles);
@@ -888,8 +894,8 @@ int launch_bucket(const TzProgram* p, const SolverParams& sp, const StepArgs& a,
   // (list mode -- the tiles fast_step_kernel deferred, normally none or a handful: one CTA per SM keeps the empty pass short)
   const int64_t wave = (int64_t)p->num_sms * (a.list_mode ? 1 : BK::MINB);
   const unsigned grid = (unsigned)(need < wave ? need : wave);
-  step_kernel<BK><<<grid, BK::TPB, smem, st>>>(reinterpret_cast<const QpProg<BK>*>(p->packed_dev), p->aux, sp, a);
-  TZ_CUDA(cudaGetLastError());
+  TZ_CUDA(launch_kernel(step_kernel<BK>, grid, BK::TPB, smem, st, pdl_enabled(a.S), reinterpret_cast<const QpProg<BK>*>(p->packed_dev), p->aux,
+                        sp, a));
   return TZ_OK;
 }
 
@@ -905,8 +911,7 @@ int launch_bucket_set(const TzProgram* p0, const SetEntry* entries_dev, int npro
   const int64_t wave = (int64_t)p0->num_sms * BK::MINB;
   const int64_t need = (total_tiles + BK::WPB - 1) / BK::WPB;
   const unsigned grid = (unsigned)(need < wave ? need : wave);
-  step_kernel_set<BK><<<grid, BK::TPB, smem, st>>>(entries_dev, nprog, total_tiles, p0->aux, sp, a);
-  TZ_CUDA(cudaGetLastError());
+  TZ_CUDA(launch_kernel(step_kernel_set<BK>, grid, BK::TPB, smem, st, pdl_enabled(a.S), entries_dev, nprog, total_tiles, p0->aux, sp, a));
   return TZ_OK;
 }
 
@@ -918,8 +923,7 @@ int launch_bucket_set_list(const TzProgram* p0, const SetEntry* entries_dev, con
   if (const int rc = ensure_dynamic_smem(step_kernel_set_list<BK>, (int)(sizeof(Smem<BK>) + kMaxTabBytes), p0->device, configured)) return rc;
   const int64_t ntiles = (a.S + BK::SPO - 1) / BK::SPO;
   const unsigned grid = (unsigned)(ntiles < p0->num_sms ? ntiles : p0->num_sms);
-  step_kernel_set_list<BK><<<grid, BK::TPB, smem, st>>>(entries_dev, tile_prog, p0->aux, sp, a);
-  TZ_CUDA(cudaGetLastError());
+  TZ_CUDA(launch_kernel(step_kernel_set_list<BK>, grid, BK::TPB, smem, st, pdl_enabled(a.S), entries_dev, tile_prog, p0->aux, sp, a));
   return TZ_OK;
 }
 
