@@ -21,6 +21,7 @@ the host every step); `cpu_baseline` = the CPU oracle port timed here on the sam
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import sys
@@ -299,12 +300,19 @@ def timed_leg(torch, loop, W, K, barrier, use_graph=True, sampler_dev=None):
     barrier()
     graph = None
     if use_graph:
-        side = torch.cuda.Stream(device=loop.dev)
-        side.wait_stream(torch.cuda.current_stream(loop.dev))
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=side):
-            for k in range(K):
-                loop.step(W + k)
+        # (no garbage collection inside the capture: a collected controller / ensemble of an earlier leg frees device memory
+        #  in its finaliser -- cudaFree -- which invalidates a stream capture in progress)
+        gc.collect()
+        gc.disable()
+        try:
+            side = torch.cuda.Stream(device=loop.dev)
+            side.wait_stream(torch.cuda.current_stream(loop.dev))
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                for k in range(K):
+                    loop.step(W + k)
+        finally:
+            gc.enable()
         barrier()
     sampler = ClockSampler(sampler_dev) if sampler_dev is not None else None
     ev = [torch.cuda.Event(enable_timing=True) for _ in range((1 if use_graph else K) + 1)]
@@ -364,8 +372,13 @@ def batch1_latency(tz, ops, torch, dev, steps_per_graph=12, replays=100):
         run()                                   # warm-up on the capture stream
     torch.cuda.synchronize(dev)
     graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph, stream=side):
-        run()
+    gc.collect()
+    gc.disable()                                # (see timed_leg: no finaliser may free device memory inside a capture)
+    try:
+        with torch.cuda.graph(graph, stream=side):
+            run()
+    finally:
+        gc.enable()
     for _ in range(3):
         graph.replay()
     torch.cuda.synchronize(dev)
@@ -488,9 +501,14 @@ def datasets_leg(args, tz, ops, torch, dev, cfg, nring):
     side = torch.cuda.Stream(device=dev)
     side.wait_stream(torch.cuda.current_stream(dev))
     graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph, stream=side):
-        for k in range(Kd):
-            step(5 + k)
+    gc.collect()
+    gc.disable()                                # (see timed_leg)
+    try:
+        with torch.cuda.graph(graph, stream=side):
+            for k in range(Kd):
+                step(5 + k)
+    finally:
+        gc.enable()
     torch.cuda.synchronize(dev)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
