@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(kIdThreads) identify_kernel(int T, int n, int 
   __shared__ double part[kIdWarps][kMaxRed];
   __shared__ double Rdiag[kMaxD], beta[kMaxD], Rinv[kMaxD * kMaxD];
   __shared__ double sP[kMaxD], sPK[kMaxN];
+  __shared__ double wP[kIdThreads / 32][kMaxD], wPK[kIdThreads / 32][kMaxN];      // per-warp partial sums, combined in a fixed order
   __shared__ int bad;
   const int64_t s = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31;
@@ -170,14 +171,28 @@ __global__ void __launch_bounds__(kIdThreads) identify_kernel(int T, int n, int 
           aPK[c] += fabs(t);
         }
     }
+    // (fixed-order combination, no atomics: the box widths -- and with them every program built from this data set -- come
+    //  out bit-identical on every run and every GPU, which the N-GPU == 1-GPU check of bench.py relies on)
+    const int wid = tid >> 5;
     for (int b = 0; b < d; ++b) {
       const double v = warp_sum(aP[b]);
-      if (lane == 0) atomicAdd(&sP[b], v);
+      if (lane == 0) wP[wid][b] = v;
     }
     for (int c = 0; c < n; ++c) {
       const double v = warp_sum(aPK[c]);
-      if (lane == 0) atomicAdd(&sPK[c], v);
+      if (lane == 0) wPK[wid][c] = v;
     }
+  }
+  __syncthreads();
+  if (tid < d) {
+    double t = 0.0;
+    for (int w = 0; w < kIdThreads / 32; ++w) t += wP[w][tid];
+    sP[tid] = t;
+  }
+  if (tid < n) {
+    double t = 0.0;
+    for (int w = 0; w < kIdThreads / 32; ++w) t += wPK[w][tid];
+    sPK[tid] = t;
   }
   __syncthreads();
   for (int i = tid; i < n * d; i += kIdThreads) {
