@@ -46,38 +46,47 @@ constexpr int kDeferTile = TZ_SPO_MIN;     // scenarios per deferred tile = outp
 constexpr int fast_ctas_per_sm(int tpb) { return tpb >= 512 ? 1 : 512 / tpb; }
 
 // (Output stores are st.cs: default-policy and write-through stores measured 0.0689 / 0.0674 ms against 0.0598.)
-template <class BK, int TPB, int NSLOT>
-__global__ void __launch_bounds__(TPB, fast_ctas_per_sm(TPB))
+// H > 1 (small batches, where SMs would otherwise host one or two warps): the CTA carries H threads per scenario,
+// threads [hq * TPB, (hq + 1) * TPB) being helper group hq.  Group 0 loads, solves and updates exactly as for H = 1; the
+// helper groups store the structural zeros of the block's dense tube meanwhile (they do not depend on the solve), and
+// behind a CTA barrier all H groups share the tube entries and trajectory rows of the block's scenarios, read from om.
+// Per-scenario arithmetic is the same expressions on the same operands: results do not depend on H.
+// (First version: zeros split row-wise within every run, behind the barrier: 17 instructions per store, no gain.)
+template <class BK, int TPB, int NSLOT, int H = 1>
+__global__ void __launch_bounds__(TPB * H, fast_ctas_per_sm(TPB * H))
     fast_step_kernel(const QpProg<BK>* __restrict__ gpg, const Aux ax, const SolverParams sp, const StepArgs a,
                      const SetEntry* __restrict__ entries, const int32_t* __restrict__ tile_prog, const int slot_bytes) {
   constexpr int NZ = BK::NZ, NPAR = BK::NPAR, HP = BK::NPAR / 2, NCOL = BK::NCOL, NW = BK::NW, G = BK::G;
   static_assert(kDeferTile == 16 && BK::SPO == 16, "deferred tiles are the 16-scenario output tiles of step_kernel");
   static_assert(NSLOT <= 1 || TPB == 32, "two program slots: one warp per CTA");
+  static_assert(H == 1 || NSLOT == 0, "helper groups: single-program launches only");
   constexpr int OM_X = NW + HP, OM_NS = NW + 2 * HP;        // om rows of this kernel: [1 | v | p | centre | x | noise]
   constexpr int QPB = (int)((sizeof(QpProg<BK>) + 15) & ~(size_t)15);
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tix = threadIdx.x, tid = tix % TPB, hq = tix / TPB, lane = tix & 31;      // (hq is warp-uniform: TPB % 32 == 0)
+  constexpr int NT = TPB * H;
   const int n = ax.n, m = ax.m, nv = ax.nv;
   const bool closed = a.x != nullptr;
   const int64_t LD = a.ld;
   const bool dense = a.ze1 != nullptr && !sp.tube_packed;
   // shared memory: NSLOT (or one) x [QpProg | tables | A_true | B_true], then om[KOM][TPB]
   double (*om)[TPB] = reinterpret_cast<double (*)[TPB]>(smem_raw + (NSLOT > 1 ? NSLOT : 1) * (size_t)slot_bytes);
+  int* sflag = reinterpret_cast<int*>(&om[NW + 3 * HP][0]);                 // H > 1: (emit | good << 1) per scenario of the block
   // ---- stage a program and its tables into a slot (cp.async, all in flight at once)
   auto stage = [&](unsigned char* slot, const void* pg_src, const double* tab_src) {
     const char* src = reinterpret_cast<const char*>(pg_src);
     char* dst = reinterpret_cast<char*>(slot);
     double* td = reinterpret_cast<double*>(slot + QPB);
     constexpr int NCH = (int)(sizeof(QpProg<BK>) / 16);
-    for (int i = tid; i < NCH; i += TPB) cp_async16(dst + 16 * i, src + 16 * i);
-    if (tid == 0 && (sizeof(QpProg<BK>) % 16) != 0) cp_async8(dst + 16 * NCH, src + 16 * NCH);
-    for (int i = tid; i < ax.n_dbl; i += TPB) cp_async8(td + i, tab_src + i);
+    for (int i = tix; i < NCH; i += NT) cp_async16(dst + 16 * i, src + 16 * i);
+    if (tix == 0 && (sizeof(QpProg<BK>) % 16) != 0) cp_async8(dst + 16 * NCH, src + 16 * NCH);
+    for (int i = tix; i < ax.n_dbl; i += NT) cp_async8(td + i, tab_src + i);
   };
   auto stage_plant = [&](unsigned char* slot) {              // (caller-owned arrays: behind pdl_wait)
     double* td = reinterpret_cast<double*>(slot + QPB);
     if (closed) {
-      for (int i = tid; i < n * n; i += TPB) cp_async8(td + ax.n_dbl + i, a.A_true + i);
-      for (int i = tid; i < n * m; i += TPB) cp_async8(td + ax.n_dbl + n * n + i, a.B_true + i);
+      for (int i = tix; i < n * n; i += NT) cp_async8(td + ax.n_dbl + i, a.A_true + i);
+      for (int i = tix; i < n * m; i += NT) cp_async8(td + ax.n_dbl + n * n + i, a.B_true + i);
     }
   };
   pdl_trigger();
@@ -125,6 +134,53 @@ __global__ void __launch_bounds__(TPB, fast_ctas_per_sm(TPB))
     const int64_t s = blk * TPB + tid;
     const bool live = s < a.S;
     const int64_t sc = live ? s : a.S - 1;                 // dead lanes shadow the last scenario and write nothing
+    bool emit = false, good = false;
+    enum { kDefer = -2 };
+    int status = kDefer;
+    double omr[NW];
+    double nrm2 = 0.0, cost = NAN;
+    // ---- zero runs of the dense tube: odd warps before the solve, even warps behind it
+    auto zero_runs = [&]() {
+      double* base = a.ze1 + s;
+#pragma unroll 1
+      for (int r = 0; r < ax.n_zrun; ++r) {
+        double* ptr = base + (int64_t)zs[2 * r] * LD;
+#pragma unroll 4
+        for (int c = zs[2 * r + 1]; c > 0; --c, ptr += LD) __stcs(ptr, 0.0);
+      }
+    };
+    // Vector form (16-byte aligned rows): a thread keeps a 16-byte chunk (two scenarios) of the block's [entries x TPB
+    // scenarios] slab and walks down the zero runs -- the first half of the CTA the runs [0, zrun_split), the second half the
+    // rest -- so a warp instruction stores 512 contiguous bytes.  The zero entries are disjoint from the table's entries, so
+    // no ordering is needed, and the stores are DRIPPED: a few at a time between the stages of the solve (`drip(k)` resumes
+    // where the previous call stopped).  Issued in one burst -- before or behind the solve -- a warp sits on the back-pressure
+    // of a saturated DRAM for ~20 us while its own arithmetic waits (profiles/r2_fast_v3_*): the step took solve + stores,
+    // 0.071 ms; spread over the solve the stores ride along.
+    constexpr int CPR = TPB / 2;                                     // 16-byte chunks per entry row of the slab
+    const int z_half = tid / CPR;
+    const int64_t z_sv = blk * TPB + 2 * (tid % CPR);
+    int z_run = z_half == 0 ? 0 : ax.zrun_split;                     // current run, rows left in it, next row's address
+    const int z_end = z_half == 0 ? ax.zrun_split : ax.n_zrun;
+    int z_left = 0;
+    double* z_ptr = a.ze1;
+    if (!(zvec && z_sv < a.S) || H > 1) z_run = z_end;      // (H > 1: the helper groups share the zero rows, below)
+    auto drip = [&](int budget) {
+      while (budget > 0) {
+        if (z_left == 0) {
+          if (z_run >= z_end) return;
+          z_ptr = a.ze1 + z_sv + (int64_t)zs[2 * z_run] * LD;
+          z_left = zs[2 * z_run + 1];
+          ++z_run;
+        }
+        const int k = z_left < budget ? z_left : budget;
+#pragma unroll 4
+        for (int c = k; c > 0; --c, z_ptr += LD) __stcs(reinterpret_cast<double2*>(z_ptr), make_double2(0.0, 0.0));
+        z_left -= k;
+        budget -= k;
+      }
+    };
+    const bool zero_first = H == 1 && dense && !zvec && (((tid >> 5) + (int)blk) & 1);
+    if (hq == 0) {
     // ---- inputs: parameters p = [xbar0 | e0] and the hint words (coalesced: lane = scenario)
     double w[2 * BK::NCOL2];                               // w = [1 | p | |p| | general atoms] (+ a zero pad)
     w[0] = 1.0;
@@ -159,47 +215,6 @@ __global__ void __launch_bounds__(TPB, fast_ctas_per_sm(TPB))
       __syncthreads();
       staged = true;
     }
-    // ---- zero runs of the dense tube: odd warps before the solve, even warps behind it
-    auto zero_runs = [&]() {
-      double* base = a.ze1 + s;
-#pragma unroll 1
-      for (int r = 0; r < ax.n_zrun; ++r) {
-        double* ptr = base + (int64_t)zs[2 * r] * LD;
-#pragma unroll 4
-        for (int c = zs[2 * r + 1]; c > 0; --c, ptr += LD) __stcs(ptr, 0.0);
-      }
-    };
-    // Vector form (16-byte aligned rows): a thread keeps a 16-byte chunk (two scenarios) of the block's [entries x TPB
-    // scenarios] slab and walks down the zero runs -- the first half of the CTA the runs [0, zrun_split), the second half the
-    // rest -- so a warp instruction stores 512 contiguous bytes.  The zero entries are disjoint from the table's entries, so
-    // no ordering is needed, and the stores are DRIPPED: a few at a time between the stages of the solve (`drip(k)` resumes
-    // where the previous call stopped).  Issued in one burst -- before or behind the solve -- a warp sits on the back-pressure
-    // of a saturated DRAM for ~20 us while its own arithmetic waits (profiles/r2_fast_v3_*): the step took solve + stores,
-    // 0.071 ms; spread over the solve the stores ride along.
-    constexpr int CPR = TPB / 2;                                     // 16-byte chunks per entry row of the slab
-    const int z_half = tid / CPR;
-    const int64_t z_sv = blk * TPB + 2 * (tid % CPR);
-    int z_run = z_half == 0 ? 0 : ax.zrun_split;                     // current run, rows left in it, next row's address
-    const int z_end = z_half == 0 ? ax.zrun_split : ax.n_zrun;
-    int z_left = 0;
-    double* z_ptr = a.ze1;
-    if (!(zvec && z_sv < a.S)) z_run = z_end;
-    auto drip = [&](int budget) {
-      while (budget > 0) {
-        if (z_left == 0) {
-          if (z_run >= z_end) return;
-          z_ptr = a.ze1 + z_sv + (int64_t)zs[2 * z_run] * LD;
-          z_left = zs[2 * z_run + 1];
-          ++z_run;
-        }
-        const int k = z_left < budget ? z_left : budget;
-#pragma unroll 4
-        for (int c = k; c > 0; --c, z_ptr += LD) __stcs(reinterpret_cast<double2*>(z_ptr), make_double2(0.0, 0.0));
-        z_left -= k;
-        budget -= k;
-      }
-    };
-    const bool zero_first = dense && !zvec && (((tid >> 5) + (int)blk) & 1);
     if (zero_first && live) zero_runs();
     drip(24);
 
@@ -226,8 +241,6 @@ __global__ void __launch_bounds__(TPB, fast_ctas_per_sm(TPB))
     unsigned long long code[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) code[g] = hw[g] & ~(kCodeValid | kCodeFresh);
-    enum { kDefer = -2 };
-    int status = kDefer;
     if (!finite) status = TZ_STATUS_NONFINITE;
     else if (!param_ok) status = TZ_STATUS_INFEASIBLE;
     Cert2Result res;
@@ -250,10 +263,9 @@ __global__ void __launch_bounds__(TPB, fast_ctas_per_sm(TPB))
       const int slot = atomicAdd(a.defer, 1);
       if (slot >= 0 && slot < (a.S + kDeferTile - 1) / kDeferTile) a.defer_list[slot] = (int32_t)(s / kDeferTile);
     }
-    const bool emit = live && !deferred;
-    const bool good = status == TZ_STATUS_OK;
+    emit = live && !deferred;
+    good = status == TZ_STATUS_OK;
     drip(16);
-    double nrm2 = 0.0, cost = NAN;
     if (emit) {
       // ---- hints: rows [0, G) the active set for the next step, rows [G, 2G) the active set of the run's first step
 #pragma unroll
@@ -269,7 +281,6 @@ __global__ void __launch_bounds__(TPB, fast_ctas_per_sm(TPB))
         hint_w[(int64_t)g * LD + s] = wnext;
       }
       // ---- om = [1 | v | p | centre of Ze[1]]
-      double omr[NW];
       omr[0] = 1.0;
 #pragma unroll
       for (int j = 0; j < NZ; ++j) omr[BK::OM_V + j] = (j < nv) ? (good ? pg.D[j] * res.x[j] : NAN) : 0.0;
@@ -288,21 +299,56 @@ __global__ void __launch_bounds__(TPB, fast_ctas_per_sm(TPB))
         om[BK::OM_C + r][tid] = acc;
       }
       drip(16);
-      // (sm.om columns are thread-private: no barrier)
+    }
+    if constexpr (H > 1) sflag[tid] = (emit ? 1 : 0) | (good ? 2 : 0);
+    } else {
+      if (!staged) {                                       // helper groups: the staging barrier of the CTA
+        cp_async_wait<0>();
+        __syncthreads();
+        staged = true;
+      }
+      // while group 0 solves, the helper groups store the structural zeros of the block (whole runs each; the zeros do not
+      // depend on the solve, and a deferred tile is rewritten by step_kernel anyway)
+      if (dense && live) {
+        double* base = a.ze1 + s;
+#pragma unroll 1
+        for (int r = hq - 1; r < ax.n_zrun; r += H - 1) {
+          double* ptr = base + (int64_t)zs[2 * r] * LD;
+#pragma unroll 4
+          for (int c = zs[2 * r + 1]; c > 0; --c, ptr += LD) __stcs(ptr, 0.0);
+        }
+      }
+    }
+    if constexpr (H > 1) {
+      __syncthreads();                                     // om and the flags of the block are complete
+      if (hq > 0) {
+        const int f = sflag[tid];
+        emit = (f & 1) != 0;
+        good = (f & 2) != 0;
+        if (emit) {
+#pragma unroll
+          for (int j = 0; j < NW; ++j) omr[j] = omc[j * TPB];
+        }
+      }
+    }
+    if (emit) {
+      // (H == 1: om columns are thread-private, no barrier)
       // ---- Ze[1].Z at the optimum (examples/2.pulley_sim.py:96): the entries of the term table
       if (a.ze1 != nullptr) {
         double* base = a.ze1 + s;
         if (sp.tube_packed) {
-          double* ptr = base;
+          double* ptr = base + (int64_t)hq * LD;
 #pragma unroll 4
-          for (int i = 0; i < ax.n_nz; ++i, ptr += LD) {
+          for (int i = hq; i < ax.n_nz; i += H, ptr += H * LD) {
             const double2 e = tt[i];
             __stcs(ptr, e.x * omc[(int)(__double_as_longlong(e.y) & 0xffffffffll) * TPB]);
           }
         } else {
-          if (!zero_first && !zvec) zero_runs();
+          if constexpr (H == 1) {
+            if (!zero_first && !zvec) zero_runs();
+          }
 #pragma unroll 4
-          for (int i = 0; i < ax.n_nz; ++i) {
+          for (int i = hq; i < ax.n_nz; i += H) {
             const double2 e = tt[i];
             const long long ie = __double_as_longlong(e.y);
             __stcs(base + (ie >> 32) * LD, e.x * omc[(int)(ie & 0xffffffffll) * TPB]);
@@ -321,21 +367,36 @@ __global__ void __launch_bounds__(TPB, fast_ctas_per_sm(TPB))
         if (a.xbar_traj != nullptr) a.xbar_traj[(int64_t)i * LD + s] = acc;
         return acc;
       };
-      if (a.xbar_traj != nullptr) {
+      if constexpr (H == 1) {
+        if (a.xbar_traj != nullptr) {
 #pragma unroll 2
-        for (int i = 0; i < n; ++i) (void)xb_row(i);
-      }
-      drip(16);
-      if (a.xbar_traj != nullptr || closed) {
+          for (int i = 0; i < n; ++i) (void)xb_row(i);
+        }
+        drip(16);
+        if (a.xbar_traj != nullptr || closed) {
 #pragma unroll
-        for (int k = 0; k < HP; ++k)
-          if (k < n) xb1[k] = xb_row(n + k);
-      }
-      drip(16);
-      if (a.xbar_traj != nullptr) {
+          for (int k = 0; k < HP; ++k)
+            if (k < n) xb1[k] = xb_row(n + k);
+        }
+        drip(16);
+        if (a.xbar_traj != nullptr) {
 #pragma unroll 2
-        for (int i = 2 * n; i < (ax.N + 1) * n; ++i) (void)xb_row(i);
+          for (int i = 2 * n; i < (ax.N + 1) * n; ++i) (void)xb_row(i);
+        }
+      } else {
+        // rows [n, 2n) (xbar_1: needed by the update) stay with group 0, the others are shared by the helper groups
+        if (hq == 0 && (a.xbar_traj != nullptr || closed)) {
+#pragma unroll
+          for (int k = 0; k < HP; ++k)
+            if (k < n) xb1[k] = xb_row(n + k);
+        }
+        if (a.xbar_traj != nullptr && hq > 0) {
+#pragma unroll 1
+          for (int i = hq - 1; i < (ax.N + 1) * n; i += H - 1)
+            if (i < n || i >= 2 * n) (void)xb_row(i);
+        }
       }
+      if (hq == 0) {
       if (a.v != nullptr)
         for (int j = 0; j < nv; ++j) a.v[(int64_t)j * LD + s] = omc[(BK::OM_V + j) * TPB];
       if (a.status) a.status[s] = status;
@@ -387,10 +448,11 @@ __global__ void __launch_bounds__(TPB, fast_ctas_per_sm(TPB))
           }
         }
       }
+      }      // hq == 0
     }
     drip(1 << 20);      // whatever is left of this thread's share of the zero entries (every thread: the shares cover other lanes' scenarios)
     // ---- closed-loop statistics: warp reduction, one atomic per statistic and warp
-    if (a.stats != nullptr && closed) {
+    if (a.stats != nullptr && closed && hq == 0) {
       const bool eg = emit && good;
       double s0 = eg ? sqrt(nrm2) : 0.0, s1 = eg ? nrm2 : 0.0, s2 = eg ? cost : 0.0;
 #pragma unroll
@@ -411,6 +473,7 @@ __global__ void __launch_bounds__(TPB, fast_ctas_per_sm(TPB))
         atomicAdd(a.stats + 7, (double)__popc(bem));
       }
     }
+    if constexpr (H > 1) __syncthreads();                  // the helper groups are done with om before the next block overwrites it
   }
   if (!staged) cp_async_wait<0>();
 }
@@ -422,26 +485,26 @@ size_t fast_slot_bytes(const TzProgram* p) {
 
 // CTAs of `tpb` threads that are resident on one SM: registers (launch bounds) and shared memory (227 KB, 1 KB per CTA reserved)
 template <class BK>
-int fast_resident(const TzProgram* p, int tpb, int nslot) {
-  const size_t per_cta = (nslot > 1 ? nslot : 1) * fast_slot_bytes<BK>(p) + sizeof(double) * (BK::NW + 3 * (BK::NPAR / 2)) * tpb + 1024;
+int fast_resident(const TzProgram* p, int tpb, int nslot, int h = 1) {
+  const size_t per_cta = (nslot > 1 ? nslot : 1) * fast_slot_bytes<BK>(p) + sizeof(double) * (BK::NW + 3 * (BK::NPAR / 2)) * tpb + 4 * tpb + 1024;
   const int by_smem = (int)((size_t)227 * 1024 / per_cta);
-  const int by_regs = fast_ctas_per_sm(tpb);
+  const int by_regs = fast_ctas_per_sm(tpb * h);
   return by_smem < by_regs ? (by_smem > 0 ? by_smem : 1) : by_regs;
 }
 
-template <class BK, int TPB, int NSLOT>
+template <class BK, int TPB, int NSLOT, int H = 1>
 int launch_fast_tpb(const TzProgram* p, const SolverParams& sp, const StepArgs& a, const SetEntry* entries, const int32_t* tile_prog,
                     cudaStream_t st) {
   const size_t slot = fast_slot_bytes<BK>(p);
-  constexpr size_t om_bytes = sizeof(double) * (BK::NW + 3 * (BK::NPAR / 2)) * TPB;
+  constexpr size_t om_bytes = sizeof(double) * (BK::NW + 3 * (BK::NPAR / 2)) * TPB + sizeof(int) * TPB;      // om + the H > 1 flags
   const size_t smem = (NSLOT > 1 ? NSLOT : 1) * slot + om_bytes;
   static std::atomic<unsigned long long> configured{0ull};
   const size_t smem_max = (NSLOT > 1 ? NSLOT : 1) * (((sizeof(QpProg<BK>) + 15) & ~(size_t)15) + kMaxTabBytes) + om_bytes;
-  if (const int rc = ensure_dynamic_smem(fast_step_kernel<BK, TPB, NSLOT>, (int)smem_max, p->device, configured)) return rc;
+  if (const int rc = ensure_dynamic_smem(fast_step_kernel<BK, TPB, NSLOT, H>, (int)smem_max, p->device, configured)) return rc;
   const int64_t nblk = (a.S + TPB - 1) / TPB;
-  const int64_t wave = (int64_t)p->num_sms * fast_resident<BK>(p, TPB, NSLOT);
+  const int64_t wave = (int64_t)p->num_sms * fast_resident<BK>(p, TPB, NSLOT, H);
   const unsigned grid = (unsigned)(NSLOT == 0 ? (nblk < wave ? nblk : wave) : nblk);
-  TZ_CUDA(launch_kernel(fast_step_kernel<BK, TPB, NSLOT>, grid, TPB, smem, st, pdl_enabled(a.S),
+  TZ_CUDA(launch_kernel(fast_step_kernel<BK, TPB, NSLOT, H>, grid, TPB * H, smem, st, pdl_enabled(a.S),
                         reinterpret_cast<const QpProg<BK>*>(p->packed_dev), p->aux, sp, a, entries, tile_prog, (int)slot));
   return TZ_OK;
 }
@@ -468,6 +531,16 @@ int launch_fast(const TzProgram* p, const SolverParams& sp, const StepArgs& a, c
         if (load < best) { best = load; tpb = t; }
       }
     }
+  }
+  // helper groups (H = 2: a second thread per scenario stores the zeros while the first one solves, then both share the tube
+  // and trajectory rows): 8,192 scenarios 0.0298 -> 0.0232 ms per step, 16,384: 0.0322 -> 0.0272, 32,768: no gain (0.0394
+  // against 0.0383) -- below one scenario per two thread slots of the chip the step is one warp's latency, above it the
+  // helpers take issue slots from other scenarios' solves
+  int h = (tpb == 64 && a.S <= (int64_t)p->num_sms * 128) ? 2 : 1;
+  if (const char* e = getenv("TZDDPC_FAST_H")) h = atoi(e);        // tuning knob: helper groups per scenario
+  if (h > 1) {
+    if (tpb == 64 && h == 2) return launch_fast_tpb<BK, 64, 0, 2>(p, sp, a, nullptr, nullptr, st);
+    if (tpb == 64 && h == 4) return launch_fast_tpb<BK, 64, 0, 4>(p, sp, a, nullptr, nullptr, st);
   }
   switch (tpb) {
     case 256: return launch_fast_tpb<BK, 256, 0>(p, sp, a, nullptr, nullptr, st);
