@@ -910,7 +910,7 @@ def main():
     ap.add_argument("--polish", type=int, default=3, help="augmented-Lagrangian iterations of the certificate / polish")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--e2e-chunks", type=int, default=2)
-    ap.add_argument("--e2e-chunks-resident", type=int, default=4)
+    ap.add_argument("--e2e-chunks-resident", type=int, default=2)
     ap.add_argument("--regime-steps", type=int, default=200, help="length of the long window of the `regimes` leg (0 = skip)")
     ap.add_argument("--datasets", type=int, default=4096, help="data sets of the data-set-axis leg (0 = skip)")
     ap.add_argument("--cpu-scen", type=int, default=48, help="scenarios per core of the CPU baseline")
