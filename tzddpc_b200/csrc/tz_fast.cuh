@@ -52,6 +52,9 @@ constexpr int fast_ctas_per_sm(int tpb) { return tpb >= 512 ? 1 : 512 / tpb; }
 // behind a CTA barrier all H groups share the tube entries and trajectory rows of the block's scenarios, read from om.
 // Per-scenario arithmetic is the same expressions on the same operands: results do not depend on H.
 // (First version: zeros split row-wise within every run, behind the barrier: 17 instructions per store, no gain.)
+// (Measured and dropped, round 2 again: the zeros as bulk copies -- cp.async.bulk shared -> global of a TPB * 8-byte block
+// of zeros, one 2 KB copy per zero row and CTA block, issued by the block's threads a row each, either all behind the
+// staging barrier or spread over the drip sites: 0.072-0.073 ms against 0.060-0.061 with the dripped 16-byte stores.)
 template <class BK, int TPB, int NSLOT, int H = 1>
 __global__ void __launch_bounds__(TPB * H, fast_ctas_per_sm(TPB * H))
     fast_step_kernel(const QpProg<BK>* __restrict__ gpg, const Aux ax, const SolverParams sp, const StepArgs a,
@@ -123,7 +126,10 @@ __global__ void __launch_bounds__(TPB * H, fast_ctas_per_sm(TPB * H))
   const double2* tt = reinterpret_cast<const double2*>(tabd + ax.o_tt);      // term table: (coef, idx | ent << 32)
   const int* zs = reinterpret_cast<const int*>(tabd + ax.o_zrun);           // zero runs: (first row, length) pairs
   // 16-byte zero stores need 16-byte aligned rows and an even batch (a pair of scenarios is in or out together)
-  const bool zvec = dense && (reinterpret_cast<uintptr_t>(a.ze1) & 15u) == 0 && (a.ld & 1) == 0 && (a.S & 1) == 0;
+  // (... and a row offset in bytes that fits 32 bits, for the one-instruction address)
+  const bool zvec = dense && (reinterpret_cast<uintptr_t>(a.ze1) & 15u) == 0 && (a.ld & 1) == 0 && (a.S & 1) == 0 &&
+                    (int64_t)(ax.n * (1 + ax.g1)) * a.ld * 8 < (int64_t)0x7fffffff;
+  const int* zrow = reinterpret_cast<const int*>(tabd + ax.o_zrow);         // the zero rows as a flat list, two padded halves
   const int64_t nblk = (a.S + TPB - 1) / TPB;
   const unsigned long long* hint = reinterpret_cast<const unsigned long long*>(a.warm);
   unsigned long long* hint_w = reinterpret_cast<unsigned long long*>(a.warm);
@@ -150,33 +156,33 @@ __global__ void __launch_bounds__(TPB * H, fast_ctas_per_sm(TPB * H))
       }
     };
     // Vector form (16-byte aligned rows): a thread keeps a 16-byte chunk (two scenarios) of the block's [entries x TPB
-    // scenarios] slab and walks down the zero runs -- the first half of the CTA the runs [0, zrun_split), the second half the
-    // rest -- so a warp instruction stores 512 contiguous bytes.  The zero entries are disjoint from the table's entries, so
-    // no ordering is needed, and the stores are DRIPPED: a few at a time between the stages of the solve (`drip(k)` resumes
-    // where the previous call stopped).  Issued in one burst -- before or behind the solve -- a warp sits on the back-pressure
-    // of a saturated DRAM for ~20 us while its own arithmetic waits (profiles/r2_fast_v3_*): the step took solve + stores,
-    // 0.071 ms; spread over the solve the stores ride along.
+    // scenarios] slab and walks down the flat list of zero rows -- the first half of the CTA the first half of the list, the
+    // second half the rest -- so a warp instruction stores 512 contiguous bytes.  The zero entries are disjoint from the
+    // table's entries, so no ordering is needed, and the stores are DRIPPED: a few at a time between the stages of the solve
+    // (`drip(k)`, k a multiple of 4, resumes where the previous call stopped).  Issued in one burst -- before or behind the
+    // solve -- the step took solve + stores, 0.071 ms (profiles/r2_fast_v3_*); spread over the solve the stores ride along.
+    // Four rows per trip: one 16-byte load of four row indices, one IMAD.WIDE per address (row * 8 ld fits 32 bits: zvec),
+    // no remainder code (the list is padded to a multiple of 4) -- ~3 instructions per store where walking the (first row,
+    // length) runs, 8 rows long on average, took 11 and made the dense step 74 % longer in instructions than the packed one.
     constexpr int CPR = TPB / 2;                                     // 16-byte chunks per entry row of the slab
     const int z_half = tid / CPR;
     const int64_t z_sv = blk * TPB + 2 * (tid % CPR);
-    int z_run = z_half == 0 ? 0 : ax.zrun_split;                     // current run, rows left in it, next row's address
-    const int z_end = z_half == 0 ? ax.zrun_split : ax.n_zrun;
-    int z_left = 0;
-    double* z_ptr = a.ze1;
-    if (!(zvec && z_sv < a.S) || H > 1) z_run = z_end;      // (H > 1: the helper groups share the zero rows, below)
+    int z_pos = z_half * ax.n_zrow_half;                             // next entry of the zero-row list
+    const int z_stop = z_pos + ax.n_zrow_half;
+    if (!(zvec && z_sv < a.S) || H > 1) z_pos = z_stop;              // (H > 1: the helper groups store the zero rows)
+    char* const z_base = reinterpret_cast<char*>(a.ze1 + z_sv);
+    const int ld8 = (int)(LD * 8);
     auto drip = [&](int budget) {
-      while (budget > 0) {
-        if (z_left == 0) {
-          if (z_run >= z_end) return;
-          z_ptr = a.ze1 + z_sv + (int64_t)zs[2 * z_run] * LD;
-          z_left = zs[2 * z_run + 1];
-          ++z_run;
-        }
-        const int k = z_left < budget ? z_left : budget;
-#pragma unroll 4
-        for (int c = k; c > 0; --c, z_ptr += LD) __stcs(reinterpret_cast<double2*>(z_ptr), make_double2(0.0, 0.0));
-        z_left -= k;
-        budget -= k;
+      int k = z_stop - z_pos;
+      k = k < budget ? k : budget;
+#pragma unroll 2
+      for (; k > 0; k -= 4, z_pos += 4) {
+        const int4 r = *reinterpret_cast<const int4*>(zrow + z_pos);
+        const double2 z2 = make_double2(0.0, 0.0);
+        __stcs(reinterpret_cast<double2*>(z_base + (int64_t)r.x * ld8), z2);
+        __stcs(reinterpret_cast<double2*>(z_base + (int64_t)r.y * ld8), z2);
+        __stcs(reinterpret_cast<double2*>(z_base + (int64_t)r.z * ld8), z2);
+        __stcs(reinterpret_cast<double2*>(z_base + (int64_t)r.w * ld8), z2);
       }
     };
     const bool zero_first = H == 1 && dense && !zvec && (((tid >> 5) + (int)blk) & 1);

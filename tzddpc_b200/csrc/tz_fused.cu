@@ -287,7 +287,28 @@ static int build_program_host(const TzProgramDesc* d, TzProgram* p, HostImage& i
     for (int v : zlen) total += v;
     while (zrun_split < (int)zlen.size() && 2 * acc < total) acc += zlen[zrun_split++];
   }
-  const size_t ndbl = o_zrun + zstart.size(), nint = ent.size() + idx.size();
+  // ... and once more as a flat list of rows in two halves (fast_step_kernel: the two halves of a CTA, 16-byte index loads)
+  std::vector<int32_t> zrow;
+  int n_zrow_half = 0;
+  {
+    std::vector<int32_t> all;
+    for (size_t i = 0; i < zstart.size(); ++i)
+      for (int c = 0; c < zlen[i]; ++c) all.push_back(zstart[i] + c);
+    const size_t h0 = (all.size() + 1) / 2, h1 = all.size() - h0;
+    n_zrow_half = (int)((std::max(h0, h1) + 3) & ~(size_t)3);
+    if (h1 == 0) n_zrow_half = all.empty() ? 0 : n_zrow_half;
+    zrow.assign((size_t)2 * n_zrow_half, 0);
+    for (int half = 0; half < 2 && !all.empty(); ++half) {
+      const size_t b = half == 0 ? 0 : h0, cnt = half == 0 ? h0 : h1;
+      for (int k = 0; k < n_zrow_half; ++k) {
+        // (an empty second half repeats the first half's last row: storing a zero twice is harmless)
+        const size_t src = cnt == 0 ? h0 - 1 : b + std::min((size_t)k, cnt - 1);
+        zrow[(size_t)half * n_zrow_half + k] = all[src];
+      }
+    }
+  }
+  const size_t o_zrow = (o_zrun + zstart.size() + 1) & ~(size_t)1;
+  const size_t ndbl = o_zrow + (size_t)n_zrow_half, nint = ent.size() + idx.size();
   const size_t smem_tab = (ndbl + (size_t)n * n + (size_t)n * d->m) * sizeof(double) + nint * sizeof(int32_t);
   if (smem_tab > kMaxTabBytes) {
     return fail(TZ_ERANGE, "program tables need %zu bytes of shared memory (limit %d)", smem_tab, kMaxTabBytes);
@@ -311,6 +332,7 @@ static int build_program_host(const TzProgramDesc* d, TzProgram* p, HostImage& i
     const int32_t pr[2] = {zstart[i], zlen[i]};
     std::memcpy(&hd[o_zrun + i], pr, sizeof(pr));
   }
+  if (!zrow.empty()) std::memcpy(&hd[o_zrow], zrow.data(), zrow.size() * sizeof(int32_t));
   Aux& ax = p->aux;
   ax.tab = nullptr;                      // (set when the tables are uploaded)
   ax.n_dbl = (int)ndbl; ax.n_int = (int)nint;
@@ -318,6 +340,7 @@ static int build_program_host(const TzProgramDesc* d, TzProgram* p, HostImage& i
   ax.o_ent = 0; ax.o_idx = (int)ent.size();
   ax.o_tt = (int)o_tt; ax.o_zrun = (int)o_zrun; ax.n_zrun = (int)zstart.size();
   ax.zrun_split = zrun_split;
+  ax.o_zrow = (int)o_zrow; ax.n_zrow_half = n_zrow_half;
   ax.n_nz = (int)ent.size();
   p->tube_ent = ent;
   ax.n = n; ax.m = d->m; ax.N = d->horizon; ax.nv = d->nv; ax.g1 = d->g1;
@@ -595,7 +618,7 @@ extern "C" int tz_program_set_create(const TzProgram* const* progs, int32_t npro
     TZ_REQUIRE(p->bucket != 4, "programs of the generic large-program path cannot be combined into a set");
     TZ_REQUIRE(p->bucket == p0->bucket && p->smem_tab == p0->smem_tab && a.n_dbl == b.n_dbl && a.n_int == b.n_int &&
                a.o_XB == b.o_XB && a.o_CZ == b.o_CZ && a.o_K == b.o_K && a.o_coef == b.o_coef && a.o_ent == b.o_ent &&
-               a.o_idx == b.o_idx && a.o_tt == b.o_tt && a.o_zrun == b.o_zrun && a.n_zrun == b.n_zrun && a.zrun_split == b.zrun_split && a.n_nz == b.n_nz && a.n == b.n && a.m == b.m && a.N == b.N && a.nv == b.nv && a.g1 == b.g1,
+               a.o_idx == b.o_idx && a.o_tt == b.o_tt && a.o_zrun == b.o_zrun && a.n_zrun == b.n_zrun && a.zrun_split == b.zrun_split && a.o_zrow == b.o_zrow && a.n_zrow_half == b.n_zrow_half && a.n_nz == b.n_nz && a.n == b.n && a.m == b.m && a.N == b.N && a.nv == b.nv && a.g1 == b.g1,
                "program %d does not have the structure of program 0 (bucket / table sizes differ)", j);
     TZ_REQUIRE(p->tube_ent == p0->tube_ent, "program %d: Ze[1] has a different sparsity pattern than program 0", j);
     const int64_t cnt = begin[j + 1] - begin[j];

@@ -33,6 +33,8 @@ struct Aux {
   int o_tt;                        // (doubles, even) term table of fast_step_kernel: n_nz pairs (coef, bits of idx | ent << 32)
   int o_zrun, n_zrun;              // (doubles) zero runs of the dense Ze[1].Z between its non-zero entries: int32 pairs (first row, length)
   int zrun_split;                  // runs [0, zrun_split) hold about half of the zero entries (the two halves of a CTA share the zero-fill)
+  int o_zrow, n_zrow_half;         // (doubles, even) the zero rows as a flat int32 list in two halves of n_zrow_half entries (a
+                                   // multiple of 4: each half padded by repeating its last row), for 16-byte index loads
   int n_nz;                        // entries of Ze[1].Z that are not structurally zero (centre column included)
   int n, m, N, nv, g1;
 };
