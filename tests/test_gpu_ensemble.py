@@ -257,3 +257,30 @@ def test_program_set_over_several_rounds(cuda_lib, per):
         for k in ("x", "xbar", "e", "u", "v", "cost", "status"):
             np.testing.assert_array_equal(r[k][:, sl], rd[k], err_msg=f"{k}, data set {d}")
     assert (r["status"] == 0).mean() > 0.9
+
+
+@pytest.mark.parametrize("per", [16, 32, 64, 48])       # two program slots per warp / one program per 32- and 64-scenario CTA / mixed
+def test_program_set_hot_path_with_and_without_helper_groups(cuda_lib, per, monkeypatch):
+    """fast_step_kernel over a program set: the helper group of the small-block kernels (TZDDPC_FAST_SET_H, csrc/tz_fast.cuh)
+    changes nothing in the results, and both equal the per-data-set controllers bit for bit."""
+    import tzddpc_b200 as tz
+    cfg = configs.CONFIGS["pulley"]()
+    D, steps = 18, 8
+    ctls, _ = _controllers(cfg, D)
+    ens = tz.TZDDPCEnsemble(ctls, per)
+    S = D * per
+    x0 = np.tile(np.asarray(cfg.X0[0], dtype=np.float64), (S, 1))
+    x0 += 0.01 * np.random.default_rng(4).standard_normal(x0.shape)
+    opts = tz.SolverOptions(warm_start=2, hot_path=1)
+    runs = {}
+    for h in ("1", "2"):
+        monkeypatch.setenv("TZDDPC_FAST_SET_H", h)
+        runs[h] = ens.simulate(cfg.A, cfg.B, x0, steps=steps, seed=5, options=opts, restart=True, keep_tubes=True)
+    for k in ("x", "xbar", "e", "u", "v", "cost", "status", "tubes"):
+        np.testing.assert_array_equal(runs["1"][k], runs["2"][k], err_msg=k)
+    monkeypatch.delenv("TZDDPC_FAST_SET_H")
+    for d in (0, 7, D - 1):
+        sl = slice(d * per, (d + 1) * per)
+        rd = ctls[d].simulate(cfg.A, cfg.B, x0[sl], steps=steps, seed=5, options=opts, restart=True, scenario_offset=d * per, keep_tubes=True)
+        for k in ("x", "u", "cost", "status", "tubes"):
+            np.testing.assert_array_equal(runs["2"][k][:, sl], rd[k], err_msg=f"{k}, data set {d}")

@@ -46,6 +46,30 @@ def test_hot_path_equals_the_admm_kernel_bitwise(pair, S, packed):
     assert (hot["stats"][:, 7] == S).all()
 
 
+@pytest.mark.parametrize("knobs", [dict(TZDDPC_FAST_TPB="32"), dict(TZDDPC_FAST_TPB="64", TZDDPC_FAST_H="1"),
+                                   dict(TZDDPC_FAST_TPB="64", TZDDPC_FAST_H="2"), dict(TZDDPC_FAST_TPB="64", TZDDPC_FAST_H="4"),
+                                   dict(TZDDPC_FAST_TPB="128"), dict(TZDDPC_FAST_TPB="256"), dict(TZDDPC_PDL="2"), dict(TZDDPC_PDL="0")])
+@pytest.mark.parametrize("packed", [0, 1])
+def test_results_do_not_depend_on_the_launch_shape(pair, knobs, packed, monkeypatch):
+    """CTA size, helper groups per scenario and programmatic dependent launch (the diagnostic knobs of csrc/tz_fast.cuh and
+    csrc/tz_common.cuh, read per launch) change how the scenarios are laid over threads, never a scenario's arithmetic."""
+    import tzddpc_b200 as tz
+    cfg, o, t = pair
+    S = 1000 + 2 * packed                         # ragged last block; even: the 16-byte zero stores are in play
+    rng = np.random.default_rng(55)
+    steps = min(cfg.steps, 14)
+    noise = common.noise_for(cfg, steps, S, rng)
+    x0 = np.tile(np.asarray(cfg.X0[0], dtype=np.float64), (S, 1))
+    opts = tz.SolverOptions(warm_start=2, hot_path=1, tube_packed=packed)
+    for k in ("TZDDPC_FAST_TPB", "TZDDPC_FAST_H", "TZDDPC_PDL"):
+        monkeypatch.delenv(k, raising=False)
+    ref = t.simulate(cfg.A, cfg.B, x0, noise, keep_tubes=True, restart=True, options=opts)
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    got = t.simulate(cfg.A, cfg.B, x0, noise, keep_tubes=True, restart=True, options=opts)
+    _same(got, ref, f"{knobs} packed={packed}")
+
+
 def test_hot_path_matches_the_oracle_closed_loop(pair):
     import tzddpc_b200 as tz
     cfg, o, t = pair
