@@ -74,6 +74,9 @@ __global__ void __launch_bounds__(TPB * H, fast_ctas_per_sm(TPB * H))
   // shared memory: NSLOT (or one) x [QpProg | tables | A_true | B_true], then om[KOM][TPB]
   double (*om)[TPB] = reinterpret_cast<double (*)[TPB]>(smem_raw + (NSLOT > 1 ? NSLOT : 1) * (size_t)slot_bytes);
   int* sflag = reinterpret_cast<int*>(&om[NW + 3 * HP][0]);                 // H > 1: (emit | good << 1) per scenario of the block
+  // tables staged per slot: with helper groups the flat zero-row list (the tail of the tables, 2 KB) is not used -- the
+  // helpers walk the runs -- and stays in global memory: the two-slot set kernel then fits 5 CTAs on an SM instead of 4
+  const int n_tab = H > 1 ? ax.o_zrow : ax.n_dbl;
   // ---- stage a program and its tables into a slot (cp.async, all in flight at once)
   auto stage = [&](unsigned char* slot, const void* pg_src, const double* tab_src) {
     const char* src = reinterpret_cast<const char*>(pg_src);
@@ -82,13 +85,13 @@ __global__ void __launch_bounds__(TPB * H, fast_ctas_per_sm(TPB * H))
     constexpr int NCH = (int)(sizeof(QpProg<BK>) / 16);
     for (int i = tix; i < NCH; i += NT) cp_async16(dst + 16 * i, src + 16 * i);
     if (tix == 0 && (sizeof(QpProg<BK>) % 16) != 0) cp_async8(dst + 16 * NCH, src + 16 * NCH);
-    for (int i = tix; i < ax.n_dbl; i += NT) cp_async8(td + i, tab_src + i);
+    for (int i = tix; i < n_tab; i += NT) cp_async8(td + i, tab_src + i);
   };
   auto stage_plant = [&](unsigned char* slot) {              // (caller-owned arrays: behind pdl_wait)
     double* td = reinterpret_cast<double*>(slot + QPB);
     if (closed) {
-      for (int i = tix; i < n * n; i += NT) cp_async8(td + ax.n_dbl + i, a.A_true + i);
-      for (int i = tix; i < n * m; i += NT) cp_async8(td + ax.n_dbl + n * n + i, a.B_true + i);
+      for (int i = tix; i < n * n; i += NT) cp_async8(td + n_tab + i, a.A_true + i);
+      for (int i = tix; i < n * m; i += NT) cp_async8(td + n_tab + n * n + i, a.B_true + i);
     }
   };
   pdl_trigger();
@@ -120,7 +123,7 @@ __global__ void __launch_bounds__(TPB * H, fast_ctas_per_sm(TPB * H))
   const double* sXB = tabd + ax.o_XB;
   const double* sCZ = tabd + ax.o_CZ;
   const double* sK = tabd + ax.o_K;
-  const double* sA = tabd + ax.n_dbl;
+  const double* sA = tabd + n_tab;
   const double* sB = sA + n * n;
   const double2* tt = reinterpret_cast<const double2*>(tabd + ax.o_tt);      // term table: (coef, idx | ent << 32)
   const int* zs = reinterpret_cast<const int*>(tabd + ax.o_zrun);           // zero runs: (first row, length) pairs
@@ -484,14 +487,18 @@ __global__ void __launch_bounds__(TPB * H, fast_ctas_per_sm(TPB * H))
 }
 
 template <class BK>
-size_t fast_slot_bytes(const TzProgram* p) {
-  return ((sizeof(QpProg<BK>) + 15) & ~(size_t)15) + p->smem_tab;
+size_t fast_slot_bytes(const TzProgram* p, int h = 1) {
+  const size_t qpb = (sizeof(QpProg<BK>) + 15) & ~(size_t)15;
+  if (h <= 1) return qpb + p->smem_tab;
+  // helper-group kernels: [tables up to the flat zero-row list | A_true | B_true]
+  const size_t tab = ((size_t)p->aux.o_zrow + (size_t)p->aux.n * p->aux.n + (size_t)p->aux.n * p->aux.m) * sizeof(double);
+  return qpb + ((tab + 15) & ~(size_t)15);
 }
 
 // CTAs of `tpb` threads that are resident on one SM: registers (launch bounds) and shared memory (227 KB, 1 KB per CTA reserved)
 template <class BK>
 int fast_resident(const TzProgram* p, int tpb, int nslot, int h = 1) {
-  const size_t per_cta = (nslot > 1 ? nslot : 1) * fast_slot_bytes<BK>(p) + sizeof(double) * (BK::NW + 3 * (BK::NPAR / 2)) * tpb + 4 * tpb + 1024;
+  const size_t per_cta = (nslot > 1 ? nslot : 1) * fast_slot_bytes<BK>(p, h) + sizeof(double) * (BK::NW + 3 * (BK::NPAR / 2)) * tpb + 4 * tpb + 1024;
   const int by_smem = (int)((size_t)227 * 1024 / per_cta);
   const int by_regs = fast_ctas_per_sm(tpb * h);
   return by_smem < by_regs ? (by_smem > 0 ? by_smem : 1) : by_regs;
@@ -500,7 +507,7 @@ int fast_resident(const TzProgram* p, int tpb, int nslot, int h = 1) {
 template <class BK, int TPB, int NSLOT, int H = 1>
 int launch_fast_tpb(const TzProgram* p, const SolverParams& sp, const StepArgs& a, const SetEntry* entries, const int32_t* tile_prog,
                     cudaStream_t st) {
-  const size_t slot = fast_slot_bytes<BK>(p);
+  const size_t slot = fast_slot_bytes<BK>(p, H);
   constexpr size_t om_bytes = sizeof(double) * (BK::NW + 3 * (BK::NPAR / 2)) * TPB + sizeof(int) * TPB;      // om + the H > 1 flags
   const size_t smem = (NSLOT > 1 ? NSLOT : 1) * slot + om_bytes;
   static std::atomic<unsigned long long> configured{0ull};
