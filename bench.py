@@ -615,7 +615,8 @@ def run_stress(args):
       rollout_order*     tz_tube_rollout: product + Minkowski sum + Girard reduction + hull per step with the zonotope resident
                          in shared memory (the fused path; rho <= 30 at n = 5);
       standalone_order*  tz_reach_step / tz_girard_reduce / tz_interval_hull on blocks of the same size: algorithmic bytes (read
-                         + written once) over the CUDA-event time, as a fraction of the measured HBM peak.
+                         + written once) over the CUDA-event time, as a fraction of the measured HBM peak;
+      chain_order40      the rollout at rho = 40 through the chain of stand-alone kernels (beyond the fused kernel's shared memory).
     `value` = scenario-steps/s of the fused rollout at rho = 20, all ranks."""
     import torch
     import torch.distributed as dist
@@ -687,6 +688,40 @@ def run_stress(args):
                                            "frac_hull": b_hull / t_hull / 1e6 / peak, "girard_GBps": b_gir / t_gir / 1e6,
                                            "generators_in": int(pre.shape[2] - 1), "zonotopes_per_gpu": Sz}
         del Z0, XU, Zin, pre
+    # ---- order 40 (configs[4] names rho = 10..40): the fused rollout keeps the pre-reduction block in shared memory and stops
+    # at order 30 for n = 5 (order 40 needs 278 KB); beyond that the same recursion runs through the chain of stand-alone
+    # kernels -- tz_reach_step (M_K x Ze and M_Delta x (x, u) + W), concatenation, tz_girard_reduce, tz_interval_hull per step
+    order = 40
+    gcap = n * (order - 1) + n
+    Sc = min(S, 4096)
+    Z0 = torch.zeros((Sc, n, 2), dtype=torch.float64, device=dev)
+    Z0[:, :, 0] = torch.rand((Sc, n), dtype=torch.float64, device=dev, generator=gen) - 0.5
+    XU = torch.rand((Sc, steps, n + m), dtype=torch.float64, device=dev, generator=gen) * 4 - 2
+    dA_, dGK_, dGD_, dW_ = f(A), f(GK), f(GD), f(W)
+    zeroC = torch.zeros((n, n + m), dtype=torch.float64, device=dev)
+    state = {}
+
+    def chain():
+        Z = Z0
+        for k in range(steps):
+            T1 = torch.ops.tzddpc.reach_step(dA_, dGK_, Z, None)
+            xu = torch.zeros((Sc, n + m, 2), dtype=torch.float64, device=dev)
+            xu[:, :, 0] = XU[:, k]
+            Zn = torch.ops.tzddpc.reach_step(zeroC, dGD_, xu, dW_)
+            pre = torch.cat([T1, Zn[:, :, 1:]], dim=2)
+            pre[:, :, 0] += Zn[:, :, 0]
+            red, gout = torch.ops.tzddpc.girard_reduce(pre, float(order), 0, gcap)
+            Z = red
+            lo, hi = torch.ops.tzddpc.interval_hull(Z)
+        state["gmax"], state["width"] = gout, hi - lo
+
+    ms = ev(chain, 1)
+    out["chain_order40"] = {"ms": ms, "scenario_steps_per_s": world * Sc * steps / ms * 1e3, "scenarios_per_gpu": Sc,
+                            "generators_after_reduction": int(state["gmax"].max().item()), "pre_reduce_generators": 26 * gcap + 25 + 30 + 1,
+                            "mean_tube_width_last_step": float(state["width"].mean().item()),
+                            "how": "reach_step x2 + cat + girard_reduce + interval_hull per step (stand-alone kernels; the fused rollout "
+                                   "stops at order 30)"}
+    del Z0, XU
     r20 = out["rollout_order20"]
     line = {"metric": "tube-rollout scenario-steps/s (synthetic stress: Girard order cap 20, horizon 32)", "value": r20["scenario_steps_per_s"],
             "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r20["ms"] / steps,
