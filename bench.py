@@ -291,12 +291,28 @@ class ClosedLoop:
                                   None if self.ablate >= 1 else self.ze1[r], None, self.iters[r], self.warm, self.stats[t], self.po)
 
 
+def _nvtx_push(torch, msg):
+    try:
+        torch.cuda.nvtx.range_push(msg)
+    except Exception:      # noqa: BLE001  (NVTX is an annotation, never a reason to fail)
+        pass
+
+
+def _nvtx_pop(torch):
+    try:
+        torch.cuda.nvtx.range_pop()
+    except Exception:      # noqa: BLE001
+        pass
+
+
 def timed_leg(torch, loop, W, K, barrier, use_graph=True, sampler_dev=None):
     """W untimed steps, then K steps in ONE CUDA graph (no host work between steps), CUDA events around the replay.
     Returns (elapsed ms of the K steps, per-step ms list, clocks or None, statistics of the timed steps)."""
     loop.reset(W + K)
+    _nvtx_push(torch, f"tzddpc warm-up: {W} closed-loop steps x {loop.S} scenarios")      # (NVTX: visible under nsys / ncu --nvtx)
     for t in range(W):
         loop.step(t)
+    _nvtx_pop(torch)
     barrier()
     graph = None
     if use_graph:
@@ -317,6 +333,7 @@ def timed_leg(torch, loop, W, K, barrier, use_graph=True, sampler_dev=None):
     sampler = ClockSampler(sampler_dev) if sampler_dev is not None else None
     ev = [torch.cuda.Event(enable_timing=True) for _ in range((1 if use_graph else K) + 1)]
     t0 = time.perf_counter()
+    _nvtx_push(torch, f"tzddpc timed: {K} closed-loop steps x {loop.S} scenarios")
     ev[0].record()
     if use_graph:
         graph.replay()
@@ -325,6 +342,7 @@ def timed_leg(torch, loop, W, K, barrier, use_graph=True, sampler_dev=None):
         for k in range(K):
             loop.step(W + k)
             ev[k + 1].record()
+    _nvtx_pop(torch)
     if sampler is not None:          # the work is asynchronous: sample the clocks while the GPU goes through it
         while not ev[-1].query():
             sampler.sample()
