@@ -1,0 +1,156 @@
+"""A third, NUMERIC route to the per-step program, independent of the coefficient-tensor machinery that both
+oracle/program.py and tzddpc_b200/program.py use: for given numbers (xbar0, e0, v) the statements of
+tzddpc/tzddpc.py:163-207 are executed literally on numeric zonotopes written out here (matrix-zonotope product, Minkowski
+sum, interval hull -- SURVEY.md App. A.1-A.4), and the result is compared with what the PRODUCT's compiled program says at
+the same point:
+
+  * Ze[1].Z (generators as a column multiset),
+  * the largest constraint violation (tightened state / input sets of :191-197 and the user's box constraints) -- i.e.
+    the feasible set of the canonical program is the feasible set of the literal statements,
+  * the objective value.
+
+No solver, no GPU.  (The oracle only supplies the identified model matrices here.)"""
+import numpy as np
+import pytest
+
+from tests import common
+from tzddpc_b200 import configs
+
+
+# ---- numeric zonotope arithmetic, written out ---------------------------------------------------
+def mz_times_z(C, Gm, Z):
+    """<C, {G_i}> * <c, G>  =  < C c,  [C G | G_1 c ... G_N c | G_1 G ... G_N G] >."""
+    c, G = Z[:, :1], Z[:, 1:]
+    cols = [C @ c, C @ G]
+    cols += [Gi @ c for Gi in Gm]
+    cols += [Gi @ G for Gi in Gm]
+    return np.hstack(cols)
+
+
+def plus(Z1, Z2):
+    return np.hstack([Z1[:, :1] + Z2[:, :1], Z1[:, 1:], Z2[:, 1:]])
+
+
+def radius(Z):
+    return np.abs(Z[:, 1:]).sum(axis=1)
+
+
+def literal(o, cfg, xbar0, e0, v):
+    """tzddpc/tzddpc.py:163-207 with numbers.  Returns (Ze list, xbar, worst violation of the tube constraints)."""
+    n, m, N = cfg.n, cfg.m, cfg.horizon
+    A, B = o.Mdata.center[:, :n], o.Mdata.center[:, n:]                                   # :163
+    K = o.theta.K
+    MK = (o.MdataK.center, list(o.MdataK.generators))
+    MD = (o.Mdelta.center, list(o.Mdelta.generators))
+    W = o.zonotopes.W.Z
+    xbar = [np.asarray(xbar0, dtype=np.float64)]
+    for k in range(N):                                                                    # :166-170
+        xbar.append(A @ xbar[k] + B @ v[k])
+    Ze = [np.hstack([np.asarray(e0, dtype=np.float64)[:, None], np.zeros((n, 1))])]       # :172
+    XU = [np.hstack([np.r_[xbar[k], v[k]][:, None], np.zeros((n + m, 1))]) for k in range(N)]      # :174
+    T1 = [mz_times_z(*MK, Ze[0])]                                                         # :175
+    Zn = [plus(mz_times_z(*MD, XU[k]), W) for k in range(N)]                              # :176
+    Xi, Ui = o.zonotopes.X.interval, o.zonotopes.U.interval
+    viol = -np.inf
+    for k in range(N):                                                                    # :178-209
+        T1.append(mz_times_z(*MK, T1[-1]))                                                # :181
+        noise = Zn[0]
+        for j in range(1, k):                                                             # :183-185
+            noise = plus(mz_times_z(*MK, noise), Zn[j])
+        Zk = Ze[-1]
+        c, r = Zk[:, 0] + xbar[k], radius(Zk)                                             # :191,194-195
+        viol = max(viol, (Xi.left_limit - (c - r)).max(), ((c + r) - Xi.right_limit).max())
+        KZ = K @ Zk                                                                       # :192,196-197
+        cu, ru = KZ[:, 0] + v[k], radius(KZ)
+        viol = max(viol, (Ui.left_limit - (cu - ru)).max(), ((cu + ru) - Ui.right_limit).max())
+        Ze.append(plus(T1[k], noise))                                                     # :205
+    return Ze, np.array(xbar), viol
+
+
+def stage_cost(cfg, xbar, N):
+    """The loss callbacks of the examples receive the FREE variable u (quirk Q7: the u terms sit at their floor 0) and the
+    rows xbar_0..xbar_{N-1} (tzddpc/tzddpc.py:160,222)."""
+    c = cfg.cost
+    total = 0.0
+    for k in range(N):
+        d = xbar[k] - (c["x_ref"] if c.get("x_ref") is not None else 0.0)
+        if c.get("Q") is not None:
+            total += float(d @ np.asarray(c["Q"]) @ d)
+        if c.get("w_abs") is not None:
+            total += float(np.abs(d) @ np.asarray(c["w_abs"]))
+    return total
+
+
+def box_violation(cfg, xbar, v):
+    b = cfg.box or {}
+    viol = -np.inf
+    if b.get("x_lo") is not None:
+        viol = max(viol, (np.asarray(b["x_lo"]) - xbar).max())
+    if b.get("x_hi") is not None:
+        viol = max(viol, (xbar - np.asarray(b["x_hi"])).max())
+    if b.get("v_lo") is not None:
+        viol = max(viol, (np.asarray(b["v_lo"]) - v).max())
+    if b.get("v_hi") is not None:
+        viol = max(viol, (v - np.asarray(b["v_hi"])).max())
+    return viol
+
+
+def program_at(prog, p, z):
+    """Worst row violation and objective of the CompiledProgram (include/tzddpc.h, TzProgramDesc) at parameters p, variables z."""
+    alpha = np.abs(prog.Bt @ p + prog.gam) if prog.na else np.zeros(0)
+    w = np.r_[1.0, p, alpha]
+    r = prog.R @ w
+    Az = prog.A @ z
+    viol = max((prog.l0 + r - Az).max(), (Az - prog.u0 - r).max())
+    if prog.Rchk.shape[0]:
+        viol = max(viol, (prog.Rchk @ w).max())
+    obj = 0.5 * z @ prog.P @ z + (prog.q0 + prog.Qp @ p) @ z + float(prog.wabs @ np.abs(Az - prog.kink0 - r)) + prog.cc @ w + p @ prog.CC2 @ p
+    return viol, float(obj)
+
+
+@pytest.mark.parametrize("name", ["double_integrator", "pulley", "fivedim"])
+def test_compiled_program_equals_the_literal_numeric_statements(name):
+    cfg = configs.CONFIGS[name]()
+    u, x = common.dataset(cfg)
+    o, _ = common.make_oracle(cfg, u, x)
+    prog = common.make_compiled(cfg, o)
+    assert prog.nz == prog.nv, "the shipped examples need no epigraph variable (z = v)"
+    n, m, N = cfg.n, cfg.m, cfg.horizon
+    rng = np.random.default_rng(17)
+    Xi, Ui = o.zonotopes.X.interval, o.zonotopes.U.interval
+    feas = infeas = 0
+    for trial in range(60):
+        spread = 0.45 if trial % 3 else 1.2                      # inside the state set / well outside it
+        mid, half = 0.5 * (Xi.left_limit + Xi.right_limit), 0.5 * (Xi.right_limit - Xi.left_limit)
+        xbar0 = mid + spread * half * rng.uniform(-1, 1, n)
+        e0 = 0.02 * rng.uniform(-1, 1, n)
+        v = (0.5 * (Ui.left_limit + Ui.right_limit) + spread * 0.5 * (Ui.right_limit - Ui.left_limit) * rng.uniform(-1, 1, (N, m)))
+        if trial % 4 == 0:                                       # a point that is feasible for sure: the optimum near X0
+            xbar0 = np.asarray(cfg.X0[0], dtype=np.float64) + 0.02 * rng.uniform(-1, 1, n)
+            e0 = 0.005 * rng.uniform(-1, 1, n)
+            r0 = o.solve_status(xbar0, e0)
+            if r0.status == 0:
+                v = np.asarray(r0.v, dtype=np.float64).reshape(N, m)
+        Ze, xbar, viol_tube = literal(o, cfg, xbar0, e0, v)
+        viol_lit = max(viol_tube, box_violation(cfg, xbar, v))
+        p = np.r_[xbar0, e0]
+        viol_prog, obj_prog = program_at(prog, p, v.ravel())
+        scale = max(1.0, np.abs(xbar).max(), np.abs(v).max())
+        assert abs(viol_prog - viol_lit) <= 1e-9 * scale, (name, trial, viol_prog, viol_lit)
+        obj_lit = stage_cost(cfg, xbar, N)
+        assert abs(obj_prog - obj_lit) <= 1e-9 * max(1.0, abs(obj_lit)), (name, trial, obj_prog, obj_lit)
+        # Ze[1].Z as the program's term table evaluates it, against the literal set: same centre, same generator multiset
+        om = np.r_[1.0, v.ravel(), p]
+        Zp = np.zeros((n, 1 + prog.g1))
+        for e in range(n * (1 + prog.g1)):
+            t0, t1 = prog.ze1_ptr[e], prog.ze1_ptr[e + 1]
+            Zp.flat[e] = float(prog.ze1_val[t0:t1] @ om[prog.ze1_idx[t0:t1]])
+        Zl = Ze[1]
+        np.testing.assert_allclose(Zp[:, 0], Zl[:, 0], rtol=1e-12, atol=1e-13)
+        keep_p = Zp[:, 1:][:, np.any(Zp[:, 1:] != 0, axis=0)]
+        keep_l = Zl[:, 1:][:, np.any(Zl[:, 1:] != 0, axis=0)]
+        assert keep_p.shape == keep_l.shape, (name, trial, keep_p.shape, keep_l.shape)
+        np.testing.assert_allclose(common.sort_columns(keep_p), common.sort_columns(keep_l), rtol=1e-12, atol=1e-13)
+        feas += viol_lit <= 1e-7 * scale                         # (an optimum sits ON its active constraints)
+        infeas += viol_lit > 1e-7 * scale
+    assert feas >= 5 and infeas >= 5, (feas, infeas)
