@@ -16,14 +16,16 @@
 //   * the code is kept COMPACT (row loops are real loops): a warp runs through the kernel once, so straight-line code is
 //     fetched from L2 by every warp -- the first, fully unrolled version spent 3-4 stall cycles per issued instruction
 //     waiting for instructions (profiles/r2_fast_v0_*: no_instruction);
-//   * the dense Ze[1].Z (88 % structural zeros, but dense by the reference's contract) is written once: the zero runs
-//     between the term table's entries as plain streaming stores -- odd warps before they solve, even warps behind, so
-//     that the stores of one half drain while the other half computes -- and the other entries from the table.
+//   * the dense Ze[1].Z (88 % structural zeros, but dense by the reference's contract) is written once: the zero rows as
+//     16-byte streaming stores DRIPPED between the stages of the solve (a flat row list in the program tables: one
+//     16-byte index load and one IMAD.WIDE + STG.128 per row), the other entries from the term table.
 //     (Measured and dropped: zero-filling the CTA's [entries x scenarios] block with cp.async.bulk.tensor stores of a
-//     shared-memory tile of zeros, UTMASTG.2D through a tensor map over the caller's array.  The entries that are not
-//     structurally zero can only be stored once the bulk group has completed, and with one tile per CTA nothing is left
-//     to overlap that wait with: 8 barrier-stall cycles per issued instruction, 0.0784 ms per step against 0.0705 with
-//     plain stores -- profiles/r2_fast_v1_tma_*.)
+//     shared-memory tile of zeros, UTMASTG.2D through a tensor map over the caller's array: the entries that are not
+//     structurally zero can only be stored once the bulk group has completed -- 0.0784 ms per step against 0.0705,
+//     profiles/r2_fast_v1_tma_*.  Odd warps storing the zeros before they solve and even warps behind: 0.0711 ms against
+//     0.0646 dripped.  A dedicated zero warp per CTA, 1D bulk copies per zero row: DESIGN.md section 5.1.)
+//   * all loads of the step (parameters, hints, and by cp.async the state x and the noise of the closed-loop update) are
+//     in flight before the first store is issued.
 // Scenarios the hint cannot decide (no hint yet, active set changed) are DEFERRED in units of 16-scenario output
 // tiles: the tile index goes to a list in the caller's warm-start scratch and step_kernel, launched right behind on
 // the same stream, solves exactly those tiles (ADMM + certificate).  Both kernels use the same closed-form function
