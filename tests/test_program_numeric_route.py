@@ -37,7 +37,7 @@ def radius(Z):
 
 def literal(o, cfg, xbar0, e0, v):
     """tzddpc/tzddpc.py:163-207 with numbers.  Returns (Ze list, xbar, worst violation of the tube constraints)."""
-    n, m, N = cfg.n, cfg.m, cfg.horizon
+    n, m, N = cfg.n, cfg.m, v.shape[0]
     A, B = o.Mdata.center[:, :n], o.Mdata.center[:, n:]                                   # :163
     K = o.theta.K
     MK = (o.MdataK.center, list(o.MdataK.generators))
@@ -108,14 +108,15 @@ def program_at(prog, p, z):
     return viol, float(obj)
 
 
-@pytest.mark.parametrize("name", ["double_integrator", "pulley", "fivedim"])
-def test_compiled_program_equals_the_literal_numeric_statements(name):
+@pytest.mark.parametrize("name,horizon", [("double_integrator", None), ("pulley", None), ("fivedim", None),
+                                          ("double_integrator", 1), ("double_integrator", 3)])
+def test_compiled_program_equals_the_literal_numeric_statements(name, horizon):
     cfg = configs.CONFIGS[name]()
     u, x = common.dataset(cfg)
-    o, _ = common.make_oracle(cfg, u, x)
-    prog = common.make_compiled(cfg, o)
-    assert prog.nz == prog.nv, "the shipped examples need no epigraph variable (z = v)"
-    n, m, N = cfg.n, cfg.m, cfg.horizon
+    o, _ = common.make_oracle(cfg, u, x, horizon=horizon)
+    prog = common.make_compiled(cfg, o, horizon=horizon)
+    assert prog.nz == prog.nv, "no epigraph variable (z = v) in these programs"
+    n, m, N = cfg.n, cfg.m, horizon or cfg.horizon
     rng = np.random.default_rng(17)
     Xi, Ui = o.zonotopes.X.interval, o.zonotopes.U.interval
     feas = infeas = 0
