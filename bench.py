@@ -414,7 +414,42 @@ def batch1_latency(tz, ops, torch, dev, steps_per_graph=12, replays=100):
         run()
     torch.cuda.synchronize(dev)
     us_eager = 1e6 * (time.perf_counter() - t0) / (4 * steps_per_graph)
-    return {"us_per_step": us, "us_per_step_eager_launches": us_eager, "scenarios": 1,
+    # ... and as ONE launch for the whole run (tz_closed_loop_run: the step loop inside the kernel)
+    us_fused, fused_equal = None, None
+    if hasattr(ops, "closed_loop_run"):
+        ref_x = x.clone()
+        status2 = torch.zeros_like(status)
+        cost2, v2, traj2, ze2 = torch.empty_like(cost), torch.empty_like(v), torch.empty_like(traj), torch.empty_like(ze1)
+
+        def run_fused():
+            x.copy_(x0); xbar.copy_(x0); e.zero_(); warm.zero_()
+            ops.closed_loop_run(h, steps_per_graph, x, xbar, e, noise, x0, At, Bt, status2, cost2, v2, traj2, ze2, None, None, None, warm,
+                                None, po)
+        run_fused()
+        torch.cuda.synchronize(dev)
+        fused_equal = bool(torch.equal(x, ref_x) and torch.equal(status2, status) and torch.equal(ze2, ze1))
+        g2 = torch.cuda.CUDAGraph()
+        gc.collect()
+        gc.disable()
+        try:
+            with torch.cuda.stream(side):
+                run_fused()
+            torch.cuda.synchronize(dev)
+            with torch.cuda.graph(g2, stream=side):
+                run_fused()
+        finally:
+            gc.enable()
+        for _ in range(3):
+            g2.replay()
+        torch.cuda.synchronize(dev)
+        a.record()
+        for _ in range(replays):
+            g2.replay()
+        b.record()
+        torch.cuda.synchronize(dev)
+        us_fused = 1e3 * a.elapsed_time(b) / (replays * steps_per_graph)
+    return {"us_per_step": us, "us_per_step_eager_launches": us_eager, "us_per_step_fused_run": us_fused,
+            "fused_run_equals_step_loop": fused_equal, "scenarios": 1,
             "workload": "double_integrator: n=2 m=1 T=100 horizon=2 (examples/1.double_integrator_sim.py), closed loop",
             "how": f"CUDA graph of the example's {steps_per_graph} closed-loop steps from X0, {replays} replays, CUDA events",
             "status_ok": bool((status == 0).all().item()), "kernel_bucket": prog.bucket}

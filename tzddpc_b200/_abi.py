@@ -45,7 +45,7 @@ EXPORTS = ["tz_version", "tz_last_error", "tz_device_cc", "tz_program_create", "
            "tz_program_tube_pattern", "tz_program_set_create", "tz_program_set_destroy", "tz_program_set_scenarios",
            "tz_solve_set", "tz_closed_loop_step_set", "tz_gain_synthesis", "tz_gain_robust_samples", "tz_gain_adversary", "tz_program_dims",
            "tz_program_set_dims", "tz_closed_loop_run_host", "tz_program_create_batch",
-           "tz_program_batch_get", "tz_program_batch_destroy"]
+           "tz_program_batch_get", "tz_program_batch_destroy", "tz_closed_loop_run"]
 
 
 def lib() -> C.CDLL:
@@ -82,6 +82,8 @@ def lib() -> C.CDLL:
     L.tz_solve.argtypes = [vp, C.POINTER(TzSolverOpts), i64] + [vp] * 10
     L.tz_closed_loop_step.restype = C.c_int
     L.tz_closed_loop_step.argtypes = [vp, C.POINTER(TzSolverOpts), i64] + [vp] * 17
+    L.tz_closed_loop_run.restype = C.c_int
+    L.tz_closed_loop_run.argtypes = [vp, C.POINTER(TzSolverOpts), i64, C.c_int32] + [vp] * 18
     L.tz_program_dims.restype = C.c_int
     L.tz_program_dims.argtypes = [vp, vp]
     L.tz_program_set_dims.restype = C.c_int

@@ -511,7 +511,7 @@ static SolverParams to_params(const TzSolverOpts* o) {
 
 // two scenarios per lane in the output phase need 16-byte aligned rows: S, ld even and aligned base pointers
 static int vec2_ok(const StepArgs& a) {
-  const void* ptrs[] = {a.x, a.xbar, a.e, a.noise, a.x_restart, a.cost, a.v, a.xbar_traj, a.ze1, a.u_out, a.xbar0, a.e0};
+  const void* ptrs[] = {a.x, a.xbar, a.e, a.noise, a.x_restart, a.cost, a.v, a.xbar_traj, a.ze1, a.u_out, a.xbar0, a.e0, a.x_hist};
   bool ok = (a.S % 2 == 0) && (a.ld % 2 == 0);
   for (const void* q : ptrs) ok = ok && ((reinterpret_cast<uintptr_t>(q) & 15u) == 0);
   ok = ok && ((reinterpret_cast<uintptr_t>(a.status) & 7u) == 0) && ((reinterpret_cast<uintptr_t>(a.iters) & 7u) == 0);
@@ -534,7 +534,7 @@ static int launch(const TzProgram* p, const TzSolverOpts* o, const StepArgs& a_i
              "bad solver options");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // (batches below kHotMinBatch scenarios stay on the ADMM kernel: one launch instead of two -- batch-1 latency)
-  if (p->bucket == 0 && sp.hot && sp.warm == 2 && a.warm != nullptr && a.q_in == nullptr && a.S >= kHotMinBatch) {
+  if (p->bucket == 0 && sp.hot && sp.warm == 2 && a.warm != nullptr && a.q_in == nullptr && a.S >= kHotMinBatch && a.nsteps <= 1) {
     // hint mode of the two-variable programs: fast_step_kernel (one thread per scenario, closed-form certificate) decides
     // every scenario whose hint still holds; the 16-scenario tiles it defers are listed in the warm-start scratch (rows
     // 2G: counters, 2G + 1: list) and solved by step_kernel right behind it
@@ -578,6 +578,24 @@ extern "C" int tz_closed_loop_step(const TzProgram* prog, const TzSolverOpts* op
   a.S = S; a.ld = S; a.xbar0 = xbar; a.e0 = e; a.x = x; a.xbar = xbar; a.e = e; a.noise = noise; a.x_restart = x_restart; a.A_true = A_true; a.B_true = B_true;
   a.cost = cost; a.v = v; a.xbar_traj = xbar_traj; a.ze1 = ze1; a.u_out = u_out; a.status = status; a.iters = iters;
   a.warm = warm; a.stats = stats;
+  return launch(prog, opts, a, stream);
+}
+
+// ---- fused run: K closed-loop steps in one launch (small batches: the launch per step is what the step costs) -----------
+extern "C" int tz_closed_loop_run(const TzProgram* prog, const TzSolverOpts* opts, int64_t S, int32_t nsteps, double* x, double* xbar,
+                                  double* e, const double* noise, const double* x_restart, const double* A_true,
+                                  const double* B_true, double* cost, double* v, double* xbar_traj, double* ze1, double* u_out,
+                                  double* x_hist, int32_t* status, int32_t* iters, double* warm, double* stats, void* stream) {
+  TZ_REQUIRE(prog != nullptr, "null program");
+  TZ_REQUIRE(nsteps >= 1, "nsteps must be >= 1");
+  TZ_REQUIRE(S == 0 || (x && xbar && e && A_true && B_true && status), "x, xbar, e, A_true, B_true, status are required");
+  TZ_REQUIRE(prog->bucket >= 0 && prog->bucket <= 3, "tz_closed_loop_run serves the register-bucket programs (up to 12 variables)");
+  StepArgs a{};
+  a.S = S; a.ld = S; a.xbar0 = xbar; a.e0 = e; a.x = x; a.xbar = xbar; a.e = e; a.noise = noise; a.x_restart = x_restart; a.A_true = A_true; a.B_true = B_true;
+  a.cost = cost; a.v = v; a.xbar_traj = xbar_traj; a.ze1 = ze1; a.u_out = u_out; a.status = status; a.iters = iters;
+  a.warm = warm; a.stats = stats;
+  a.nsteps = nsteps; a.x_hist = x_hist;
+  // (two-scenarios-per-lane output: vec2_ok wants an even batch, and then every per-step block starts 16-byte aligned too)
   return launch(prog, opts, a, stream);
 }
 

@@ -72,6 +72,10 @@ struct StepArgs {
   int32_t* defer;
   int32_t* defer_list;
   int list_mode;
+  // fused run (tz_closed_loop_run): nsteps > 1 closed-loop steps in one launch; noise and every per-step output then hold
+  // nsteps consecutive blocks (step-major), x_hist (nsteps x n x ld, or NULL) receives the state after every step
+  int nsteps;
+  double* x_hist;
 };
 
 // Shared-memory image of one CTA: the program (read-only after staging) and, per warp, the
@@ -327,6 +331,7 @@ __device__ __forceinline__ void output_phase(WarpBuf<BK>& wb, const double (*pre
         }
         vst(&wb.om[BK::OM_XP + i][sc0], acc);
         vst(a.x + (int64_t)i * LD + so, acc);                                  // x+ = A x + B u + w
+        if (a.x_hist != nullptr) vst(a.x_hist + (int64_t)i * LD + so, acc);
         vst(a.xbar + (int64_t)i * LD + so, xb1);
         vst(a.e + (int64_t)i * LD + so, en);
       }
@@ -736,8 +741,34 @@ __global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel(const QpProg<BK
     }
     return;
   }
-  run_program<BK>(smem_raw, gpg, ax, sp, a, (int64_t)blockIdx.x * BK::WPB, (int64_t)gridDim.x * BK::WPB, ntiles,
-                  blockIdx.x * BK::WPB);
+  if (a.nsteps <= 1) {
+    run_program<BK>(smem_raw, gpg, ax, sp, a, (int64_t)blockIdx.x * BK::WPB, (int64_t)gridDim.x * BK::WPB, ntiles,
+                    blockIdx.x * BK::WPB);
+    return;
+  }
+  // fused run: a warp keeps its tiles for all steps (scenarios are independent, so nothing has to cross warps); the
+  // state, the hints and the outputs of step k are ordinary global stores of this warp, read back by the same warp in
+  // step k + 1 behind a warp barrier.  The program is staged once.
+  const int64_t LD = a.ld;
+  const int64_t tube_rows = a.ze1 ? (sp.tube_packed ? ax.n_nz : ax.n * (1 + ax.g1)) : 0;
+#pragma unroll 1
+  for (int k = 0; k < a.nsteps; ++k) {
+    StepArgs ak = a;
+    if (ak.noise) ak.noise += (int64_t)k * ax.n * LD;
+    if (ak.cost) ak.cost += (int64_t)k * LD;
+    if (ak.v) ak.v += (int64_t)k * ax.nv * LD;
+    if (ak.xbar_traj) ak.xbar_traj += (int64_t)k * (ax.N + 1) * ax.n * LD;
+    if (ak.ze1) ak.ze1 += (int64_t)k * tube_rows * LD;
+    if (ak.u_out) ak.u_out += (int64_t)k * ax.m * LD;
+    ak.status += (int64_t)k * LD;
+    if (ak.iters) ak.iters += (int64_t)k * LD;
+    if (ak.stats) ak.stats += (int64_t)k * TZ_NSTATS;
+    if (ak.x_hist) ak.x_hist += (int64_t)k * ax.n * LD;
+    run_program<BK>(smem_raw, gpg, ax, sp, ak, (int64_t)blockIdx.x * BK::WPB, (int64_t)gridDim.x * BK::WPB, ntiles,
+                    blockIdx.x * BK::WPB + k, k == 0);
+    __threadfence_block();
+    __syncwarp();
+  }
 }
 
 // Data-set axis (BASELINE.json north_star: scenarios = noise realisations x initial states x DATA SETS): `nprog` programs
