@@ -423,8 +423,8 @@ def batch1_latency(tz, ops, torch, dev, steps_per_graph=12, replays=100):
 
         def run_fused():
             x.copy_(x0); xbar.copy_(x0); e.zero_(); warm.zero_()
-            ops.closed_loop_run(h, steps_per_graph, x, xbar, e, noise, x0, At, Bt, status2, cost2, v2, traj2, ze2, None, None, None, warm,
-                                None, po)
+            ops.closed_loop_run(h, steps_per_graph, x, xbar, e, noise, x0, At, Bt, status2, cost2, v2, traj2, ze2, None, None, None, None, None,
+                                warm, None, po)
         run_fused()
         torch.cuda.synchronize(dev)
         fused_equal = bool(torch.equal(x, ref_x) and torch.equal(status2, status) and torch.equal(ze2, ze1))

@@ -183,12 +183,12 @@ int tz_closed_loop_step(const TzProgram* prog, const TzSolverOpts* opts, int64_t
  * per step is what a step costs): exactly K consecutive tz_closed_loop_step calls, bit for bit.  Scenarios are
  * independent, so a warp keeps its scenarios for all steps.  `noise` and every per-step output hold K consecutive
  * blocks (step-major: noise K x n x S, cost K x S, v K x nv x S, xbar_traj K x (N+1)n x S, ze1 K x rows x S,
- * u_out K x m x S, status / iters K x S, stats K x TZ_NSTATS); x_hist (K x n x S or NULL) receives the state after
- * every step; x, xbar, e are updated in place.  Programs of the register buckets (up to 12 variables). */
+ * u_out K x m x S, status / iters K x S, stats K x TZ_NSTATS); x_hist, xbar_hist, e_hist (K x n x S each, or NULL) receive
+ * the state after every step; x, xbar, e are updated in place.  Programs of the register buckets (up to 12 variables). */
 int tz_closed_loop_run(const TzProgram* prog, const TzSolverOpts* opts, int64_t S, int32_t nsteps, double* x, double* xbar,
                        double* e, const double* noise, const double* x_restart, const double* A_true, const double* B_true,
-                       double* cost, double* v, double* xbar_traj, double* ze1, double* u_out, double* x_hist,
-                       int32_t* status, int32_t* iters, double* warm, double* stats, void* stream);
+                       double* cost, double* v, double* xbar_traj, double* ze1, double* u_out, double* x_hist, double* xbar_hist,
+                       double* e_hist, int32_t* status, int32_t* iters, double* warm, double* stats, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Data-set axis (BASELINE.json north_star: scenarios = noise realisations x initial states x data sets).

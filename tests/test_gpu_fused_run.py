@@ -40,11 +40,12 @@ def test_fused_run_equals_the_step_loop(cuda_lib, name, S, steps):
         st1, it1 = torch.zeros((steps, S), **i32), torch.zeros((steps, S), **i32)
         c1, v1, tr1 = torch.empty((steps, S), **f64), torch.empty((steps, nv, S), **f64), torch.empty((steps, nt, S), **f64)
         z1, u1, xh1 = torch.empty((steps, rows, S), **f64), torch.empty((steps, m, S), **f64), torch.empty((steps, n, S), **f64)
+        xbh1, eh1 = torch.empty((steps, n, S), **f64), torch.empty((steps, n, S), **f64)
         s1 = torch.zeros((steps, 8), **f64)
         w1 = torch.zeros((prog.warm_rows, S), **f64) if opts.warm_start else None
         for k in range(steps):
             ops.closed_loop_step(h, x1, xb1, e1, noise[k], xr, At, Bt, st1[k], c1[k], v1[k], tr1[k], z1[k], u1[k], it1[k], w1, s1[k], opts.pack())
-            xh1[k].copy_(x1)
+            xh1[k].copy_(x1); xbh1[k].copy_(xb1); eh1[k].copy_(e1)
         # ---- fused
         x2, xb2, e2 = torch.tensor(x0, **f64), torch.tensor(x0, **f64), torch.zeros((n, S), **f64)
         st2, it2 = torch.zeros((steps, S), **i32), torch.zeros((steps, S), **i32)
@@ -52,10 +53,11 @@ def test_fused_run_equals_the_step_loop(cuda_lib, name, S, steps):
         z2, u2, xh2 = torch.empty((steps, rows, S), **f64), torch.empty((steps, m, S), **f64), torch.empty((steps, n, S), **f64)
         s2 = torch.zeros((steps, 8), **f64)
         w2 = torch.zeros((prog.warm_rows, S), **f64) if opts.warm_start else None
-        ops.closed_loop_run(h, steps, x2, xb2, e2, noise, xr, At, Bt, st2, c2, v2, tr2, z2, u2, xh2, it2, w2, s2, opts.pack())
+        xbh2, eh2 = torch.empty((steps, n, S), **f64), torch.empty((steps, n, S), **f64)
+        ops.closed_loop_run(h, steps, x2, xb2, e2, noise, xr, At, Bt, st2, c2, v2, tr2, z2, u2, xh2, xbh2, eh2, it2, w2, s2, opts.pack())
         torch.cuda.synchronize()
         tag = f"{name} S={S} warm={opts.warm_start} packed={opts.tube_packed}"
-        for a, b, nm in ((st1, st2, "status"), (it1, it2, "iters"), (xh1, xh2, "x history"), (x1, x2, "x"), (xb1, xb2, "xbar"), (e1, e2, "e")):
+        for a, b, nm in ((st1, st2, "status"), (it1, it2, "iters"), (xh1, xh2, "x history"), (xbh1, xbh2, "xbar history"), (eh1, eh2, "e history"), (x1, x2, "x"), (xb1, xb2, "xbar"), (e1, e2, "e")):
             assert torch.equal(a, b), f"{tag}: {nm}"
         good = (st1 == 0)
         for a, b, nm in ((c1, c2, "cost"), (v1, v2, "v"), (tr1, tr2, "traj"), (z1, z2, "tube"), (u1, u2, "u")):
@@ -68,3 +70,30 @@ def test_fused_run_equals_the_step_loop(cuda_lib, name, S, steps):
         restarted += int((st1 == 2).sum().item())
     if name == "fivedim" and steps >= 70:
         assert restarted > 0, "expected infeasible steps (restarts) in the window"
+
+
+@pytest.mark.parametrize("name,S", [("pulley", 7), ("fivedim", 64), ("double_integrator", 1)])
+def test_simulate_uses_the_fused_run_for_small_batches_and_gets_the_same_answer(cuda_lib, name, S):
+    """TZDDPC.simulate below FUSED_RUN_MAX_BATCH scenarios is one tz_closed_loop_run launch; with the switch off it is the step
+    loop.  Every returned array is bit-equal."""
+    import tzddpc_b200 as tz
+    cfg = configs.CONFIGS[name]()
+    u, x = common.dataset(cfg)
+    o, K = common.make_oracle(cfg, u, x)
+    t = common.make_product(cfg, u, x, K)
+    steps = min(cfg.steps, 30)
+    rng = np.random.default_rng(12)
+    noise = common.noise_for(cfg, steps, S, rng)
+    x0 = np.tile(np.asarray(cfg.X0[0], dtype=np.float64), (S, 1))
+    assert t._fused_run_ok(S, steps)
+    for opts in (tz.SolverOptions(warm_start=2), tz.SolverOptions(tube_packed=1)):
+        fused = t.simulate(cfg.A, cfg.B, x0, noise, keep_tubes=True, restart=True, options=opts)
+        t.FUSED_RUN_MAX_BATCH = 0
+        try:
+            assert not t._fused_run_ok(S, steps)
+            loop = t.simulate(cfg.A, cfg.B, x0, noise, keep_tubes=True, restart=True, options=opts)
+        finally:
+            del t.FUSED_RUN_MAX_BATCH
+        for k in ("x", "xbar", "e", "u", "v", "cost", "status", "iters", "tubes"):
+            np.testing.assert_array_equal(fused[k], loop[k], err_msg=f"{name} {k}")
+        np.testing.assert_allclose(fused["stats"], loop["stats"], rtol=1e-12, atol=1e-12)

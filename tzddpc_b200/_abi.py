@@ -83,7 +83,7 @@ def lib() -> C.CDLL:
     L.tz_closed_loop_step.restype = C.c_int
     L.tz_closed_loop_step.argtypes = [vp, C.POINTER(TzSolverOpts), i64] + [vp] * 17
     L.tz_closed_loop_run.restype = C.c_int
-    L.tz_closed_loop_run.argtypes = [vp, C.POINTER(TzSolverOpts), i64, C.c_int32] + [vp] * 18
+    L.tz_closed_loop_run.argtypes = [vp, C.POINTER(TzSolverOpts), i64, C.c_int32] + [vp] * 20
     L.tz_program_dims.restype = C.c_int
     L.tz_program_dims.argtypes = [vp, vp]
     L.tz_program_set_dims.restype = C.c_int

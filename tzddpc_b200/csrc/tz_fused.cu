@@ -511,7 +511,7 @@ static SolverParams to_params(const TzSolverOpts* o) {
 
 // two scenarios per lane in the output phase need 16-byte aligned rows: S, ld even and aligned base pointers
 static int vec2_ok(const StepArgs& a) {
-  const void* ptrs[] = {a.x, a.xbar, a.e, a.noise, a.x_restart, a.cost, a.v, a.xbar_traj, a.ze1, a.u_out, a.xbar0, a.e0, a.x_hist};
+  const void* ptrs[] = {a.x, a.xbar, a.e, a.noise, a.x_restart, a.cost, a.v, a.xbar_traj, a.ze1, a.u_out, a.xbar0, a.e0, a.x_hist, a.xbar_hist, a.e_hist};
   bool ok = (a.S % 2 == 0) && (a.ld % 2 == 0);
   for (const void* q : ptrs) ok = ok && ((reinterpret_cast<uintptr_t>(q) & 15u) == 0);
   ok = ok && ((reinterpret_cast<uintptr_t>(a.status) & 7u) == 0) && ((reinterpret_cast<uintptr_t>(a.iters) & 7u) == 0);
@@ -585,7 +585,8 @@ extern "C" int tz_closed_loop_step(const TzProgram* prog, const TzSolverOpts* op
 extern "C" int tz_closed_loop_run(const TzProgram* prog, const TzSolverOpts* opts, int64_t S, int32_t nsteps, double* x, double* xbar,
                                   double* e, const double* noise, const double* x_restart, const double* A_true,
                                   const double* B_true, double* cost, double* v, double* xbar_traj, double* ze1, double* u_out,
-                                  double* x_hist, int32_t* status, int32_t* iters, double* warm, double* stats, void* stream) {
+                                  double* x_hist, double* xbar_hist, double* e_hist, int32_t* status, int32_t* iters, double* warm,
+                                  double* stats, void* stream) {
   TZ_REQUIRE(prog != nullptr, "null program");
   TZ_REQUIRE(nsteps >= 1, "nsteps must be >= 1");
   TZ_REQUIRE(S == 0 || (x && xbar && e && A_true && B_true && status), "x, xbar, e, A_true, B_true, status are required");
@@ -594,7 +595,7 @@ extern "C" int tz_closed_loop_run(const TzProgram* prog, const TzSolverOpts* opt
   a.S = S; a.ld = S; a.xbar0 = xbar; a.e0 = e; a.x = x; a.xbar = xbar; a.e = e; a.noise = noise; a.x_restart = x_restart; a.A_true = A_true; a.B_true = B_true;
   a.cost = cost; a.v = v; a.xbar_traj = xbar_traj; a.ze1 = ze1; a.u_out = u_out; a.status = status; a.iters = iters;
   a.warm = warm; a.stats = stats;
-  a.nsteps = nsteps; a.x_hist = x_hist;
+  a.nsteps = nsteps; a.x_hist = x_hist; a.xbar_hist = xbar_hist; a.e_hist = e_hist;
   // (two-scenarios-per-lane output: vec2_ok wants an even batch, and then every per-step block starts 16-byte aligned too)
   return launch(prog, opts, a, stream);
 }

@@ -76,6 +76,8 @@ struct StepArgs {
   // nsteps consecutive blocks (step-major), x_hist (nsteps x n x ld, or NULL) receives the state after every step
   int nsteps;
   double* x_hist;
+  double* xbar_hist;
+  double* e_hist;
 };
 
 // Shared-memory image of one CTA: the program (read-only after staging) and, per warp, the
@@ -332,6 +334,8 @@ __device__ __forceinline__ void output_phase(WarpBuf<BK>& wb, const double (*pre
         vst(&wb.om[BK::OM_XP + i][sc0], acc);
         vst(a.x + (int64_t)i * LD + so, acc);                                  // x+ = A x + B u + w
         if (a.x_hist != nullptr) vst(a.x_hist + (int64_t)i * LD + so, acc);
+        if (a.xbar_hist != nullptr) vst(a.xbar_hist + (int64_t)i * LD + so, xb1);
+        if (a.e_hist != nullptr) vst(a.e_hist + (int64_t)i * LD + so, en);
         vst(a.xbar + (int64_t)i * LD + so, xb1);
         vst(a.e + (int64_t)i * LD + so, en);
       }
@@ -764,6 +768,8 @@ __global__ void __launch_bounds__(BK::TPB, BK::MINB) step_kernel(const QpProg<BK
     if (ak.iters) ak.iters += (int64_t)k * LD;
     if (ak.stats) ak.stats += (int64_t)k * TZ_NSTATS;
     if (ak.x_hist) ak.x_hist += (int64_t)k * ax.n * LD;
+    if (ak.xbar_hist) ak.xbar_hist += (int64_t)k * ax.n * LD;
+    if (ak.e_hist) ak.e_hist += (int64_t)k * ax.n * LD;
     run_program<BK>(smem_raw, gpg, ax, sp, ak, (int64_t)blockIdx.x * BK::WPB, (int64_t)gridDim.x * BK::WPB, ntiles,
                     blockIdx.x * BK::WPB + k, k == 0);
     __threadfence_block();

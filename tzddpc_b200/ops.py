@@ -148,15 +148,16 @@ def closed_loop_step(prog: int, x: Tensor, xbar: Tensor, e: Tensor, noise: Tenso
 
 
 @torch.library.custom_op("tzddpc::closed_loop_run",
-                         mutates_args=("x", "xbar", "e", "cost", "v", "traj", "ze1", "u", "x_hist", "status", "iters", "warm", "stats"),
+                         mutates_args=("x", "xbar", "e", "cost", "v", "traj", "ze1", "u", "x_hist", "xbar_hist", "e_hist", "status", "iters", "warm",
+                                       "stats"),
                          device_types="cuda")
 def closed_loop_run(prog: int, steps: int, x: Tensor, xbar: Tensor, e: Tensor, noise: Tensor, x_restart: Optional[Tensor],
                     A_true: Tensor, B_true: Tensor, status: Tensor, cost: Optional[Tensor], v: Optional[Tensor], traj: Optional[Tensor],
-                    ze1: Optional[Tensor], u: Optional[Tensor], x_hist: Optional[Tensor], iters: Optional[Tensor], warm: Optional[Tensor],
-                    stats: Optional[Tensor], opts: List[float]) -> None:
+                    ze1: Optional[Tensor], u: Optional[Tensor], x_hist: Optional[Tensor], xbar_hist: Optional[Tensor], e_hist: Optional[Tensor],
+                    iters: Optional[Tensor], warm: Optional[Tensor], stats: Optional[Tensor], opts: List[float]) -> None:
     """`steps` fused closed-loop steps in ONE launch (tz_closed_loop_run): the loop of examples/2.pulley_sim.py:81-96 for a small
     batch.  noise: (steps, n, S); per-step outputs are step-major: status / iters / cost (steps, S), v (steps, nv, S),
-    traj (steps, (N+1)n, S), ze1 (steps, rows, S), u (steps, m, S), x_hist (steps, n, S), stats (steps, TZ_NSTATS)."""
+    traj (steps, (N+1)n, S), ze1 (steps, rows, S), u (steps, m, S), x_hist / xbar_hist / e_hist (steps, n, S), stats (steps, TZ_NSTATS)."""
     _chk(x), _chk(xbar), _chk(e), _chk(noise), _chk(A_true), _chk(B_true), _chk(status, torch.int32)
     S = x.shape[1]
     o = _opts(opts)
@@ -172,7 +173,8 @@ def closed_loop_run(prog: int, steps: int, x: Tensor, xbar: Tensor, e: Tensor, n
             assert tuple(t.shape) == shape, f"{what}: expected {shape}, got {tuple(t.shape)}"
     chk(cost, (steps, S), "cost"), chk(iters, (steps, S), "iters", torch.int32), chk(v, (steps, nv, S), "v")
     chk(traj, (steps, nt, S), "traj"), chk(ze1, (steps, n_nz if o.tube_packed else nent, S), "ze1"), chk(u, (steps, m, S), "u")
-    chk(x_hist, (steps, n, S), "x_hist"), chk(x_restart, (n, S), "x_restart")
+    chk(x_hist, (steps, n, S), "x_hist"), chk(xbar_hist, (steps, n, S), "xbar_hist"), chk(e_hist, (steps, n, S), "e_hist")
+    chk(x_restart, (n, S), "x_restart")
     if stats is not None:
         _chk(stats)
         assert stats.numel() >= steps * _abi.TZ_NSTATS, "stats: needs steps x TZ_NSTATS doubles"
@@ -180,7 +182,8 @@ def closed_loop_run(prog: int, steps: int, x: Tensor, xbar: Tensor, e: Tensor, n
     with torch.cuda.device(x.device):
         rc = _abi.lib().tz_closed_loop_run(C.c_void_p(prog), C.byref(o), S, int(steps), _ptr(x), _ptr(xbar), _ptr(e), _ptr(noise),
                                            _ptr(x_restart), _ptr(A_true), _ptr(B_true), _ptr(cost), _ptr(v), _ptr(traj), _ptr(ze1),
-                                           _ptr(u), _ptr(x_hist), _ptr(status), _ptr(iters), _ptr(warm), _ptr(stats), _stream(x))
+                                           _ptr(u), _ptr(x_hist), _ptr(xbar_hist), _ptr(e_hist), _ptr(status), _ptr(iters), _ptr(warm),
+                                           _ptr(stats), _stream(x))
     _abi.check(rc, "tz_closed_loop_run")
 
 

@@ -326,6 +326,14 @@ class TZDDPC(object):
         return float(cost[0]), v[0], xbar[0], tube
 
     # ---- batched closed loop (examples/2.pulley_sim.py:62-103, one scenario per column) --------
+    #: batches below this many scenarios run `simulate` as one fused launch (csrc/tz_fused.cu: kHotMinBatch -- from there on
+    #: the two-kernel hot path is faster than the step loop inside step_kernel)
+    FUSED_RUN_MAX_BATCH = 256
+
+    def _fused_run_ok(self, S: int, steps: int) -> bool:
+        return (type(self)._step_op is TZDDPC._step_op and steps >= 2 and S < self.FUSED_RUN_MAX_BATCH
+                and str(self._program.bucket)[:2] in ("B0", "B1", "B2", "B3") and hasattr(ops, "closed_loop_run"))
+
     def simulate(self, A_true: np.ndarray, B_true: np.ndarray, x0: np.ndarray, noise=None, keep_tubes: bool = False,
                  options: Optional[SolverOptions] = None, restart: bool = False, steps: Optional[int] = None,
                  seed: Optional[int] = None, vertex_noise: bool = False, scenario_offset: int = 0):
@@ -371,10 +379,15 @@ class TZDDPC(object):
         xs[0], xbars[0], es[0] = x, xbar, e
         xr = x.clone() if restart else None
         h = self._program.handle.value
-        for t in range(steps):
-            self._step_op(h, x, xbar, e, w[t].contiguous(), xr, At, Bt, stat[t], costs[t], vs[t], None,
-                                 tubes[t] if keep_tubes else None, us[t], iters[t], warm, stats[t], o.pack())
-            xs[t + 1], xbars[t + 1], es[t + 1] = x, xbar, e
+        if isinstance(self, TZDDPC) and self._fused_run_ok(S, steps):      # (TZDDPCEnsemble borrows this method: step loop)
+            # small batch: the whole run in ONE launch (tz_closed_loop_run; bit-equal to the step loop below)
+            ops.closed_loop_run(h, steps, x, xbar, e, w.contiguous(), xr, At, Bt, stat, costs, vs, None, tubes if keep_tubes else None,
+                                us, xs[1:], xbars[1:], es[1:], iters, warm, stats, o.pack())
+        else:
+            for t in range(steps):
+                self._step_op(h, x, xbar, e, w[t].contiguous(), xr, At, Bt, stat[t], costs[t], vs[t], None,
+                              tubes[t] if keep_tubes else None, us[t], iters[t], warm, stats[t], o.pack())
+                xs[t + 1], xbars[t + 1], es[t + 1] = x, xbar, e
         out = {"x": xs.permute(0, 2, 1).cpu().numpy(), "xbar": xbars.permute(0, 2, 1).cpu().numpy(),
                "e": es.permute(0, 2, 1).cpu().numpy(), "u": us.permute(0, 2, 1).cpu().numpy(),
                "v": vs.permute(0, 2, 1).cpu().numpy(), "cost": costs.cpu().numpy(), "status": stat.cpu().numpy(),
