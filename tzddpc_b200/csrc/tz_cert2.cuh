@@ -45,31 +45,6 @@ __device__ __forceinline__ void row_LA(const QpProg<BK>& pg, int i, const double
   }
 }
 
-// (L, A) of NR rows at once: 2 NR independent fma chains in flight (a thread of fast_step_kernel runs through the program
-// once, at ~14 warps per SM: the dependent-issue latency of a single chain is what bounds it).  Same arithmetic per row.
-template <class BK, int NR>
-__device__ __forceinline__ void row_LAn(const QpProg<BK>& pg, const int (&rows)[NR], const double (&w)[2 * BK::NCOL2],
-                                        double (&L)[NR], double (&A)[NR]) {
-  const double2* Rr[NR];
-#pragma unroll
-  for (int q = 0; q < NR; ++q) {
-    Rr[q] = reinterpret_cast<const double2*>(&pg.R[rows[q]][0]);
-    L[q] = 0.0;
-    A[q] = 0.0;
-  }
-#pragma unroll
-  for (int j = 0; j < BK::NCOL2; ++j) {
-#pragma unroll
-    for (int q = 0; q < NR; ++q) {
-      const double2 c2 = Rr[q][j];
-      if (2 * j >= 1 && 2 * j <= BK::NPAR) L[q] = fma(c2.x, w[2 * j], L[q]);
-      else A[q] = fma(c2.x, w[2 * j], A[q]);
-      if (2 * j + 1 >= 1 && 2 * j + 1 <= BK::NPAR) L[q] = fma(c2.y, w[2 * j + 1], L[q]);
-      else A[q] = fma(c2.y, w[2 * j + 1], A[q]);
-    }
-  }
-}
-
 // r_i(p) = E_i (R_i . w): the arithmetic every kernel of this library uses for the parametric shift of a row
 template <class BK>
 __device__ __forceinline__ double row_shift(const QpProg<BK>& pg, int i, const double (&w)[2 * BK::NCOL2]) {
