@@ -67,6 +67,60 @@ def literal(o, cfg, xbar0, e0, v):
     return Ze, np.array(xbar), viol
 
 
+def literal_simplified(o, cfg, xbar0, e0, v, k0):
+    """tzddpc/tzddpc.py:274-327 (build_problem_simplified) with numbers."""
+    n, m, N = cfg.n, cfg.m, v.shape[0]
+    A, B = o.Mdata.center[:, :n], o.Mdata.center[:, n:]                                   # :274
+    K = o.theta.K
+    MK = (o.MdataK.center, list(o.MdataK.generators))
+    MD = (o.Mdelta.center, list(o.Mdelta.generators))
+    W = o.zonotopes.W.Z
+    xbar = [np.asarray(xbar0, dtype=np.float64)]
+    for k in range(N):                                                                    # :277-281
+        xbar.append(A @ xbar[k] + B @ v[k])
+    Ze = [np.hstack([np.asarray(e0, dtype=np.float64)[:, None], np.zeros((n, 1))])]       # :283
+    XU = [np.hstack([np.r_[xbar[k], v[k]][:, None], np.zeros((n + m, 1))]) for k in range(N)]      # :285
+    T1 = [mz_times_z(*MK, Ze[0])]                                                         # :286
+    Zn = [plus(mz_times_z(*MD, XU[k]), W) for k in range(N)]                              # :287
+    T2 = []
+    for k in range(N):                                                                    # :291-302
+        T1.append(T1[-1] if k > k0 else mz_times_z(*MK, T1[-1]))
+        start = max(0, k - k0)
+        noise = Zn[start]
+        for j in range(1, min(k, k0)):
+            noise = plus(mz_times_z(*MK, noise), Zn[start + j])
+        T2.append(noise)
+    Xi, Ui = o.zonotopes.X.interval, o.zonotopes.U.interval
+    viol = -np.inf
+    for k in range(N):                                                                    # :305-323
+        Zk = Ze[-1]
+        c, r = Zk[:, 0] + xbar[k], radius(Zk)
+        viol = max(viol, (Xi.left_limit - (c - r)).max(), ((c + r) - Xi.right_limit).max())
+        KZ = K @ Zk
+        cu, ru = KZ[:, 0] + v[k], radius(KZ)
+        viol = max(viol, (Ui.left_limit - (cu - ru)).max(), ((cu + ru) - Ui.right_limit).max())
+        Ze.append(plus(T1[k], T2[k]))
+    return Ze, np.array(xbar), viol
+
+
+def stage_cost_simplified(cfg, xbar, v):
+    """build_loss(v, xbar[1:]) (tzddpc/tzddpc.py:336): the x terms over xbar_1..xbar_N, the u terms over v."""
+    c = cfg.cost
+    total = 0.0
+    for k in range(v.shape[0]):
+        d = xbar[k + 1] - (c["x_ref"] if c.get("x_ref") is not None else 0.0)
+        if c.get("Q") is not None:
+            total += float(d @ np.asarray(c["Q"]) @ d)
+        if c.get("w_abs") is not None:
+            total += float(np.abs(d) @ np.asarray(c["w_abs"]))
+        du = v[k] - (c["u_ref"] if c.get("u_ref") is not None else 0.0)
+        if c.get("R") is not None:
+            total += float(du @ np.asarray(c["R"]) @ du)
+        if c.get("r_abs") is not None:
+            total += float(np.abs(du) @ np.asarray(c["r_abs"]))
+    return total
+
+
 def stage_cost(cfg, xbar, N):
     """The loss callbacks of the examples receive the FREE variable u (quirk Q7: the u terms sit at their floor 0) and the
     rows xbar_0..xbar_{N-1} (tzddpc/tzddpc.py:160,222)."""
@@ -153,5 +207,40 @@ def test_compiled_program_equals_the_literal_numeric_statements(name, horizon):
         assert keep_p.shape == keep_l.shape, (name, trial, keep_p.shape, keep_l.shape)
         np.testing.assert_allclose(common.sort_columns(keep_p), common.sort_columns(keep_l), rtol=1e-12, atol=1e-13)
         feas += viol_lit <= 1e-7 * scale                         # (an optimum sits ON its active constraints)
+        infeas += viol_lit > 1e-7 * scale
+    assert feas >= 5 and infeas >= 5, (feas, infeas)
+
+
+@pytest.mark.parametrize("horizon,k0", [(2, 1), (3, 1), (3, 2)])
+def test_simplified_program_equals_the_literal_numeric_statements(horizon, k0):
+    """build_problem_simplified (tzddpc/tzddpc.py:243-355; the `-m stzddpc` rows of the complexity sweep) on the sweep system,
+    for the (horizon, k0) whose canonical program needs no epigraph variable."""
+    cfg = configs.sweep()
+    u, x = common.dataset(cfg)
+    o, _ = common.make_oracle(cfg, u, x, horizon=horizon, k0=k0)
+    prog = common.make_compiled(cfg, o, horizon=horizon, k0=k0)
+    assert prog.nz == prog.nv
+    n, m, N = cfg.n, cfg.m, horizon
+    rng = np.random.default_rng(23)
+    Xi, Ui = o.zonotopes.X.interval, o.zonotopes.U.interval
+    feas = infeas = 0
+    for trial in range(60):
+        spread = 0.4 if trial % 3 else 2.5                       # inside the state set / well outside it
+        mid, half = 0.5 * (Xi.left_limit + Xi.right_limit), 0.5 * (Xi.right_limit - Xi.left_limit)
+        xbar0 = mid + spread * half * rng.uniform(-1, 1, n)
+        e0 = 0.01 * rng.uniform(-1, 1, n)
+        v = 0.5 * (Ui.left_limit + Ui.right_limit) + spread * 0.3 * (Ui.right_limit - Ui.left_limit) * rng.uniform(-1, 1, (N, m))
+        if trial % 4 == 0:
+            r0 = o.solve_status(xbar0, e0)
+            if r0.status == 0:
+                v = np.asarray(r0.v, dtype=np.float64).reshape(N, m)
+        Ze, xbar, viol_lit = literal_simplified(o, cfg, xbar0, e0, v, k0)
+        p = np.r_[xbar0, e0]
+        viol_prog, obj_prog = program_at(prog, p, v.ravel())
+        scale = max(1.0, np.abs(xbar).max(), np.abs(v).max())
+        assert abs(viol_prog - viol_lit) <= 1e-9 * scale, (trial, viol_prog, viol_lit)
+        obj_lit = stage_cost_simplified(cfg, xbar, v)
+        assert abs(obj_prog - obj_lit) <= 1e-9 * max(1.0, abs(obj_lit)), (trial, obj_prog, obj_lit)
+        feas += viol_lit <= 1e-7 * scale
         infeas += viol_lit > 1e-7 * scale
     assert feas >= 5 and infeas >= 5, (feas, infeas)
