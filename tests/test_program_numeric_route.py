@@ -244,3 +244,61 @@ def test_simplified_program_equals_the_literal_numeric_statements(horizon, k0):
         feas += viol_lit <= 1e-7 * scale
         infeas += viol_lit > 1e-7 * scale
     assert feas >= 5 and infeas >= 5, (feas, infeas)
+
+
+@pytest.mark.parametrize("horizon,k0", [(4, None), (5, None), (4, 1), (6, 1)])
+def test_programs_with_epigraph_variables_have_the_literal_feasible_set(horizon, k0):
+    """Longer horizons put several |.| atoms into one tightened row and the canonical program carries epigraph variables
+    s (z = [v; s]).  For fixed (p, v) the program is feasible iff some s makes every row hold -- an LP in s, solved here
+    with HiGHS -- and that must be exactly when the literal numeric statements hold."""
+    from scipy.optimize import linprog
+    cfg = configs.sweep()
+    u, x = common.dataset(cfg)
+    o, _ = common.make_oracle(cfg, u, x, horizon=horizon, k0=k0)
+    prog = common.make_compiled(cfg, o, horizon=horizon, k0=k0)
+    ns = prog.nz - prog.nv
+    assert ns > 0
+    n, m, N = cfg.n, cfg.m, horizon
+    rng = np.random.default_rng(31)
+    Xi, Ui = o.zonotopes.X.interval, o.zonotopes.U.interval
+    feas = infeas = 0
+    for trial in range(40):
+        spread = 0.35 if trial % 2 else 1.6
+        mid, half = 0.5 * (Xi.left_limit + Xi.right_limit), 0.5 * (Xi.right_limit - Xi.left_limit)
+        xbar0 = mid + spread * half * rng.uniform(-1, 1, n)
+        e0 = 0.01 * rng.uniform(-1, 1, n)
+        v = 0.5 * (Ui.left_limit + Ui.right_limit) + spread * 0.25 * (Ui.right_limit - Ui.left_limit) * rng.uniform(-1, 1, (N, m))
+        if trial % 4 == 1:
+            r0 = o.solve_status(xbar0, e0)
+            if r0.status == 0:
+                v = np.asarray(r0.v, dtype=np.float64).reshape(N, m)
+        if k0 is None:
+            _, xbar, viol_lit = literal(o, cfg, xbar0, e0, v)
+        else:
+            _, xbar, viol_lit = literal_simplified(o, cfg, xbar0, e0, v, k0)
+        scale = max(1.0, np.abs(xbar).max(), np.abs(v).max())
+        if abs(viol_lit) < 1e-6 * scale:
+            continue                                            # on the boundary: the verdict is a matter of rounding
+        # min_t  s.t.  l - A z <= t,  A z - u <= t  over (s, t) with v fixed
+        p = np.r_[xbar0, e0]
+        alpha = np.abs(prog.Bt @ p + prog.gam) if prog.na else np.zeros(0)
+        w = np.r_[1.0, p, alpha]
+        r = prog.R @ w
+        Av, As = prog.A[:, :prog.nv], prog.A[:, prog.nv:]
+        base = Av @ v.ravel()
+        lo, hi = prog.l0 + r, prog.u0 + r
+        rows, rhs = [], []
+        for i in range(prog.nc):
+            if np.isfinite(hi[i]):
+                rows.append(np.r_[As[i], -1.0]); rhs.append(hi[i] - base[i])
+            if np.isfinite(lo[i]):
+                rows.append(np.r_[-As[i], -1.0]); rhs.append(base[i] - lo[i])
+        res = linprog(np.r_[np.zeros(ns), 1.0], A_ub=np.array(rows), b_ub=np.array(rhs), bounds=[(None, None)] * (ns + 1), method="highs")
+        assert res.status == 0, res.message
+        t_min = res.x[-1]
+        if prog.Rchk.shape[0]:
+            t_min = max(t_min, float((prog.Rchk @ w).max()))
+        assert (t_min <= 1e-9 * scale) == (viol_lit <= 0), (horizon, k0, trial, t_min, viol_lit)
+        feas += viol_lit <= 0
+        infeas += viol_lit > 0
+    assert feas >= 3 and infeas >= 3, (feas, infeas)
